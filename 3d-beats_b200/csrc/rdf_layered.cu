@@ -1,0 +1,154 @@
+// Stacked ("layered") forests: replaces LayeredDecisionForest.run (reference src/decision_tree.py:233-264) and
+// make_composite_labels_image (src/cuda/tree_eval.cu:214-248).
+#include <string.h>
+
+#include "rdf_traverse.cuh"
+
+// ---- stand-alone composite (API parity with DecisionTreeEvaluator.make_composite_labels_image) -----------------
+__global__ void __launch_bounds__(256) rdf_composite_kernel(const uint16_t* const* __restrict__ label_images, int L, int w,
+                                                            int h, const int2* __restrict__ cond,
+                                                            uint16_t* __restrict__ composite) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w * h) return;
+    int off = 0;
+    for (int k = 0; k < L; k++) {
+        const unsigned l = __ldg(label_images[k] + i);
+        if (l == 0u || l == RDF_NO_PIXEL) return;                  // composite left untouched (tree_eval.cu:235)
+        const int2 tv = __ldg(cond + off + (int)l - 1);
+        if (tv.x == 0) {
+            composite[i] = (uint16_t)tv.y;
+            return;
+        }
+        off = tv.y;
+    }
+    // the reference asserts here (tree_eval.cu:246-247); a malformed table simply leaves the pixel untouched
+}
+
+extern "C" int rdf_composite(const uint16_t* const* label_images_dev, int num_label_images, int dim_x, int dim_y,
+                             const int32_t* conditions_dev, uint16_t* composite_dev, void* stream) {
+    RDF_REQUIRE(label_images_dev && conditions_dev && composite_dev, "rdf_composite: NULL argument");
+    RDF_REQUIRE(num_label_images >= 1 && dim_x > 0 && dim_y > 0, "rdf_composite: bad shape");
+    const int n = dim_x * dim_y;
+    rdf_composite_kernel<<<(n + 255) / 256, 256, 0, rdf_stream(stream)>>>(label_images_dev, num_label_images, dim_x, dim_y,
+                                                                           reinterpret_cast<const int2*>(conditions_dev),
+                                                                           composite_dev);
+    RDF_LAUNCH_CHECK("rdf_composite_kernel");
+    return RDF_OK;
+}
+
+// ---- fused layered run ---------------------------------------------------------------------------------------
+// One thread per labels pixel evaluates every layer in turn; the gate of layer i (label of layer filter_model[i])
+// is read from a register, the composite walk happens on the same registers, and every output pixel is written
+// exactly once (65535 where the reference's pre-fill would survive).  No fills, no intermediate global reads.
+struct rdf_layered_params {
+    rdf_forest_view fv[RDF_MAX_LAYERS];
+    int filter_model[RDF_MAX_LAYERS];
+    int filter_class[RDF_MAX_LAYERS];
+    uint16_t* layer_labels[RDF_MAX_LAYERS];
+    const uint16_t* depth;
+    const int2* cond;
+    uint16_t* composite;
+    int L, n_cond;
+    int W, H, w, h, r;
+    int tiles_x;
+    float scale;
+};
+
+template <int WARP_W>
+__global__ void __launch_bounds__(256) rdf_layered_kernel(const __grid_constant__ rdf_layered_params p) {
+    constexpr int WARP_H = 32 / WARP_W;
+    constexpr int WARPS_X = 32 / WARP_W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile_y = blockIdx.x / p.tiles_x, tile_x = blockIdx.x - tile_y * p.tiles_x;
+    const int x = tile_x * 32 + (warp % WARPS_X) * WARP_W + (lane % WARP_W);
+    const int y = tile_y * 8 + (warp / WARPS_X) * WARP_H + (lane / WARP_W);
+    if (x >= p.w || y >= p.h) return;
+    const size_t li = (size_t)y * p.w + x;
+    const int X = x * p.r, Y = y * p.r;
+    const unsigned d = __ldg(p.depth + (size_t)Y * p.W + X);
+    const bool valid = !(d == 0u || d == RDF_NO_PIXEL);
+    const float df = (float)d;
+
+    // per-layer labels of this pixel, 16 bits each, packed so the layer loop can stay rolled (RDF_MAX_LAYERS == 8)
+    unsigned long long lab_lo = ~0ull, lab_hi = ~0ull;              // all 65535 = the reference's pre-fill
+    auto get_lab = [&](int i) -> unsigned {
+        const unsigned long long wd = i < 4 ? lab_lo : lab_hi;
+        return (unsigned)(wd >> (16 * (i & 3))) & 0xffffu;
+    };
+    auto set_lab = [&](int i, unsigned v) {
+        const unsigned long long m = 0xffffull << (16 * (i & 3));
+        const unsigned long long b = (unsigned long long)(v & 0xffffu) << (16 * (i & 3));
+        if (i < 4) lab_lo = (lab_lo & ~m) | b; else lab_hi = (lab_hi & ~m) | b;
+    };
+
+#pragma unroll 1
+    for (int i = 0; i < p.L; i++) {
+        bool run = valid;
+        const int fm = p.filter_model[i];
+        // layers not yet evaluated still hold the 65535 pre-fill, as in the reference
+        if (fm >= 0 && p.filter_class[i] != -1) run = run && ((int)get_lab(fm) == p.filter_class[i]);
+        unsigned l = RDF_NO_PIXEL;
+        if (run) {
+            l = (unsigned)rdf_eval_pixel(p.fv[i], p.depth, p.W, p.H, X, Y, df, p.scale, nullptr);
+            set_lab(i, l);
+        }
+        p.layer_labels[i][li] = (uint16_t)l;
+    }
+
+    // composite walk (tree_eval.cu:232-244) on registers
+    unsigned comp = RDF_NO_PIXEL;
+    int off = 0;
+#pragma unroll 1
+    for (int i = 0; i < p.L; i++) {
+        const unsigned l = get_lab(i);
+        if (l == 0u || l == RDF_NO_PIXEL) break;
+        const int idx = off + (int)l - 1;
+        if (idx < 0 || idx >= p.n_cond) break;                     // malformed table: leave 65535
+        const int2 tv = __ldg(p.cond + idx);
+        if (tv.x == 0) {
+            comp = (unsigned)tv.y & 0xffffu;
+            break;
+        }
+        off = tv.y;
+    }
+    p.composite[li] = (uint16_t)comp;
+}
+
+extern "C" int rdf_layered_run(const rdf_forest_t* const* forests, int num_layers, const int* filter_model,
+                               const int* filter_class, const uint16_t* depth_dev, int dim_x, int dim_y,
+                               uint16_t* const* labels_per_layer, const int32_t* conditions_dev, int n_cond,
+                               uint16_t* composite_dev, int labels_reduce, float scale, void* stream) {
+    RDF_REQUIRE(forests && filter_model && filter_class && depth_dev && labels_per_layer && conditions_dev && composite_dev,
+                "rdf_layered_run: NULL argument");
+    RDF_REQUIRE(num_layers >= 1 && num_layers <= RDF_MAX_LAYERS, "rdf_layered_run: num_layers=%d outside 1..%d", num_layers,
+                RDF_MAX_LAYERS);
+    RDF_REQUIRE(dim_x > 0 && dim_y > 0 && labels_reduce >= 1 && n_cond >= 1, "rdf_layered_run: bad shape");
+    rdf_layered_params p;
+    memset(&p, 0, sizeof(p));
+    for (int i = 0; i < num_layers; i++) {
+        RDF_REQUIRE(forests[i] != nullptr && labels_per_layer[i] != nullptr, "rdf_layered_run: layer %d is NULL", i);
+        if (forests[i]->T > RDF_FAST_MAX_TREES) {
+            rdf_set_error("rdf_layered_run: layer %d has %d trees (max %d in the fused path)", i, forests[i]->T, RDF_FAST_MAX_TREES);
+            return RDF_ERR_UNSUPPORTED;
+        }
+        RDF_REQUIRE(filter_model[i] < num_layers, "rdf_layered_run: filter_model[%d]=%d out of range", i, filter_model[i]);
+        p.fv[i] = rdf_view(forests[i]);
+        p.filter_model[i] = filter_model[i];
+        p.filter_class[i] = filter_class[i];
+        p.layer_labels[i] = labels_per_layer[i];
+    }
+    p.depth = depth_dev;
+    p.cond = reinterpret_cast<const int2*>(conditions_dev);
+    p.composite = composite_dev;
+    p.L = num_layers;
+    p.n_cond = n_cond;
+    p.W = dim_x; p.H = dim_y; p.r = labels_reduce;
+    p.w = dim_x / labels_reduce; p.h = dim_y / labels_reduce;
+    if (p.w == 0 || p.h == 0) return RDF_OK;
+    p.tiles_x = (p.w + 31) / 32;
+    p.scale = scale;
+    const int tiles_y = (p.h + 7) / 8;
+    rdf_layered_kernel<8><<<p.tiles_x * tiles_y, 256, 0, rdf_stream(stream)>>>(p);
+    RDF_LAUNCH_CHECK("rdf_layered_kernel");
+    return RDF_OK;
+}

@@ -1,0 +1,270 @@
+// Mean-shift fingertip centroids: replaces MeanShift.run (reference src/cuda/mean_shift.py:19-59) and its kernel
+// `run` (src/cuda/mean_shift.cu:3-48).
+//
+// The reference runs, per round, one fill + one kernel doing three global fp64 atomics per labelled pixel onto K*3
+// addresses + two blocking D2H copies + a host divide + one H2D copy.  Here all rounds run in ONE launch of a single
+// thread-block cluster:
+//   1. each CTA counting-sorts the labelled pixels of its slice of the image by class into a compact coordinate
+//      list (ballot/match based, deterministic order, no atomics);
+//   2. per round, warps reduce fixed-size items of one class each with shuffles (fp64, fixed order), CTAs exchange
+//      their K*3 partial sums through distributed shared memory, and after one cluster barrier every CTA computes
+//      the new means redundantly - no global atomics, no grid relaunch, no host round trip.
+// Results are bitwise reproducible run to run for a given launch shape.
+#include <cooperative_groups.h>
+
+#include "rdf_common.cuh"
+
+namespace cg = cooperative_groups;
+
+#define MS_THREADS 512
+#define MS_WARPS (MS_THREADS / 32)
+#define MS_MAX_ITEMS 1024
+#define MS_MAX_CLUSTER 8
+
+struct rdf_ms_params {
+    const uint16_t* labels;
+    const float* variances;
+    double* means_out;
+    uint32_t* entries;      // workspace: uint32[h*w], x | y << 16
+    int w, h, K, rounds;
+    int chunk;              // pixels per CTA (multiple of 32 * MS_WARPS)
+    int item;               // entries per work item (multiple of 32)
+};
+
+__device__ __forceinline__ double ms_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(MS_THREADS) rdf_mean_shift_kernel(const rdf_ms_params p) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int NC = (int)cluster.num_blocks();
+    const int K = p.K;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    extern __shared__ __align__(16) unsigned char ms_smem[];
+    double* all_partial = reinterpret_cast<double*>(ms_smem);                 // [2][NC][K][3]
+    double* partial = all_partial + 2 * (size_t)NC * K * 3;                   // [MS_MAX_ITEMS][3]
+    double* means_s = partial + MS_MAX_ITEMS * 3;                             // [K][2]
+    double* v2_s = means_s + 2 * K;                                           // [K]
+    int* cnt = reinterpret_cast<int*>(v2_s + K);                              // [MS_WARPS][K]  (counts, then cursors)
+    int* seg_start = cnt + MS_WARPS * K;                                      // [K+1]
+    int* item_start = seg_start + (K + 1);                                    // [K+1]
+
+    const int npx = p.w * p.h;
+    const int p0 = rank * p.chunk;
+    const int p1 = min(npx, p0 + p.chunk);
+    const int warp_chunk = p.chunk / MS_WARPS;                                // multiple of 32
+    const int wp0 = p0 + warp * warp_chunk;
+    const int wp1 = min(p1, wp0 + warp_chunk);
+
+    for (int i = tid; i < MS_WARPS * K; i += MS_THREADS) cnt[i] = 0;
+    for (int k = tid; k < K; k += MS_THREADS) {
+        means_s[2 * k] = 0.0;
+        means_s[2 * k + 1] = 0.0;
+        const float v = p.variances[k];
+        v2_s[k] = (double)__fmul_rn(v, v);                                    // fp32 product, widened (mean_shift.cu:41)
+    }
+    __syncthreads();
+
+    // ---- pass A: per-warp class counts --------------------------------------------------------------------
+    for (int base = wp0; base < wp1; base += 32) {
+        const int px = base + lane;
+        int key = -1;
+        if (px < wp1) {
+            const unsigned l = __ldg(p.labels + px);
+            if (l != 0u && l != RDF_NO_PIXEL && (int)l <= K) key = (int)l - 1;  // mean_shift.cu:23
+        }
+        const unsigned grp = __match_any_sync(0xffffffffu, key);
+        if (key >= 0 && lane == __ffs(grp) - 1) cnt[warp * K + key] += __popc(grp);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- class segment offsets and per-warp cursors (class-major, warp-minor => raster order within a class) ----
+    for (int k = tid; k < K; k += MS_THREADS) {
+        int s = 0;
+        for (int wv = 0; wv < MS_WARPS; wv++) s += cnt[wv * K + k];
+        seg_start[k + 1] = s;                                                 // lengths for now
+    }
+    __syncthreads();
+    if (tid == 0) {
+        seg_start[0] = 0;
+        item_start[0] = 0;
+        for (int k = 0; k < K; k++) {
+            const int len = seg_start[k + 1];
+            seg_start[k + 1] = seg_start[k] + len;
+            item_start[k + 1] = item_start[k] + (len + p.item - 1) / p.item;
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += MS_THREADS) {
+        int s = seg_start[k];
+        for (int wv = 0; wv < MS_WARPS; wv++) {
+            const int c = cnt[wv * K + k];
+            cnt[wv * K + k] = s;
+            s += c;
+        }
+    }
+    __syncthreads();
+
+    // ---- pass B: scatter coordinates into the class-sorted list ----------------------------------------------
+    uint32_t* my_entries = p.entries + p0;
+    for (int base = wp0; base < wp1; base += 32) {
+        const int px = base + lane;
+        int key = -1;
+        if (px < wp1) {
+            const unsigned l = __ldg(p.labels + px);
+            if (l != 0u && l != RDF_NO_PIXEL && (int)l <= K) key = (int)l - 1;
+        }
+        const unsigned grp = __match_any_sync(0xffffffffu, key);
+        int pos = 0;
+        if (key >= 0) pos = cnt[warp * K + key] + __popc(grp & ((1u << lane) - 1u));
+        __syncwarp();
+        if (key >= 0) {
+            const int y = px / p.w, x = px - y * p.w;
+            my_entries[pos] = (uint32_t)x | ((uint32_t)y << 16);
+            if (lane == __ffs(grp) - 1) cnt[warp * K + key] += __popc(grp);
+        }
+        __syncwarp();
+    }
+    __syncthreads();   // entries written by this CTA are read back by this CTA only
+
+    // ---- rounds ----------------------------------------------------------------------------------------------
+    const int n_items = item_start[K];
+    for (int it = 0; it < p.rounds; it++) {
+        for (int item = warp; item < n_items; item += MS_WARPS) {
+            // class of this item: last k with item_start[k] <= item
+            int lo = 0, hi = K - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (item_start[mid] <= item) lo = mid; else hi = mid - 1;
+            }
+            const int k = lo;
+            const int e0 = seg_start[k] + (item - item_start[k]) * p.item;
+            const int e1 = min(seg_start[k + 1], e0 + p.item);
+            const double mx = means_s[2 * k], my = means_s[2 * k + 1];
+            const double two_v2 = 2.0 * v2_s[k];
+            double sx = 0.0, sy = 0.0, sp = 0.0;
+            for (int e = e0 + lane; e < e1; e += 32) {
+                const uint32_t c = my_entries[e];
+                const double cx = (double)(c & 0xffffu), cy = (double)(c >> 16);
+                if (it == 0) {                                               // mean_shift.cu:31-34
+                    sx += cx;
+                    sy += cy;
+                    sp += 1.0;
+                } else {                                                     // mean_shift.cu:36-46
+                    const double dx = cx - mx, dy = cy - my;
+                    const double pr = exp(-(dx * dx + dy * dy) / two_v2);
+                    sx += dx * pr;
+                    sy += dy * pr;
+                    sp += pr;
+                }
+            }
+            sx = ms_warp_sum(sx);
+            sy = ms_warp_sum(sy);
+            sp = ms_warp_sum(sp);
+            if (lane == 0) {
+                partial[item * 3 + 0] = sx;
+                partial[item * 3 + 1] = sy;
+                partial[item * 3 + 2] = sp;
+            }
+        }
+        __syncthreads();
+        // CTA partial per (class, component), items in order; broadcast to every CTA of the cluster through DSMEM
+        double* buf = all_partial + (size_t)(it & 1) * NC * K * 3;
+        for (int i = tid; i < 3 * K; i += MS_THREADS) {
+            const int k = i / 3, comp = i - 3 * k;
+            double s = 0.0;
+            for (int item = item_start[k]; item < item_start[k + 1]; item++) s += partial[item * 3 + comp];
+            for (int r = 0; r < NC; r++) {
+                double* remote = cluster.map_shared_rank(buf, r);
+                remote[((size_t)rank * K + k) * 3 + comp] = s;
+            }
+        }
+        cluster.sync();
+        for (int k = tid; k < K; k += MS_THREADS) {
+            double sx = 0.0, sy = 0.0, sp = 0.0;
+            for (int r = 0; r < NC; r++) {
+                sx += buf[((size_t)r * K + k) * 3 + 0];
+                sy += buf[((size_t)r * K + k) * 3 + 1];
+                sp += buf[((size_t)r * K + k) * 3 + 2];
+            }
+            means_s[2 * k] += sx / sp;                                       // mean_shift.py:53-55 (0/0 -> NaN)
+            means_s[2 * k + 1] += sy / sp;
+        }
+        __syncthreads();
+    }
+    if (rank == 0)
+        for (int i = tid; i < 2 * K; i += MS_THREADS) p.means_out[i] = means_s[i];
+    cluster.sync();   // no CTA may exit while peers can still address its shared memory
+}
+
+static size_t ms_smem_bytes(int K, int NC) {
+    size_t b = 0;
+    b += sizeof(double) * 2 * (size_t)NC * K * 3;
+    b += sizeof(double) * MS_MAX_ITEMS * 3;
+    b += sizeof(double) * 3 * (size_t)K;
+    b += sizeof(int) * ((size_t)MS_WARPS * K + 2 * (K + 1));
+    return b;
+}
+
+extern "C" int rdf_mean_shift_workspace_bytes(int dim_x, int dim_y, int num_labels, size_t* bytes) {
+    RDF_REQUIRE(bytes != nullptr && dim_x > 0 && dim_y > 0 && num_labels >= 0, "rdf_mean_shift_workspace_bytes: bad argument");
+    // one uint32 per pixel, padded so every CTA slice (multiple of 512 pixels) stays in bounds
+    *bytes = sizeof(uint32_t) * ((size_t)dim_x * dim_y + (size_t)MS_MAX_CLUSTER * 32 * MS_WARPS);
+    return RDF_OK;
+}
+
+extern "C" int rdf_mean_shift(const uint16_t* labels_dev, int dim_x, int dim_y, int num_labels, const float* variances_dev,
+                              int rounds, double* means_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    RDF_REQUIRE(labels_dev && variances_dev && means_dev && workspace_dev, "rdf_mean_shift: NULL argument");
+    RDF_REQUIRE(dim_x > 0 && dim_y > 0 && dim_x <= 65535 && dim_y <= 65535, "rdf_mean_shift: bad image shape %dx%d", dim_x, dim_y);
+    RDF_REQUIRE(num_labels >= 1 && num_labels <= RDF_MAX_CLASSES, "rdf_mean_shift: num_labels=%d outside 1..%d", num_labels,
+                RDF_MAX_CLASSES);
+    RDF_REQUIRE(rounds >= 0, "rdf_mean_shift: rounds=%d", rounds);
+    size_t need = 0;
+    rdf_mean_shift_workspace_bytes(dim_x, dim_y, num_labels, &need);
+    RDF_REQUIRE(workspace_bytes >= need, "rdf_mean_shift: workspace %zu < %zu bytes", workspace_bytes, need);
+    RDF_REQUIRE((int64_t)dim_x * dim_y < (1LL << 30), "rdf_mean_shift: image too large");
+
+    const int npx = dim_x * dim_y;
+    const int gran = 32 * MS_WARPS;
+    int NC = (npx + 8191) / 8192;                  // >= 8192 pixels per CTA before adding CTAs
+    if (NC > MS_MAX_CLUSTER) NC = MS_MAX_CLUSTER;
+    if (NC < 1) NC = 1;
+    rdf_ms_params p;
+    p.labels = labels_dev;
+    p.variances = variances_dev;
+    p.means_out = means_dev;
+    p.entries = reinterpret_cast<uint32_t*>(workspace_dev);
+    p.w = dim_x; p.h = dim_y; p.K = num_labels; p.rounds = rounds;
+    p.chunk = (((npx + NC - 1) / NC) + gran - 1) / gran * gran;
+    int item = (p.chunk + (MS_MAX_ITEMS - RDF_MAX_CLASSES) - 1) / (MS_MAX_ITEMS - RDF_MAX_CLASSES);
+    item = (item + 31) / 32 * 32;
+    if (item < 256) item = 256;
+    p.item = item;
+
+    const size_t smem = ms_smem_bytes(num_labels, NC);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        RDF_CUDA(cudaFuncSetAttribute(rdf_mean_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(NC, 1, 1);
+    cfg.blockDim = dim3(MS_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = rdf_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NC;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RDF_CUDA(cudaLaunchKernelEx(&cfg, rdf_mean_shift_kernel, p));
+    return RDF_OK;
+}

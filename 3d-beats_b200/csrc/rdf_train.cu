@@ -1,0 +1,476 @@
+// Training split search: replaces evaluate_random_features, pick_best_features, get_active_nodes_next_level and
+// copy_pixel_groups (reference src/cuda/tree_train.cu:4-64, :66-236, :238-273, :275-324) plus the host-side root
+// statistics of DecisionTreeTrainer.train (src/decision_tree.py:452-467).
+#include "rdf_common.cuh"
+
+// ---------------------------------------------------------------------------------------------------------------
+// root statistics
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rdf_train_init_kernel(const uint16_t* __restrict__ labels, int64_t n, int C,
+                                                             int32_t* __restrict__ nodes_by_pixel,
+                                                             unsigned long long* __restrict__ root_counts) {
+    extern __shared__ unsigned int cnt_s[];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) cnt_s[c] = 0u;
+    __syncthreads();
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned l = __ldg(labels + i);
+        // labels outside 1..C-1 cannot be counted (the reference would index node_counts out of bounds); keep them inactive
+        const bool active = l > 0u && l < (unsigned)C;
+        nodes_by_pixel[i] = active ? 0 : -1;                       // decision_tree.py:462-463
+        if (active) atomicAdd(&cnt_s[l], 1u);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+        if (cnt_s[c]) atomicAdd(&root_counts[c], (unsigned long long)cnt_s[c]);   // decision_tree.py:457-460
+}
+
+extern "C" int rdf_train_init(const uint16_t* labels_dev, int64_t num_pixels, int num_classes, int32_t* nodes_by_pixel_dev,
+                              uint64_t* root_counts_dev, void* stream) {
+    RDF_REQUIRE(labels_dev && nodes_by_pixel_dev && root_counts_dev, "rdf_train_init: NULL argument");
+    RDF_REQUIRE(num_pixels >= 0 && num_classes >= 1 && num_classes <= RDF_MAX_CLASSES, "rdf_train_init: bad argument");
+    cudaStream_t st = rdf_stream(stream);
+    RDF_CUDA(cudaMemsetAsync(root_counts_dev, 0, sizeof(uint64_t) * num_classes, st));
+    if (num_pixels == 0) return RDF_OK;
+    rdf_train_init_kernel<<<148 * 8, 256, sizeof(unsigned) * num_classes, st>>>(
+        labels_dev, num_pixels, num_classes, nodes_by_pixel_dev, reinterpret_cast<unsigned long long*>(root_counts_dev));
+    RDF_LAUNCH_CHECK("rdf_train_init_kernel");
+    return RDF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// split histograms
+// ---------------------------------------------------------------------------------------------------------------
+// Work decomposition: blockIdx.x = tile of TH_PIX consecutive pixels, blockIdx.y = chunk of FC features.
+// Lanes of a warp are consecutive pixels evaluating the SAME feature, so both depth probes of a warp land on
+// neighbouring addresses (coalesced gathers), and the feature's offsets / thresholds are shared-memory broadcasts.
+// Histogram updates go to a shared-memory privatised copy when all slots x FC features fit (shallow levels, where
+// every pixel of the GPU hits the same few nodes), otherwise straight to global memory (deep levels, low contention).
+#define TH_THREADS 512
+#define TH_PIX 4096          // pixels per block
+#define TH_MAX_FC 128
+
+struct rdf_hist_params {
+    const uint16_t* depth;
+    const uint16_t* labels;
+    const int32_t* nodes_by_pixel;
+    const int32_t* node_slot;
+    const float* offsets;        // [F][4]
+    const float* thresholds;     // [F][NT]
+    uint32_t* hist;              // [S][F][NB][C]
+    int64_t num_pixels;
+    int W, H, S, F, NT, NB, C, FC;
+    int privatise;               // 1: shared-memory histogram [S][FC][NB][C]
+};
+
+__global__ void __launch_bounds__(TH_THREADS) rdf_train_hist_kernel(const rdf_hist_params p) {
+    extern __shared__ __align__(16) unsigned char th_smem[];
+    float* off_s = reinterpret_cast<float*>(th_smem);                         // [FC][4]
+    float* thr_s = off_s + 4 * p.FC;                                          // [FC][NT]
+    uint32_t* hist_s = reinterpret_cast<uint32_t*>(thr_s + (size_t)p.FC * p.NT);   // [S][FC][NB][C] if privatise
+
+    const int f0 = blockIdx.y * p.FC;
+    const int nf = min(p.FC, p.F - f0);
+    for (int i = threadIdx.x; i < nf * 4; i += TH_THREADS) off_s[i] = __ldg(p.offsets + (size_t)f0 * 4 + i);
+    for (int i = threadIdx.x; i < nf * p.NT; i += TH_THREADS) thr_s[i] = __ldg(p.thresholds + (size_t)f0 * p.NT + i);
+    const int per_slot = p.FC * p.NB * p.C;
+    if (p.privatise)
+        for (int i = threadIdx.x; i < p.S * per_slot; i += TH_THREADS) hist_s[i] = 0u;
+    __syncthreads();
+
+    const int64_t tile0 = (int64_t)blockIdx.x * TH_PIX;
+    const int per_img = p.W * p.H;
+    for (int k = threadIdx.x; k < TH_PIX; k += TH_THREADS) {
+        const int64_t i = tile0 + k;
+        if (i >= p.num_pixels) break;
+        const int g = __ldg(p.nodes_by_pixel + i);
+        if (g < 0) continue;                                                  // tree_train.cu:36-37
+        const int slot = __ldg(p.node_slot + g);
+        if (slot < 0) continue;                                               // node not in this block (tree_train.cu:42)
+        const int n = (int)(i / per_img);
+        const int rem = (int)(i - (int64_t)n * per_img);
+        const int Y = rem / p.W, X = rem - Y * p.W;
+        const uint16_t* img = p.depth + (size_t)n * per_img;
+        const unsigned d = __ldg(img + rem);
+        const unsigned label = __ldg(p.labels + i);
+        if (label >= (unsigned)p.C) continue;
+        const float df = (float)d;
+        uint32_t* dst = p.privatise ? hist_s + (size_t)slot * per_slot
+                                    : p.hist + ((size_t)slot * p.F + f0) * p.NB * p.C;
+        for (int j = 0; j < nf; j++) {
+            const float4 o = *reinterpret_cast<const float4*>(off_s + 4 * j);
+            // compute_feature with scale 1 (tree_train.cu:58); d == 0 -> 0.f (decision_tree_common.hpp:12)
+            const float f = d == 0u ? 0.f : rdf_feature(img, p.W, p.H, X, Y, df, o.x, o.y, o.z, o.w);
+            // bin = #{k : t_k <= f}: branch-free binary search over the ascending thresholds
+            const float* th = thr_s + j * p.NT;
+            int lo = 0, len = p.NT;
+            while (len > 0) {
+                const int half = len >> 1;
+                const bool go = th[lo + half] <= f;
+                lo = go ? lo + half + 1 : lo;
+                len = go ? len - half - 1 : half;
+            }
+            atomicAdd(dst + ((size_t)j * p.NB + lo) * p.C + label, 1u);
+        }
+    }
+    if (p.privatise) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < p.S * per_slot; i += TH_THREADS) {
+            const uint32_t v = hist_s[i];
+            if (v) {
+                const int slot = i / per_slot;
+                const int r = i - slot * per_slot;                 // (j, bin, class) within the chunk
+                const int j = r / (p.NB * p.C);
+                if (j < nf) atomicAdd(p.hist + ((size_t)slot * p.F + f0) * p.NB * p.C + r, v);
+            }
+        }
+    }
+}
+
+extern "C" int rdf_train_hist(const uint16_t* depth_dev, const uint16_t* labels_dev, const int32_t* nodes_by_pixel_dev,
+                              int num_images, int dim_x, int dim_y, const int32_t* node_slot_dev, int num_slots,
+                              const float* offsets_dev, const float* thresholds_dev, int num_features, int num_thresholds,
+                              int num_classes, uint32_t* hist_dev, void* stream) {
+    RDF_REQUIRE(depth_dev && labels_dev && nodes_by_pixel_dev && node_slot_dev && offsets_dev && thresholds_dev && hist_dev,
+                "rdf_train_hist: NULL argument");
+    RDF_REQUIRE(num_images >= 0 && dim_x > 0 && dim_y > 0 && num_slots >= 1 && num_features >= 1 && num_thresholds >= 1 &&
+                    num_classes >= 1 && num_classes <= RDF_MAX_CLASSES,
+                "rdf_train_hist: bad shape");
+    rdf_hist_params p;
+    p.depth = depth_dev; p.labels = labels_dev; p.nodes_by_pixel = nodes_by_pixel_dev; p.node_slot = node_slot_dev;
+    p.offsets = offsets_dev; p.thresholds = thresholds_dev; p.hist = hist_dev;
+    p.num_pixels = (int64_t)num_images * dim_x * dim_y;
+    p.W = dim_x; p.H = dim_y; p.S = num_slots; p.F = num_features; p.NT = num_thresholds; p.NB = num_thresholds + 1;
+    p.C = num_classes;
+    if (p.num_pixels == 0) return RDF_OK;
+
+    const size_t smem_budget = 200 * 1024;
+    const size_t per_feature_static = sizeof(float) * (4 + (size_t)p.NT);
+    const size_t per_feature_hist = sizeof(uint32_t) * (size_t)p.S * p.NB * p.C;
+    int fc = (int)(smem_budget / (per_feature_static + per_feature_hist));
+    p.privatise = fc >= 8 ? 1 : 0;
+    if (!p.privatise) fc = (int)(smem_budget / per_feature_static);
+    if (fc > TH_MAX_FC) fc = TH_MAX_FC;
+    if (fc > p.F) fc = p.F;
+    if (fc < 1) {
+        rdf_set_error("rdf_train_hist: %d thresholds per feature do not fit shared memory", p.NT);
+        return RDF_ERR_UNSUPPORTED;
+    }
+    p.FC = fc;
+    const size_t smem = per_feature_static * fc + (p.privatise ? per_feature_hist * fc : 0);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        RDF_CUDA(cudaFuncSetAttribute(rdf_train_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget + 1024));
+        smem_set = smem_budget + 1024;
+    }
+    const int64_t tiles = (p.num_pixels + TH_PIX - 1) / TH_PIX;
+    const int chunks = (p.F + fc - 1) / fc;
+    RDF_REQUIRE(tiles <= 0x7fffffffLL && chunks <= 65535, "rdf_train_hist: grid too large (%lld tiles, %d feature chunks)",
+                (long long)tiles, chunks);
+    rdf_train_hist_kernel<<<dim3((unsigned)tiles, (unsigned)chunks), TH_THREADS, smem, rdf_stream(stream)>>>(p);
+    RDF_LAUNCH_CHECK("rdf_train_hist_kernel");
+    return RDF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pick best split per active node
+// ---------------------------------------------------------------------------------------------------------------
+// fp32 operation order = what nvcc 12.9 emits for the reference's gini helpers on sm_100a (checked in PTX):
+//   gini(c)  : s = cvt.rn.f32.u64(sum); p = fma(c_i/s, c_i/s, p) in class order; 1 - p          (tree_train.cu:72-80)
+//   gain     : lt = (l/p) * gini(l); rem = fma(r/p, gini(r), lt); gini(parent) - rem            (tree_train.cu:82-89)
+__device__ __forceinline__ float rdf_gini(const unsigned long long* c, int C, unsigned long long sum) {
+    const float s = __ull2float_rn(sum);
+    float p = 0.f;
+    for (int i = 0; i < C; i++) {
+        const float pi = __fdiv_rn(__ull2float_rn(c[i]), s);
+        p = __fmaf_rn(pi, pi, p);
+    }
+    return __fsub_rn(1.f, p);
+}
+
+#define PB_THREADS 256
+
+struct rdf_pick_params {
+    const int32_t* active_nodes;
+    const int32_t* node_slot;
+    const unsigned long long* parent_counts;   // [2^D][C] by node id
+    const uint32_t* hist;                      // [S][F][NB][C]
+    const float* offsets;
+    const float* thresholds;
+    float* tree;
+    unsigned long long* next_counts;           // [2^D][C] by child node id
+    float* best_gain;                          // [num_active]
+    int num_active, S, F, NT, NB, C, level, D;
+};
+
+// one block per active node; threads stride over features, each scanning its feature's NT thresholds with a running
+// prefix of the bin histogram.  Winner = greatest gain, ties -> smallest candidate index (= first in proposal order).
+__global__ void __launch_bounds__(PB_THREADS) rdf_train_pick_best_kernel(const rdf_pick_params p) {
+    const int a = blockIdx.x;
+    if (a >= p.num_active) return;
+    const int node = p.active_nodes[a];
+    const int slot = p.node_slot[node];
+    if (slot < 0) return;                                          // not in this node block (tree_train.cu:135)
+    const int C = p.C;
+
+    extern __shared__ unsigned long long pb_smem[];
+    unsigned long long* par = pb_smem;                             // [C]
+    unsigned long long* scratch = par + C;                         // [PB_THREADS][2][C] left/right of the running candidate
+    __shared__ float red_g[PB_THREADS];
+    __shared__ int red_i[PB_THREADS];
+    __shared__ float s_gini_parent;
+    __shared__ unsigned long long s_parent_sum;
+
+    for (int c = threadIdx.x; c < C; c += PB_THREADS) par[c] = p.parent_counts[(size_t)node * C + c];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long s = 0;
+        for (int c = 0; c < C; c++) s += par[c];
+        s_parent_sum = s;
+        s_gini_parent = rdf_gini(par, C, s);
+    }
+    __syncthreads();
+    const unsigned long long parent_sum = s_parent_sum;
+    const float p_sum_f = __ull2float_rn(parent_sum);
+    const float gini_parent = s_gini_parent;
+
+    unsigned long long* left = scratch + (size_t)threadIdx.x * 2 * C;
+    unsigned long long* right = left + C;
+    float best_g = -1.f;
+    int best_i = 0x7fffffff;
+    for (int f = threadIdx.x; f < p.F; f += PB_THREADS) {
+        const uint32_t* h = p.hist + ((size_t)slot * p.F + f) * p.NB * C;
+        for (int c = 0; c < C; c++) {
+            unsigned long long tot = 0;
+            for (int b = 0; b < p.NB; b++) tot += h[b * C + c];
+            left[c] = 0;
+            right[c] = tot;
+        }
+        for (int k = 0; k < p.NT; k++) {
+            unsigned long long ls = 0, rs = 0;
+            for (int c = 0; c < C; c++) {                          // left = bins 0..k  (f < t_k)
+                const unsigned long long v = h[k * C + c];
+                left[c] += v;
+                right[c] -= v;
+                ls += left[c];
+                rs += right[c];
+            }
+            float g = 0.f;                                         // a side empty -> 0 (tree_train.cu:158-160)
+            if (ls && rs) {
+                const float lt = __fmul_rn(__fdiv_rn(__ull2float_rn(ls), p_sum_f), rdf_gini(left, C, ls));
+                const float rem = __fmaf_rn(__fdiv_rn(__ull2float_rn(rs), p_sum_f), rdf_gini(right, C, rs), lt);
+                g = __fsub_rn(gini_parent, rem);
+            }
+            if (g > best_g) {                                      // strict >, candidates visited in ascending index
+                best_g = g;
+                best_i = f * p.NT + k;
+            }
+        }
+    }
+    red_g[threadIdx.x] = best_g;
+    red_i[threadIdx.x] = best_i;
+    __syncthreads();
+    for (int s = PB_THREADS / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            const float g2 = red_g[threadIdx.x + s];
+            const int i2 = red_i[threadIdx.x + s];
+            const float g1 = red_g[threadIdx.x];
+            const int i1 = red_i[threadIdx.x];
+            if (g2 > g1 || (g2 == g1 && i2 < i1)) {
+                red_g[threadIdx.x] = g2;
+                red_i[threadIdx.x] = i2;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    best_g = red_g[0];
+    best_i = red_i[0];
+    if (!(best_g > -1.f)) return;                                  // the reference asserts best_g > -1 (tree_train.cu:170)
+    if (best_g <= p.best_gain[a]) return;                          // tree_train.cu:172
+    p.best_gain[a] = best_g;
+
+    const int bf = best_i / p.NT, bk = best_i - bf * p.NT;
+    const uint32_t* h = p.hist + ((size_t)slot * p.F + bf) * p.NB * C;
+    unsigned long long ls = 0, rs = 0;
+    for (int c = 0; c < C; c++) {
+        unsigned long long l = 0, tot = 0;
+        for (int b = 0; b < p.NB; b++) {
+            const unsigned long long v = h[b * C + c];
+            tot += v;
+            if (b <= bk) l += v;
+        }
+        left[c] = l;
+        right[c] = tot - l;
+        ls += l;
+        rs += tot - l;
+    }
+    const int E = 7 + 2 * C;
+    float* out = p.tree + ((((size_t)1 << p.level) - 1) + node) * E;
+    out[0] = p.offsets[4 * bf + 0];                                // tree_train.cu:183-186
+    out[1] = p.offsets[4 * bf + 1];
+    out[2] = p.offsets[4 * bf + 2];
+    out[3] = p.offsets[4 * bf + 3];
+    out[4] = p.thresholds[(size_t)bf * p.NT + bk];
+    if (best_g <= 0.f) {                                           // tree_train.cu:190-198
+        out[5] = 0.f;
+        out[6] = 0.f;
+        for (int c = 0; c < C; c++) {
+            const float v = __fdiv_rn(__ull2float_rn(par[c]), p_sum_f);
+            out[7 + c] = v;
+            out[7 + C + c] = v;
+        }
+        return;
+    }
+    for (int side = 0; side < 2; side++) {                         // tree_train.cu:201-235
+        const unsigned long long* cnt = side ? right : left;
+        const unsigned long long sum = side ? rs : ls;
+        const float sum_f = __ull2float_rn(sum);
+        float* pdf = out + 7 + side * C;
+        int cut = -1;
+        for (int c = 0; c < C; c++)
+            if (__fdiv_rn(__ull2float_rn(cnt[c]), sum_f) >= 0.999f) { cut = c; break; }      // count_above_cutoff (:92-97)
+        if (cut > -1) {
+            out[5 + side] = 0.f;
+            pdf[cut] = 1.f;                                        // other entries keep whatever they held (:204-206)
+        } else if (p.level == p.D - 1) {
+            out[5 + side] = 0.f;
+            for (int c = 0; c < C; c++) pdf[c] = __fdiv_rn(__ull2float_rn(cnt[c]), sum_f);
+        } else {
+            out[5 + side] = -1.f;
+            unsigned long long* nc = p.next_counts + ((size_t)2 * node + side) * C;
+            for (int c = 0; c < C; c++) nc[c] = cnt[c];
+        }
+    }
+}
+
+extern "C" int rdf_train_pick_best(int num_active, const int32_t* active_nodes_dev, const int32_t* node_slot_dev,
+                                   const uint64_t* parent_counts_dev, const uint32_t* hist_dev, int num_slots,
+                                   const float* offsets_dev, const float* thresholds_dev, int num_features,
+                                   int num_thresholds, int num_classes, int level, int max_depth, float* tree_dev,
+                                   uint64_t* next_counts_dev, float* best_gain_dev, void* stream) {
+    RDF_REQUIRE(active_nodes_dev && node_slot_dev && parent_counts_dev && hist_dev && offsets_dev && thresholds_dev && tree_dev &&
+                    next_counts_dev && best_gain_dev,
+                "rdf_train_pick_best: NULL argument");
+    RDF_REQUIRE(num_active >= 0 && num_slots >= 1 && num_features >= 1 && num_thresholds >= 1 && num_classes >= 1 &&
+                    num_classes <= RDF_MAX_CLASSES && level >= 0 && level < max_depth && max_depth <= RDF_MAX_DEPTH,
+                "rdf_train_pick_best: bad argument");
+    if (num_active == 0) return RDF_OK;
+    rdf_pick_params p;
+    p.active_nodes = active_nodes_dev; p.node_slot = node_slot_dev;
+    p.parent_counts = reinterpret_cast<const unsigned long long*>(parent_counts_dev);
+    p.hist = hist_dev; p.offsets = offsets_dev; p.thresholds = thresholds_dev; p.tree = tree_dev;
+    p.next_counts = reinterpret_cast<unsigned long long*>(next_counts_dev);
+    p.best_gain = best_gain_dev;
+    p.num_active = num_active; p.S = num_slots; p.F = num_features; p.NT = num_thresholds; p.NB = num_thresholds + 1;
+    p.C = num_classes; p.level = level; p.D = max_depth;
+    const size_t smem = sizeof(unsigned long long) * ((size_t)num_classes + (size_t)PB_THREADS * 2 * num_classes);
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        RDF_CUDA(cudaFuncSetAttribute(rdf_train_pick_best_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    RDF_REQUIRE(smem <= 220 * 1024, "rdf_train_pick_best: %d classes exceed the shared-memory scratch", num_classes);
+    rdf_train_pick_best_kernel<<<num_active, PB_THREADS, smem, rdf_stream(stream)>>>(p);
+    RDF_LAUNCH_CHECK("rdf_train_pick_best_kernel");
+    return RDF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// next active nodes (deterministic compaction: ascending active index, left child before right)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) rdf_train_next_active_kernel(const float* __restrict__ tree, int level, int C,
+                                                                      const int32_t* __restrict__ active, int num_active,
+                                                                      int32_t* __restrict__ next_active,
+                                                                      int32_t* __restrict__ num_next) {
+    __shared__ int warp_tot[32];
+    __shared__ int running;
+    const int E = 7 + 2 * C;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    for (int base = 0; base < num_active; base += 1024) {
+        const int i = base + threadIdx.x;
+        int node = 0, nl = 0, nr = 0;
+        if (i < num_active) {
+            node = active[i];
+            const float* nd = tree + ((((size_t)1 << level) - 1) + node) * E;
+            nl = nd[5] == -1.f;                                    // tree_train.cu:263
+            nr = nd[6] == -1.f;                                    // tree_train.cu:268
+        }
+        const int mine = nl + nr;
+        int incl = mine;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int t = warp_tot[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t += v;
+            }
+            warp_tot[lane] = t;                                    // inclusive over warps
+        }
+        __syncthreads();
+        const int start = running + (warp ? warp_tot[warp - 1] : 0) + incl - mine;
+        if (nl) next_active[start] = 2 * node;
+        if (nr) next_active[start + nl] = 2 * node + 1;
+        __syncthreads();
+        if (threadIdx.x == 0) running += warp_tot[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *num_next = running;
+}
+
+extern "C" int rdf_train_next_active(const float* tree_dev, int level, int max_depth, int num_classes,
+                                     const int32_t* active_nodes_dev, int num_active, int32_t* next_active_dev,
+                                     int32_t* num_next_active_dev, void* stream) {
+    RDF_REQUIRE(tree_dev && active_nodes_dev && next_active_dev && num_next_active_dev, "rdf_train_next_active: NULL argument");
+    RDF_REQUIRE(level >= 0 && level < max_depth && num_active >= 0 && num_classes >= 1, "rdf_train_next_active: bad argument");
+    rdf_train_next_active_kernel<<<1, 1024, 0, rdf_stream(stream)>>>(tree_dev, level, num_classes, active_nodes_dev, num_active,
+                                                                     next_active_dev, num_next_active_dev);
+    RDF_LAUNCH_CHECK("rdf_train_next_active_kernel");
+    return RDF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// advance pixels to their child node
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rdf_train_advance_kernel(const uint16_t* __restrict__ depth, int32_t* __restrict__ nodes,
+                                                                 int64_t num_pixels, int W, int H,
+                                                                 const float* __restrict__ tree, int level, int C) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= num_pixels) return;
+    const int g = nodes[i];
+    if (g == -1) return;                                           // tree_train.cu:294
+    const int per_img = W * H;
+    const int n = (int)(i / per_img);
+    const int rem = (int)(i - (int64_t)n * per_img);
+    const int Y = rem / W, X = rem - Y * W;
+    const uint16_t* img = depth + (size_t)n * per_img;
+    const int E = 7 + 2 * C;
+    const float* nd = tree + ((((size_t)1 << level) - 1) + g) * E;
+    const unsigned d = __ldg(img + rem);
+    const float f = d == 0u ? 0.f : rdf_feature(img, W, H, X, Y, (float)d, __ldg(nd + 0), __ldg(nd + 1), __ldg(nd + 2), __ldg(nd + 3));
+    const bool left = f < __ldg(nd + 4);
+    const int status = __float2int_rd(__ldg(nd + (left ? 5 : 6)));
+    nodes[i] = status != -1 ? -1 : 2 * g + (left ? 0 : 1);         // tree_train.cu:316-323
+}
+
+extern "C" int rdf_train_advance_pixels(const uint16_t* depth_dev, int32_t* nodes_by_pixel_dev, int num_images, int dim_x,
+                                        int dim_y, const float* tree_dev, int level, int max_depth, int num_classes,
+                                        void* stream) {
+    RDF_REQUIRE(depth_dev && nodes_by_pixel_dev && tree_dev, "rdf_train_advance_pixels: NULL argument");
+    RDF_REQUIRE(num_images >= 0 && dim_x > 0 && dim_y > 0 && level >= 0 && level < max_depth && num_classes >= 1,
+                "rdf_train_advance_pixels: bad argument");
+    const int64_t n = (int64_t)num_images * dim_x * dim_y;
+    if (n == 0) return RDF_OK;
+    const int64_t blocks = (n + 255) / 256;
+    RDF_REQUIRE(blocks <= 0x7fffffffLL, "rdf_train_advance_pixels: too many pixels");
+    rdf_train_advance_kernel<<<(unsigned)blocks, 256, 0, rdf_stream(stream)>>>(depth_dev, nodes_by_pixel_dev, n, dim_x, dim_y,
+                                                                                tree_dev, level, num_classes);
+    RDF_LAUNCH_CHECK("rdf_train_advance_kernel");
+    return RDF_OK;
+}

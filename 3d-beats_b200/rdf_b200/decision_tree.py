@@ -1,0 +1,563 @@
+"""Host-side mirror of the reference's RDF library (src/decision_tree.py) over librdf_b200.so.
+
+Same class / method names, positional argument order and semantics as the reference so that run_live.py,
+run_live_layered.py, test_on_saved_model.py and train_model.py keep working (`from decision_tree import *`,
+SURVEY section 8b).  Differences, all behind the same call surface:
+  * kernels are ahead-of-time sm_100a code reached through a C ABI (no pycuda JIT, no CPU fallback);
+  * forests keep a packed device shadow (32-byte node headers) that is refreshed lazily when `forest_cu` changed;
+  * LayeredDecisionForest.run is one fused launch; training data stays uncompressed in HBM (no nvcomp).
+"""
+import ctypes
+import json
+import os
+import os.path
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import _capi
+from . import buffers as cu_array          # `cu_array.GPUArray(...)`, `cu_array.to_gpu(...)` as in the reference
+from . import py_nvcc_utils
+from .buffers import GpuBuffer, GPUArray, as_gpuarray
+
+try:                                        # callers rely on `Image` re-exported by `from decision_tree import *`
+    from PIL import Image
+except Exception:                           # pragma: no cover - PIL is optional for the hot path itself
+    Image = None
+
+MAX_UINT16 = np.uint16(65535)               # src/util.py:43
+MAX_THREADS_PER_BLOCK = 1024                # kept for callers that import it (src/decision_tree.py:16)
+
+
+def sizeof_fmt(num, suffix='B'):
+    for unit in ['', 'K', 'M', 'G', 'T', 'P', 'E', 'Z']:
+        if abs(num) < 1024.0:
+            return "%3.1f %s%s" % (num, unit, suffix)
+        num /= 1024.0
+    return "%.1f%s%s" % (num, 'Y', suffix)
+
+
+def _version_of(arr):
+    """torch bumps `_version` on every in-place write (fill_, copy_): a free dirty flag for the packed shadow."""
+    return arr.tensor._version
+
+
+class DecisionTree():
+    """src/decision_tree.py:124-144."""
+
+    def __init__(self, max_depth, num_classes):
+        self.max_depth = max_depth
+        self.num_classes = num_classes
+        self.TOTAL_TREE_NODES, self.MAX_LEAF_NODES, self.TREE_NODE_ELS = DecisionTree.get_config(max_depth, num_classes)
+        self.tree_out_cu = GPUArray((self.TOTAL_TREE_NODES, self.TREE_NODE_ELS), dtype=np.float32)
+        self.tree_out_cu.fill(np.float32(0.))
+
+    @staticmethod
+    def get_config(max_depth, num_classes):
+        TOTAL_TREE_NODES = (2 ** max_depth) - 1       # nodes of the complete tree
+        MAX_LEAF_NODES = 2 ** max_depth               # children of the deepest level
+        TREE_NODE_ELS = 7 + (num_classes * 2)         # ux,uy,vx,vy,thresh,l_next,r_next,l_pdf[C],r_pdf[C]
+        return (TOTAL_TREE_NODES, MAX_LEAF_NODES, TREE_NODE_ELS)
+
+
+class DecisionForest():
+    """src/decision_tree.py:146-168.  `forest_cu` stays the canonical float32[T,2^D-1,7+2C] array; `handle()` returns the
+    packed shadow used by the kernels, re-packed automatically after `forest_cu` was written."""
+
+    @staticmethod
+    def load(model_filename):
+        forest_cpu = np.load(model_filename)
+        num_trees = forest_cpu.shape[0]
+        tree_depth = int(np.log2(forest_cpu.shape[1] + 1))
+        num_classes = (forest_cpu.shape[2] - 7) // 2
+        f = DecisionForest(num_trees, tree_depth, num_classes)
+        f.forest_cu.set(np.ascontiguousarray(forest_cpu, dtype=np.float32))
+        return f
+
+    def __init__(self, num_trees, max_depth, num_classes):
+        self.num_trees = num_trees
+        self.max_depth = max_depth
+        self.num_classes = num_classes
+        self.TOTAL_TREE_NODES, self.MAX_LEAF_NODES, self.TREE_NODE_ELS = DecisionTree.get_config(max_depth, num_classes)
+        self.forest_cu = GPUArray((self.num_trees, self.TOTAL_TREE_NODES, self.TREE_NODE_ELS), dtype=np.float32)
+        self.forest_cu.fill(np.float32(0.))
+        self._handle = None
+        self._packed_version = None
+        self._packed_ptr = None
+
+    def handle(self):
+        lib = _capi.load()
+        ver, ptr = _version_of(self.forest_cu), self.forest_cu.ptr
+        if self._handle is not None and ptr != self._packed_ptr:
+            self._destroy()
+        if self._handle is None:
+            h = ctypes.c_void_p()
+            _capi.check(lib.rdf_forest_create(_capi.dptr(self.forest_cu), self.num_trees, self.max_depth, self.num_classes,
+                                              _capi.stream_ptr(), ctypes.byref(h)))
+            self._handle = h
+        elif ver != self._packed_version:
+            _capi.check(lib.rdf_forest_update(self._handle, _capi.dptr(self.forest_cu), _capi.stream_ptr()))
+        self._packed_version, self._packed_ptr = ver, ptr
+        return self._handle
+
+    def invalidate(self):
+        """Force a re-pack on next use (needed only if forest_cu was written outside torch, e.g. by a foreign kernel)."""
+        self._packed_version = None
+
+    def _destroy(self):
+        if self._handle is not None:
+            try:
+                _capi.load().rdf_forest_destroy(self._handle)
+            except Exception:
+                pass
+            self._handle = None
+
+    def __del__(self):
+        self._destroy()
+
+
+class DecisionTreeEvaluator():
+    """src/decision_tree.py:267-347."""
+
+    def __init__(self):
+        self._lib = _capi.load()
+
+    def get_labels(self, tree, depth_images_in, labels_out):
+        depth_images_in = as_gpuarray(depth_images_in)
+        labels_out = as_gpuarray(labels_out)
+        num_images, dim_y, dim_x = depth_images_in.shape
+        assert labels_out.shape == (num_images, dim_y, dim_x)
+        assert depth_images_in.dtype == np.uint16 and labels_out.dtype == np.uint16
+        _capi.check(self._lib.rdf_eval_tree(_capi.dptr(tree.tree_out_cu), tree.max_depth, tree.num_classes,
+                                            _capi.dptr(depth_images_in), num_images, dim_x, dim_y, _capi.dptr(labels_out),
+                                            _capi.stream_ptr()))
+
+    def get_labels_forest(self, forest, depth_images_in, labels_out, labels_reduce=1, filter_images=None,
+                          filter_images_class=None, scale_factor=1., probs_out=None):
+        depth_images_in = as_gpuarray(depth_images_in)
+        labels_out = as_gpuarray(labels_out)
+        num_images, dim_y, dim_x = depth_images_in.shape
+        assert labels_out.shape == (num_images, dim_y // labels_reduce, dim_x // labels_reduce)
+        assert depth_images_in.dtype == np.uint16 and labels_out.dtype == np.uint16
+        if filter_images is not None:                      # the reference tests truthiness; `is not None` is the intent
+            filter_images = as_gpuarray(filter_images)
+            assert filter_images_class is not None
+            assert filter_images.shape == labels_out.shape
+            assert filter_images.dtype == np.uint16
+        if probs_out is not None:
+            probs_out = as_gpuarray(probs_out)
+            assert probs_out.shape == labels_out.shape + (forest.num_classes,) and probs_out.dtype == np.float32
+        fclass = int(filter_images_class) if filter_images is not None else -1
+        if forest.num_trees <= 8:
+            _capi.check(self._lib.rdf_eval_forest(forest.handle(), _capi.dptr(depth_images_in), num_images, dim_x, dim_y,
+                                                  _capi.dptr(filter_images), fclass, _capi.dptr(labels_out),
+                                                  _capi.dptr(probs_out), int(labels_reduce), float(scale_factor),
+                                                  _capi.stream_ptr()))
+        else:
+            _capi.check(self._lib.rdf_eval_forest_canonical(_capi.dptr(forest.forest_cu), forest.num_trees, forest.max_depth,
+                                                            forest.num_classes, _capi.dptr(depth_images_in), num_images,
+                                                            dim_x, dim_y, _capi.dptr(filter_images), fclass,
+                                                            _capi.dptr(labels_out), _capi.dptr(probs_out), int(labels_reduce),
+                                                            float(scale_factor), _capi.stream_ptr()))
+
+    def make_composite_labels_image(self, images, dim_x, dim_y, labels_decision_tree, composite_image):
+        images = as_gpuarray(images)
+        labels_decision_tree = as_gpuarray(labels_decision_tree)
+        composite_image = as_gpuarray(composite_image)
+        _capi.check(self._lib.rdf_composite(_capi.dptr(images), int(images.shape[0]), int(dim_x), int(dim_y),
+                                            _capi.dptr(labels_decision_tree), _capi.dptr(composite_image), _capi.stream_ptr()))
+
+
+class LayeredDecisionForest():
+    """src/decision_tree.py:171-264.  `run` is a single fused launch (rdf_layered_run)."""
+
+    @staticmethod
+    def load(config_filename, depth_dims, labels_reduce=1):
+        cfg = json.loads(open(config_filename).read())
+        cfg['root'] = os.path.join(*Path(config_filename).parts[0:-1])    # models are relative to the config file
+        return LayeredDecisionForest(cfg, depth_dims, labels_reduce)
+
+    def __init__(self, cfg, depth_dims, labels_reduce):
+        self.eval = DecisionTreeEvaluator()
+        self.depth_dims = tuple(depth_dims)   # y,x !!
+        self.labels_reduce = labels_reduce
+        self.labels_dims = (depth_dims[0] // labels_reduce, depth_dims[1] // labels_reduce)
+
+        self.m = []
+        for l in cfg['layers']:
+            model = l['model']
+            m = model if isinstance(model, DecisionForest) else DecisionForest.load(os.path.join(cfg['root'], model))
+            if 'filter_model' in l:           # the reference's second test is a constant-true string (SURVEY note N2)
+                filter_model = l['filter_model']
+                filter_model_class = l['filter_model_class']
+            else:
+                filter_model = None
+                filter_model_class = None
+            self.m.append((m, filter_model, filter_model_class))
+        self.num_models = len(self.m)
+
+        self.label_images = [GpuBuffer(self.labels_dims, dtype=np.uint16) for _ in range(self.num_models)]
+        self.labels_images_ptrs_cu = GpuBuffer((self.num_models,), dtype=np.int64)
+        label_images_ptrs = np.array([i.cu().__cuda_array_interface__['data'][0] for i in self.label_images], dtype=np.int64)
+        self.labels_images_ptrs_cu.cu().set(label_images_ptrs)
+
+        # conditions: (0, PIXEL_ID) or (1, NEXT_IMG_CONDITION_OFFSET)   (src/decision_tree.py:209-220)
+        labels_conditions = np.array(cfg['conditions'], dtype=np.int32).reshape(-1, 2)
+        self.labels_conditions_cu = GpuBuffer(labels_conditions.shape, dtype=np.int32)
+        self.labels_conditions_cu.cu().set(labels_conditions)
+        self.num_layered_classes = int(max([c[1] for c in filter(lambda c: c[0] == 0, labels_conditions)]))
+
+        label_colors = np.array(cfg['label_colors'], dtype=np.uint8)
+        assert label_colors.shape == (self.num_layered_classes, 4)
+        self.label_colors = GpuBuffer(label_colors.shape, dtype=np.uint8)
+        self.label_colors.cu().set(label_colors)
+
+        L = self.num_models
+        self._c_filter_model = (ctypes.c_int * L)(*[(-1 if fm is None else int(fm)) for _, fm, _ in self.m])
+        self._c_filter_class = (ctypes.c_int * L)(*[(-1 if fc is None else int(fc)) for _, _, fc in self.m])
+        self._c_label_ptrs = (ctypes.c_void_p * L)(*[i.cu().ptr for i in self.label_images])
+        self._n_cond = int(labels_conditions.shape[0])
+
+    def run(self, depth_image, labels_image, scale_factor=1.):
+        depth = as_gpuarray(depth_image)
+        labels = as_gpuarray(labels_image)
+        assert depth.dtype == np.uint16 and labels.dtype == np.uint16
+        assert depth.size == self.depth_dims[0] * self.depth_dims[1], 'depth image dims'
+        assert labels.size == self.labels_dims[0] * self.labels_dims[1], 'labels image dims'
+        L = self.num_models
+        handles = (ctypes.c_void_p * L)(*[m.handle().value for m, _, _ in self.m])
+        _capi.check(self.eval._lib.rdf_layered_run(
+            handles, L, self._c_filter_model, self._c_filter_class, _capi.dptr(depth), self.depth_dims[1], self.depth_dims[0],
+            self._c_label_ptrs, _capi.dptr(self.labels_conditions_cu.cu()), self._n_cond, _capi.dptr(labels),
+            int(self.labels_reduce), float(scale_factor), _capi.stream_ptr()))
+
+    def run_unfused(self, depth_image, labels_image, scale_factor=1.):
+        """The reference's launch sequence verbatim (fills, one forest eval per layer, composite): kept for parity tests
+        of get_labels_forest(filter_images=...) and make_composite_labels_image."""
+        labels_image = as_gpuarray(labels_image)
+        depth_image = as_gpuarray(depth_image)
+        labels_image.fill(MAX_UINT16)
+        for i in self.label_images:
+            i.cu().fill(MAX_UINT16)
+        depth_img_dims = (1,) + self.depth_dims
+        label_img_dims = (1,) + self.labels_dims
+        for i in range(self.num_models):
+            m, filter_model, filter_model_class = self.m[i]
+            self.eval.get_labels_forest(
+                m, depth_image.reshape(depth_img_dims), self.label_images[i].cu().reshape(label_img_dims),
+                labels_reduce=self.labels_reduce,
+                filter_images=self.label_images[filter_model].cu().reshape(label_img_dims) if (filter_model is not None) else None,
+                filter_images_class=filter_model_class, scale_factor=scale_factor)
+        self.eval.make_composite_labels_image(self.labels_images_ptrs_cu.cu(), self.labels_dims[1], self.labels_dims[0],
+                                              self.labels_conditions_cu.cu(), labels_image.reshape(label_img_dims))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# dataset (src/decision_tree.py:21-122) - blocks stay uncompressed in HBM (the reference keeps them nvcomp-compressed)
+# ----------------------------------------------------------------------------------------------------------------
+class ResidentBlocks:
+    """Replacement for CompressedBlocksStatic/Dynamic (src/compressed_blocks.py:9-208): 180 GB of HBM holds the blocks
+    uncompressed, so `get_block_cu` is a device-to-device copy and `write_block` its inverse."""
+
+    def __init__(self, num_blocks, block_shape, dtype, fill_block=None):
+        self.num_blocks = num_blocks
+        self.block_shape = tuple(block_shape)
+        self.store = GPUArray((num_blocks,) + self.block_shape, dtype=dtype)
+        if fill_block is not None:
+            host = np.zeros(self.block_shape, dtype=dtype)
+            for i in range(num_blocks):
+                fill_block(i, host)
+                self.store[i].set(host)
+
+    def block(self, i):
+        assert i < self.num_blocks
+        return self.store[i]
+
+    def get_block_cu(self, block_num, arr_out):
+        arr_out = as_gpuarray(arr_out)
+        assert arr_out.shape == self.block_shape
+        arr_out.set(self.block(block_num))
+
+    get_block = get_block_cu
+
+    def write_block(self, block_num, arr_in):
+        self.block(block_num).set(as_gpuarray(arr_in))
+
+
+class DecisionTreeDatasetConfig():
+
+    @staticmethod
+    def multiple(dataset_dir, images):
+        """randomly split up the dataset into chunks of the requested sizes (src/decision_tree.py:24-44)"""
+        total_images = json.loads(open(dataset_dir + 'config.json').read())['num_images']
+        num_images_to_fetch = sum([num_images for num_images, _, _ in images])
+        assert num_images_to_fetch <= total_images
+        datasets = []
+        for num_images, images_per_block, imgs_name in images:
+            images_per_block = images_per_block or num_images
+            datasets.append(DecisionTreeDatasetConfig(dataset_dir, num_images=num_images, images_per_block=images_per_block,
+                                                      imgs_name=imgs_name))
+        return tuple(datasets)
+
+    def __init__(self, dataset_dir, num_images=0, images_per_block=0, imgs_name='data0'):
+        self.dataset_dir = dataset_dir
+        cfg = json.loads(open(dataset_dir + 'config.json').read())
+        self.cfg = cfg
+        self.imgs_name = imgs_name
+        self.img_dims = tuple(cfg['img_dims'])
+        self.id_to_color = {0: np.array([0, 0, 0, 0], dtype=np.uint8)}
+        for i, c in cfg['id_to_color'].items():
+            self.id_to_color[int(i)] = np.array(c, dtype=np.uint8)
+        self.total_available_images = cfg['num_images']
+        self.num_images = num_images
+        if self.num_images == 0:
+            return
+        self.images_per_block = images_per_block or self.num_images
+        assert self.num_images % self.images_per_block == 0
+        self.num_image_blocks = self.num_images // self.images_per_block
+
+        img_idxes = list(range(cfg['num_images']))
+        np.random.shuffle(img_idxes)
+        img_idxes = img_idxes[0:self.num_images]
+        block_shape = (self.images_per_block, self.img_dims[1], self.img_dims[0])
+
+        def get_image_block(i, arr_out, name):
+            assert arr_out.shape == block_shape and arr_out.dtype == np.uint16
+            for j in range(self.images_per_block):
+                img_idx = img_idxes[(i * self.images_per_block) + j]
+                arr_out[j] = np.array(Image.open(f'{self.dataset_dir}/{str(img_idx).zfill(8)}_{name}.png')).astype(np.uint16)
+
+        self.depth_blocks = ResidentBlocks(self.num_image_blocks, block_shape, np.uint16, lambda i, a: get_image_block(i, a, 'depth'))
+        self.labels_blocks = ResidentBlocks(self.num_image_blocks, block_shape, np.uint16, lambda i, a: get_image_block(i, a, 'labels'))
+
+    @classmethod
+    def from_arrays(cls, depth, labels, num_classes, images_per_block=0, imgs_name='mem'):
+        """In-memory dataset (no PNG directory): depth/labels uint16[N,H,W] as NumPy arrays or device arrays."""
+        self = cls.__new__(cls)
+        N, H, W = depth.shape
+        self.dataset_dir = None
+        self.cfg = {'img_dims': [W, H], 'num_images': N}
+        self.imgs_name = imgs_name
+        self.img_dims = (W, H)
+        self.id_to_color = {i: np.array([(53 * i) % 256, (97 * i) % 256, (29 * i + 60) % 256, 255 if i else 0], dtype=np.uint8)
+                            for i in range(num_classes)}
+        self.total_available_images = N
+        self.num_images = N
+        self.images_per_block = images_per_block or N
+        assert N % self.images_per_block == 0
+        self.num_image_blocks = N // self.images_per_block
+        block_shape = (self.images_per_block, H, W)
+        self.depth_blocks = ResidentBlocks(self.num_image_blocks, block_shape, np.uint16)
+        self.labels_blocks = ResidentBlocks(self.num_image_blocks, block_shape, np.uint16)
+        for store, src in ((self.depth_blocks, depth), (self.labels_blocks, labels)):
+            if isinstance(src, np.ndarray):
+                store.store.set(np.ascontiguousarray(src, dtype=np.uint16).reshape(store.store.shape))
+            else:
+                store.store.set(as_gpuarray(src).reshape(store.store.shape))
+        return self
+
+    def num_classes(self):
+        return len(self.id_to_color)
+
+    def convert_colors_to_ids(self, labels_color):
+        labels_ids = np.zeros((self.img_dims[1], self.img_dims[0]), dtype=np.uint16)
+        labelled_pixels_count = 0
+        for class_id, color in self.id_to_color.items():
+            pixels_of_color = np.all(labels_color == color, axis=2)
+            labels_ids[pixels_of_color] = class_id
+            labelled_pixels_count += np.sum(pixels_of_color)
+        assert (labelled_pixels_count == self.img_dims[0] * self.img_dims[1])   # every pixel was labelled
+        return labels_ids
+
+    def convert_ids_to_colors(self, labels_ids):
+        num_images, y_dim, x_dim = labels_ids.shape
+        assert y_dim == self.img_dims[1]
+        assert x_dim == self.img_dims[0]
+        labels_colors = np.zeros((num_images, y_dim, x_dim, 4), dtype=np.uint8)
+        for class_id, color in self.id_to_color.items():
+            labels_colors[np.where(labels_ids == class_id)] = color
+        return labels_colors
+
+    def get_depth_block_cu(self, block_num, arr_out):
+        self.depth_blocks.get_block_cu(block_num, arr_out)
+
+    def get_labels_block_cu(self, block_num, arr_out):
+        self.labels_blocks.get_block_cu(block_num, arr_out)
+
+    def num_pixels(self):
+        return self.num_images * self.img_dims[0] * self.img_dims[1]
+
+    def images_shape(self):
+        return (self.num_images, self.img_dims[1], self.img_dims[0])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# proposals (src/decision_tree.py:350-371): same distributions AND the same np.random draw order, so a seeded
+# np.random state yields the reference's proposal stream.
+# ----------------------------------------------------------------------------------------------------------------
+FEATURE_MAGNITUDE_MAX = 14.
+FEATURE_THRESHOLD_MAX = 11.  # _MIN = -_MAX
+
+
+def make_random_offset():
+    f_theta = np.random.uniform(0, np.pi * 2)
+    magnitude = np.power(np.e, np.random.uniform(0, FEATURE_MAGNITUDE_MAX))   # linear in log space
+    return np.array([np.cos(f_theta), np.sin(f_theta)]) * magnitude
+
+
+def make_random_feature():
+    return make_random_offset(), make_random_offset()
+
+
+def make_random_threshold():
+    return np.random.choice([-1, 1]) * np.power(np.e, np.random.uniform(0, FEATURE_THRESHOLD_MAX))
+
+
+def make_random_features(n, arr):
+    for i in range(n):
+        (u, v), t = make_random_feature(), make_random_threshold()
+        arr[i] = (u[0], u[1], v[0], v[1], t)
+
+
+class DecisionTreeTrainer():
+    """src/decision_tree.py:373-601: level-synchronous training of one tree.
+
+    Reference form: every proposal is one (feature, threshold) pair, `NUM_PROPOSALS_PER_PROPOSAL_BLOCK` of them are scored
+    per pass.  `thresholds_per_feature` > 1 switches to the cfg-4 form: a proposal block is P features with
+    that many sorted thresholds each, evaluated once per (pixel, feature).
+    Multi-GPU: when torch.distributed is initialised with world_size > 1, every rank holds a shard of the images and the
+    split histograms are sum-allreduced (NCCL) before pick-best; all ranks then build the identical tree.
+    """
+
+    def __init__(self, NUM_IMAGES_PER_IMAGE_BLOCK, NUM_PROPOSALS_PER_PROPOSAL_BLOCK, thresholds_per_feature=1,
+                 proposal_fn=None, process_group=None, hist_budget_bytes=8 << 30):
+        self._lib = _capi.load()
+        self.NUM_IMAGES_PER_IMAGE_BLOCK = NUM_IMAGES_PER_IMAGE_BLOCK
+        self.NUM_PROPOSALS_PER_PROPOSAL_BLOCK = NUM_PROPOSALS_PER_PROPOSAL_BLOCK
+        self.thresholds_per_feature = int(thresholds_per_feature)
+        self.proposal_fn = proposal_fn
+        self.process_group = process_group
+        self.hist_budget_bytes = int(hist_budget_bytes)
+
+    def allocate(self, dataset, NUM_RANDOM_FEATURES, MAX_TREE_DEPTH):
+        self.NUM_RANDOM_FEATURES = NUM_RANDOM_FEATURES
+        self.MAX_TREE_DEPTH = MAX_TREE_DEPTH
+        if self.NUM_IMAGES_PER_IMAGE_BLOCK is None:
+            self.NUM_IMAGES_PER_IMAGE_BLOCK = dataset.num_images
+        assert dataset.num_images % self.NUM_IMAGES_PER_IMAGE_BLOCK == 0
+        assert self.NUM_RANDOM_FEATURES % self.NUM_PROPOSALS_PER_PROPOSAL_BLOCK == 0
+        self.NUM_IMAGE_BLOCKS = dataset.num_images // self.NUM_IMAGES_PER_IMAGE_BLOCK
+        self.NUM_PROPOSAL_BLOCKS = self.NUM_RANDOM_FEATURES // self.NUM_PROPOSALS_PER_PROPOSAL_BLOCK
+        C = dataset.num_classes()
+        _, self.MAX_LEAF_NODES, _ = DecisionTree.get_config(MAX_TREE_DEPTH, C)
+        P, NT = self.NUM_PROPOSALS_PER_PROPOSAL_BLOCK, self.thresholds_per_feature
+
+        self.node_counts_cu = cu_array.zeros((self.MAX_LEAF_NODES, C), dtype=np.uint64)
+        self.next_node_counts_cu = cu_array.zeros((self.MAX_LEAF_NODES, C), dtype=np.uint64)
+        self.active_nodes_cu = cu_array.zeros((self.MAX_LEAF_NODES,), dtype=np.int32)
+        self.next_active_nodes_cu = cu_array.zeros((self.MAX_LEAF_NODES,), dtype=np.int32)
+        self.next_num_active_nodes_cu = cu_array.zeros((1,), dtype=np.int32)
+        self.get_next_num_active_nodes = lambda: int(self.next_num_active_nodes_cu.get()[0])
+        self.best_gain_seen_per_node = GPUArray((self.MAX_LEAF_NODES,), dtype=np.float32)
+        self.node_slot_cu = GPUArray((self.MAX_LEAF_NODES,), dtype=np.int32)
+        self.current_offsets = GPUArray((P, 4), dtype=np.float32)
+        self.current_thresholds = GPUArray((P, NT), dtype=np.float32)
+        self.current_proposals_block_cpu = np.zeros((P, 5), dtype=np.float32)
+
+        # whole dataset resident: nodes_by_pixel int32[N,H,W] (the reference keeps it nvcomp-compressed per block)
+        self.nodes_by_pixel = GPUArray(dataset.images_shape(), dtype=np.int32)
+        per_slot = P * (NT + 1) * C * 4
+        self.MAX_SLOTS_PER_BLOCK = int(max(1, min(self.MAX_LEAF_NODES // 2 or 1, self.hist_budget_bytes // per_slot)))
+        self.hist_cu = GPUArray((self.MAX_SLOTS_PER_BLOCK, P, NT + 1, C), dtype=np.uint32)
+
+    # -- proposal stream -------------------------------------------------------------------------------------
+    def _next_proposals(self, level, block):
+        P, NT = self.NUM_PROPOSALS_PER_PROPOSAL_BLOCK, self.thresholds_per_feature
+        if self.proposal_fn is not None:
+            offsets, thresholds = self.proposal_fn(level, block)
+            offsets = np.ascontiguousarray(offsets, dtype=np.float32).reshape(P, 4)
+            thresholds = np.ascontiguousarray(thresholds, dtype=np.float32).reshape(P, NT)
+        elif NT == 1:
+            make_random_features(P, self.current_proposals_block_cpu)          # src/decision_tree.py:487
+            offsets = np.ascontiguousarray(self.current_proposals_block_cpu[:, 0:4])
+            thresholds = np.ascontiguousarray(self.current_proposals_block_cpu[:, 4:5])
+        else:
+            offsets = np.zeros((P, 4), dtype=np.float32)
+            thresholds = np.zeros((P, NT), dtype=np.float32)
+            for i in range(P):
+                u, v = make_random_feature()
+                offsets[i] = (u[0], u[1], v[0], v[1])
+                thresholds[i] = np.sort(np.array([make_random_threshold() for _ in range(NT)], dtype=np.float32))
+        return offsets, thresholds
+
+    def _dist(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1:
+            return dist
+        return None
+
+    def train(self, dataset, tree):
+        lib, st = self._lib, _capi.stream_ptr
+        C = dataset.num_classes()
+        D = self.MAX_TREE_DEPTH
+        P, NT = self.NUM_PROPOSALS_PER_PROPOSAL_BLOCK, self.thresholds_per_feature
+        W, H = dataset.img_dims
+        N = dataset.num_images
+        dist = self._dist()
+        depth = dataset.depth_blocks.store.reshape((N, H, W))
+        labels = dataset.labels_blocks.store.reshape((N, H, W))
+
+        tree.tree_out_cu.fill(np.float32(0.))
+        # root statistics + nodes_by_pixel = 0 where labelled else -1 (src/decision_tree.py:450-467)
+        self.node_counts_cu.fill(0)
+        _capi.check(lib.rdf_train_init(_capi.dptr(labels), N * H * W, C, _capi.dptr(self.nodes_by_pixel),
+                                       _capi.dptr(self.node_counts_cu), st()))
+        if dist is not None:
+            root = self.node_counts_cu.tensor[0].view(torch.int64)
+            dist.all_reduce(root, group=self.process_group)
+        self.active_nodes_cu.fill(np.int32(0))
+        self.next_num_active_nodes_cu.fill(np.int32(1))
+
+        for current_level in range(D):
+            num_active_nodes = self.get_next_num_active_nodes()                 # one D2H sync per level (:479)
+            if num_active_nodes == 0:
+                break
+            self.best_gain_seen_per_node.fill(np.float32(-1.))
+            active_host = self.active_nodes_cu.tensor[:num_active_nodes].cpu().numpy()
+            slot_blocks = [active_host[i:i + self.MAX_SLOTS_PER_BLOCK] for i in range(0, num_active_nodes, self.MAX_SLOTS_PER_BLOCK)]
+            num_nodes_level = 1 << current_level
+
+            for proposal_block_idx in range(self.NUM_PROPOSAL_BLOCKS):
+                offsets, thresholds = self._next_proposals(current_level, proposal_block_idx)
+                self.current_offsets.set(offsets)
+                self.current_thresholds.set(thresholds)
+                for nodes_in_block in slot_blocks:
+                    S = len(nodes_in_block)
+                    slot_host = np.full((num_nodes_level,), -1, dtype=np.int32)
+                    slot_host[nodes_in_block] = np.arange(S, dtype=np.int32)
+                    self.node_slot_cu[:num_nodes_level].set(slot_host)
+                    hist = self.hist_cu[:S]
+                    hist.fill(0)
+                    _capi.check(lib.rdf_train_hist(_capi.dptr(depth), _capi.dptr(labels), _capi.dptr(self.nodes_by_pixel),
+                                                   N, W, H, _capi.dptr(self.node_slot_cu), S, _capi.dptr(self.current_offsets),
+                                                   _capi.dptr(self.current_thresholds), P, NT, C, _capi.dptr(hist), st()))
+                    if dist is not None:                                       # the path's only exchange step
+                        dist.all_reduce(hist.tensor.view(torch.int32), group=self.process_group)
+                    _capi.check(lib.rdf_train_pick_best(num_active_nodes, _capi.dptr(self.active_nodes_cu),
+                                                        _capi.dptr(self.node_slot_cu), _capi.dptr(self.node_counts_cu),
+                                                        _capi.dptr(hist), S, _capi.dptr(self.current_offsets),
+                                                        _capi.dptr(self.current_thresholds), P, NT, C, current_level, D,
+                                                        _capi.dptr(tree.tree_out_cu), _capi.dptr(self.next_node_counts_cu),
+                                                        _capi.dptr(self.best_gain_seen_per_node), st()))
+
+            _capi.check(lib.rdf_train_next_active(_capi.dptr(tree.tree_out_cu), current_level, D, C,
+                                                  _capi.dptr(self.active_nodes_cu), num_active_nodes,
+                                                  _capi.dptr(self.next_active_nodes_cu),
+                                                  _capi.dptr(self.next_num_active_nodes_cu), st()))
+            if current_level == D - 1:
+                break
+            self.node_counts_cu.set(self.next_node_counts_cu)                   # :574
+            _capi.check(lib.rdf_train_advance_pixels(_capi.dptr(depth), _capi.dptr(self.nodes_by_pixel), N, W, H,
+                                                     _capi.dptr(tree.tree_out_cu), current_level, D, C, st()))
+            self.active_nodes_cu.set(self.next_active_nodes_cu)                 # :598

@@ -1,0 +1,48 @@
+"""Mean-shift mode finding per label class: mirror of the reference's src/cuda/mean_shift.py over rdf_mean_shift.
+
+All rounds run in one launch of a thread-block cluster (csrc/rdf_meanshift.cu); the only host transfer is the final
+K x 2 float64 result, where the reference makes 2 blocking D2H + 1 H2D copies per round (mean_shift.py:50-55)."""
+import ctypes
+
+import numpy as np
+
+from . import _capi
+from .buffers import GPUArray, as_gpuarray
+
+
+class MeanShift:
+    def __init__(self):
+        self._lib = _capi.load()
+        self.means = None           # float64[num_labels, 2] on the device, as in the reference
+        self._workspace = None
+        self._variances = None
+
+    def _ensure(self, num_labels, dim_x, dim_y):
+        if self.means is None or self.means.shape != (num_labels, 2):
+            self.means = GPUArray((num_labels, 2), dtype=np.float64)
+        need = ctypes.c_size_t()
+        _capi.check(self._lib.rdf_mean_shift_workspace_bytes(dim_x, dim_y, num_labels, ctypes.byref(need)))
+        if self._workspace is None or self._workspace.nbytes < need.value:
+            self._workspace = GPUArray(((need.value + 3) // 4,), dtype=np.uint32)
+
+    def run_async(self, num_rounds, labels, num_labels, variances):
+        """Enqueue the whole mean shift on the current stream; returns the device array float64[num_labels,2]."""
+        labels = as_gpuarray(labels)
+        assert labels.dtype == np.uint16
+        dim_y, dim_x = labels.shape[-2:]
+        if isinstance(variances, np.ndarray):
+            if self._variances is None or self._variances.shape != variances.shape:
+                self._variances = GPUArray(variances.shape, dtype=np.float32)
+            self._variances.set(np.ascontiguousarray(variances, dtype=np.float32))
+            variances = self._variances
+        variances = as_gpuarray(variances)
+        assert variances.dtype == np.float32 and variances.size >= num_labels
+        self._ensure(num_labels, dim_x, dim_y)
+        _capi.check(self._lib.rdf_mean_shift(_capi.dptr(labels), dim_x, dim_y, int(num_labels), _capi.dptr(variances),
+                                             int(num_rounds), _capi.dptr(self.means), _capi.dptr(self._workspace),
+                                             self._workspace.nbytes, _capi.stream_ptr()))
+        return self.means
+
+    def run(self, num_rounds, labels, num_labels, variances):
+        """src/cuda/mean_shift.py:19-59: returns np.float64[num_labels, 2] = (x, y); NaN rows for classes without pixels."""
+        return self.run_async(num_rounds, labels, num_labels, variances).get()

@@ -1,0 +1,167 @@
+/*
+ * rdf_b200.h - C ABI of librdf_b200.so: the B200-native (sm_100a) implementation of the per-pixel randomized
+ * decision forest hot path of carsonswope/3d-beats.
+ *
+ * The reference has no C ABI: its operator boundary is pycuda's
+ *     module.get_function("<extern C kernel>")(np scalars, GPUArrays, grid=, block=, shared=)
+ * (src/cuda/py_nvcc_utils.py:25-37, src/decision_tree.py:269-272,315-330).  Every entry point below replaces one
+ * such kernel fetch + launch (cited per function).  All pointers marked `dev` are CUDA device pointers owned by
+ * the caller; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative rdf_status on failure; rdf_last_error() returns a
+ *     thread-local, human-readable message for the last failure on the calling thread.
+ *   - every launch is asynchronous on `stream`; nothing here allocates or synchronises after handle creation, so
+ *     all eval / layered / mean-shift / train calls are CUDA-graph capturable.
+ *   - images are C-contiguous: depth uint16[N,H,W]; label maps uint16[N,H/r,W/r] with r = labels_reduce.
+ *   - 65535 is the "no pixel" sentinel in depth and label images (src/cuda/cu_utils.hpp:8).
+ *   - outputs are NEVER written for skipped pixels (filter mismatch, centre depth 0 or 65535) - callers pre-fill,
+ *     exactly as with the reference kernels (src/run_live.py:123, src/test_on_saved_model.py:55).
+ *   - no CPU fallback exists: without a CUDA device every compute entry point fails with RDF_ERR_CUDA.
+ */
+#ifndef RDF_B200_H
+#define RDF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RDF_B200_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define RDF_API __attribute__((visibility("default")))
+#else
+#define RDF_API
+#endif
+
+typedef enum rdf_status {
+    RDF_OK = 0,
+    RDF_ERR_INVALID = -1,      /* bad argument (null pointer, non-positive size, unsupported shape) */
+    RDF_ERR_CUDA = -2,         /* a CUDA runtime call or launch failed; message holds cudaGetErrorString */
+    RDF_ERR_UNSUPPORTED = -3   /* valid request outside the compiled limits (see RDF_MAX_*) */
+} rdf_status;
+
+#define RDF_MAX_CLASSES 256    /* classes per forest, including class 0 = none */
+#define RDF_MAX_LAYERS 8       /* layers in a stacked forest */
+#define RDF_MAX_DEPTH 26       /* tree levels */
+
+typedef struct rdf_forest rdf_forest_t; /* opaque: packed device copy of a forest */
+
+RDF_API int rdf_version(void);
+RDF_API const char* rdf_last_error(void);
+
+/* ---- forest container ------------------------------------------------------------------------------------
+ * Replaces DecisionForest.__init__/.load's `forest_cu` as the thing kernels read (src/decision_tree.py:146-168).
+ * canon_dev: float32[T, 2^D-1, 7+2C] canonical layout (node = ux,uy,vx,vy,thresh,l_next,r_next,l_pdf[C],r_pdf[C];
+ * src/cuda/tree_eval.cu:47, node addressing src/cuda/cu_utils.hpp:32-39).  The handle owns a packed shadow
+ * (32-byte node headers + 16-byte aligned leaf pdf rows); the caller keeps ownership of canon_dev.
+ * rdf_forest_update re-packs after the caller mutated canon_dev (e.g. forest_cu.set(...), src/train_model.py:126). */
+RDF_API int rdf_forest_create(const float* canon_dev, int num_trees, int max_depth, int num_classes, void* stream,
+                      rdf_forest_t** out);
+RDF_API int rdf_forest_update(rdf_forest_t* forest, const float* canon_dev, void* stream);
+RDF_API int rdf_forest_destroy(rdf_forest_t* forest);
+RDF_API int rdf_forest_info(const rdf_forest_t* forest, int* num_trees, int* max_depth, int* num_classes,
+                    size_t* packed_bytes);
+
+/* ---- evaluation -----------------------------------------------------------------------------------------
+ * rdf_eval_forest replaces kernel `evaluate_image_using_forest` (src/cuda/tree_eval.cu:24-137) and its host
+ * launch DecisionTreeEvaluator.get_labels_forest (src/decision_tree.py:298-330).
+ *   filter_dev   uint16[N,h,w] or NULL; a pixel is evaluated only if filter == filter_class (ignored when
+ *                filter_dev is NULL or filter_class == -1; the reference passes a dummy pointer and -1).
+ *   labels_dev   uint16[N,h,w], h = H/labels_reduce, w = W/labels_reduce; labels pixel (x,y) samples depth (x*r,y*r).
+ *   probs_dev    optional float32[N,h,w,C]: mean over trees of the reached leaf pdfs (sum in tree order / T);
+ *                NULL to skip.  Not part of the reference; written only for evaluated pixels.
+ *   scale        uv_scale of compute_feature (src/cuda/decision_tree_common.hpp:8-28).
+ * Label = first class with the strictly greatest summed pdf > 0, else 0 (src/cuda/tree_eval.cu:7-21); pdf sums are
+ * accumulated in tree order 0..T-1. */
+RDF_API int rdf_eval_forest(const rdf_forest_t* forest, const uint16_t* depth_dev, int num_images, int dim_x, int dim_y,
+                    const uint16_t* filter_dev, int filter_class, uint16_t* labels_dev, float* probs_dev,
+                    int labels_reduce, float scale, void* stream);
+
+/* Same contract as rdf_eval_forest, reading the canonical array float32[T,2^D-1,7+2C] directly (no handle, any
+ * number of trees): the path for forests with more than 8 trees, which the packed fast path does not cover. */
+RDF_API int rdf_eval_forest_canonical(const float* forest_dev, int num_trees, int max_depth, int num_classes,
+                              const uint16_t* depth_dev, int num_images, int dim_x, int dim_y,
+                              const uint16_t* filter_dev, int filter_class, uint16_t* labels_dev, float* probs_dev,
+                              int labels_reduce, float scale, void* stream);
+
+/* rdf_eval_tree replaces kernel `evaluate_image_using_tree` (src/cuda/tree_eval.cu:140-212) / get_labels
+ * (src/decision_tree.py:277-294): one tree straight from the canonical layout float32[2^D-1,7+2C], scale 1,
+ * labels_reduce 1; a pixel whose walk falls off the last level is not written. */
+RDF_API int rdf_eval_tree(const float* tree_dev, int max_depth, int num_classes, const uint16_t* depth_dev, int num_images,
+                  int dim_x, int dim_y, uint16_t* labels_dev, void* stream);
+
+/* rdf_composite replaces kernel `make_composite_labels_image` (src/cuda/tree_eval.cu:214-248) and its wrapper
+ * (src/decision_tree.py:333-347).  label_images_dev: DEVICE array of L device pointers (the reference's int64
+ * pointer table, src/decision_tree.py:203-207); conditions_dev int32[n_cond,2]; composite_dev uint16[dim_y,dim_x]. */
+RDF_API int rdf_composite(const uint16_t* const* label_images_dev, int num_label_images, int dim_x, int dim_y,
+                  const int32_t* conditions_dev, uint16_t* composite_dev, void* stream);
+
+/* rdf_layered_run replaces the whole of LayeredDecisionForest.run (src/decision_tree.py:233-264): 1+L fills,
+ * L evaluate_image_using_forest launches and make_composite_labels_image, in ONE launch.  Layer i is gated by
+ * layer filter_model[i]'s label == filter_class[i] (filter_model[i] < 0: ungated); the gate is read from registers,
+ * never from memory.  Every pixel of every per-layer image and of the composite is written (65535 where the
+ * reference's pre-fill would have survived), so no pre-fill is needed.
+ *   forests, filter_model, filter_class, labels_per_layer: HOST arrays of length L (labels_per_layer holds device
+ *   pointers to uint16[h,w]);  depth_dev uint16[H,W];  composite_dev uint16[h,w]. */
+RDF_API int rdf_layered_run(const rdf_forest_t* const* forests, int num_layers, const int* filter_model,
+                    const int* filter_class, const uint16_t* depth_dev, int dim_x, int dim_y,
+                    uint16_t* const* labels_per_layer, const int32_t* conditions_dev, int n_cond,
+                    uint16_t* composite_dev, int labels_reduce, float scale, void* stream);
+
+/* ---- mean shift -----------------------------------------------------------------------------------------
+ * rdf_mean_shift replaces MeanShift.run (src/cuda/mean_shift.py:19-59): per round 1 fill + kernel `run`
+ * (src/cuda/mean_shift.cu:3-48) + 2 blocking D2H + host divide + H2D, all `rounds` rounds in ONE launch with no
+ * host round trip.  labels_dev uint16[h,w]; variances_dev float32[K]; means_dev float64[K,2] = (x,y) per class,
+ * NaN for classes without pixels.  Sums are fp64 and deterministic (fixed reduction order).
+ * workspace_dev: caller-provided scratch of at least rdf_mean_shift_workspace_bytes(w,h,K) bytes. */
+RDF_API int rdf_mean_shift_workspace_bytes(int dim_x, int dim_y, int num_labels, size_t* bytes);
+RDF_API int rdf_mean_shift(const uint16_t* labels_dev, int dim_x, int dim_y, int num_labels, const float* variances_dev,
+                   int rounds, double* means_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- synthetic inputs (bench / tests; bit-exact twins of rdf_b200/synth.py) -------------------------------
+ * kind: 0 dense-smooth, 1 dense-noise, 2 live-mask.  Frames first_frame .. first_frame+N-1. */
+RDF_API int rdf_synth_depth(uint16_t* depth_dev, int kind, int num_images, int dim_x, int dim_y, uint32_t seed,
+                    int first_frame, void* stream);
+RDF_API int rdf_synth_forest(float* canon_dev, int num_trees, int max_depth, int num_classes, uint32_t seed, void* stream);
+
+/* ---- training split search --------------------------------------------------------------------------------
+ * Level-synchronous training of one tree (DecisionTreeTrainer.train, src/decision_tree.py:444-601).
+ *
+ * rdf_train_hist replaces kernel `evaluate_random_features` (src/cuda/tree_train.cu:4-64), generalised to NT sorted
+ * thresholds per feature (the reference is NT = 1): one feature evaluation per (pixel, feature), then
+ *     hist[slot][feature][bin][label] += 1,  bin = #{k : thresholds[feature][k] <= f}  in 0..NT
+ * so the reference's left child for threshold k (f < t_k) is bins 0..k.
+ *   nodes_by_pixel_dev int32[N,H,W] (-1 = inactive, else node index within the current level);
+ *   node_slot_dev int32[2^level]: node index -> histogram slot, or -1 (node not in this block);
+ *   offsets_dev float32[F,4] (ux,uy,vx,vy); thresholds_dev float32[F,NT] ascending;
+ *   hist_dev uint32[num_slots,F,NT+1,C], ACCUMULATED into (zero it first; multi-GPU: allreduce it afterwards).
+ * rdf_train_pick_best replaces `pick_best_features` (src/cuda/tree_train.cu:99-236) incl. the Gini helpers (:66-97),
+ *   reading hist_dev; candidate order is feature-major, threshold-minor; first strictly greatest gain wins.
+ * rdf_train_next_active replaces `get_active_nodes_next_level` (:238-273) with a deterministic (ascending) order.
+ * rdf_train_advance_pixels replaces `copy_pixel_groups` (:275-324). */
+RDF_API int rdf_train_hist(const uint16_t* depth_dev, const uint16_t* labels_dev, const int32_t* nodes_by_pixel_dev,
+                   int num_images, int dim_x, int dim_y, const int32_t* node_slot_dev, int num_slots,
+                   const float* offsets_dev, const float* thresholds_dev, int num_features, int num_thresholds,
+                   int num_classes, uint32_t* hist_dev, void* stream);
+RDF_API int rdf_train_pick_best(int num_active, const int32_t* active_nodes_dev, const int32_t* node_slot_dev,
+                        const uint64_t* parent_counts_dev, const uint32_t* hist_dev, int num_slots,
+                        const float* offsets_dev, const float* thresholds_dev, int num_features, int num_thresholds,
+                        int num_classes, int level, int max_depth, float* tree_dev, uint64_t* next_counts_dev,
+                        float* best_gain_dev, void* stream);
+RDF_API int rdf_train_next_active(const float* tree_dev, int level, int max_depth, int num_classes,
+                          const int32_t* active_nodes_dev, int num_active, int32_t* next_active_dev,
+                          int32_t* num_next_active_dev, void* stream);
+RDF_API int rdf_train_advance_pixels(const uint16_t* depth_dev, int32_t* nodes_by_pixel_dev, int num_images, int dim_x,
+                             int dim_y, const float* tree_dev, int level, int max_depth, int num_classes, void* stream);
+/* root statistics (src/decision_tree.py:452-467): node_counts[0][label] and nodes_by_pixel = (label > 0 ? 0 : -1) */
+RDF_API int rdf_train_init(const uint16_t* labels_dev, int64_t num_pixels, int num_classes, int32_t* nodes_by_pixel_dev,
+                   uint64_t* root_counts_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RDF_B200_H */

@@ -1,0 +1,194 @@
+"""GPU parity of forest / tree evaluation through the C ABI: bit-exact label maps against the NumPy oracle, the C oracle
+and the reference's own kernels (oracle/_ref), on the same seeded synthetic inputs."""
+import numpy as np
+import pytest
+
+from conftest import to_dev, to_np, filled_u16
+
+pytestmark = pytest.mark.gpu
+
+
+def _api():
+    from rdf_b200 import decision_tree as dt
+    return dt
+
+
+def _run_ours(forest_np, depth_np, labels_reduce=1, filt=None, fclass=None, scale=1.0, want_probs=False, prefill=65535):
+    import torch
+    dt = _api()
+    T, NN, E = forest_np.shape
+    D = int(np.log2(NN + 1)); C = (E - 7) // 2
+    f = dt.DecisionForest(T, D, C)
+    f.forest_cu.set(forest_np)
+    ev = dt.DecisionTreeEvaluator()
+    N, H, W = depth_np.shape
+    labels = filled_u16((N, H // labels_reduce, W // labels_reduce), prefill)
+    probs = torch.zeros((N, H // labels_reduce, W // labels_reduce, C), dtype=torch.float32, device='cuda') if want_probs else None
+    ev.get_labels_forest(f, to_dev(depth_np), labels, labels_reduce=labels_reduce,
+                         filter_images=to_dev(filt) if filt is not None else None, filter_images_class=fclass,
+                         scale_factor=scale, probs_out=probs)
+    torch.cuda.synchronize()
+    return to_np(labels), (probs.cpu().numpy() if want_probs else None)
+
+
+@pytest.mark.parametrize('kind', ['dense-smooth', 'dense-noise', 'live-mask'])
+@pytest.mark.parametrize('T,D,C', [(3, 10, 4), (1, 6, 3), (4, 9, 11), (8, 7, 5), (5, 8, 2)])
+@pytest.mark.parametrize('ragged', [False, True])
+def test_forest_matches_oracles(kind, T, D, C, ragged):
+    from rdf_b200 import synth
+    from oracle import numpy_oracle as no, c_oracle as co
+    depth = synth.depth_frames(kind, 2, 96, 160, seed=7)
+    forest = synth.random_forest(T, D, C, seed=11, ragged=ragged)
+    ours, probs = _run_ours(forest, depth, want_probs=True)
+    exp = np.full(ours.shape, 65535, np.uint16)
+    exp_p = np.zeros(ours.shape + (C,), np.float32)
+    no.eval_forest(forest, depth, exp, probs_out=exp_p)
+    exp_c = np.full(ours.shape, 65535, np.uint16)
+    co.eval_forest(forest, depth, exp_c)
+    assert np.array_equal(exp, exp_c)
+    assert np.array_equal(ours, exp)                       # bit-exact labels
+    assert np.abs(probs - exp_p).max() <= 1e-5             # leaf-probability maps: 1e-5 absolute (north_star)
+
+
+@pytest.mark.parametrize('r,scale', [(1, 1.0), (2, 0.5), (2, 1.0), (3, 0.37)])
+def test_labels_reduce_and_scale(r, scale):
+    from rdf_b200 import synth
+    from oracle import c_oracle as co
+    depth = synth.depth_frames('dense-smooth', 1, 121, 213, seed=3)     # ragged sizes: not multiples of the tile or of r
+    forest = synth.random_forest(3, 11, 4, seed=5, ragged=True)
+    ours, _ = _run_ours(forest, depth, labels_reduce=r, scale=scale)
+    exp = np.full(ours.shape, 65535, np.uint16)
+    co.eval_forest(forest, depth, exp, labels_reduce=r, scale=scale)
+    assert np.array_equal(ours, exp)
+
+
+def test_filter_and_skip_semantics():
+    """Filtered-out pixels and pixels with centre depth 0 / 65535 keep the caller's pre-fill (tree_eval.cu:81-89)."""
+    from rdf_b200 import synth
+    from oracle import numpy_oracle as no
+    depth = synth.depth_frames('dense-noise', 1, 64, 96, seed=9)
+    depth[0, 5:20, 7:30] = 0
+    depth[0, 30:40, 50:90] = 65535
+    forest = synth.random_forest(3, 8, 4, seed=2)
+    rng = np.random.default_rng(0)
+    filt = rng.integers(0, 3, size=(1, 64, 96)).astype(np.uint16)
+    ours, _ = _run_ours(forest, depth, filt=filt, fclass=1, prefill=12345)
+    exp = np.full(ours.shape, 12345, np.uint16)
+    no.eval_forest(forest, depth, exp, filter_images=filt, filter_class=1)
+    assert np.array_equal(ours, exp)
+    assert (ours[0, 5:20, 7:30] == 12345).all() and (ours[0, 30:40, 50:90] == 12345).all()
+    assert (ours[filt != 1] == 12345).all()
+
+
+def test_zero_forest_gives_label_zero():
+    """Zero-initialised nodes: floor(0) != -1 so both sides are leaves with an all-zero pdf -> label 0 (SURVEY note N2)."""
+    from rdf_b200 import synth
+    depth = synth.depth_frames('dense-smooth', 1, 32, 48)
+    forest = np.zeros((3, 31, 7 + 8), np.float32)
+    ours, _ = _run_ours(forest, depth)
+    assert (ours == 0).all()
+
+
+def test_special_float_nodes():
+    """NaN / inf / denormal offsets and thresholds follow cvt.rmi + IEEE divide exactly like the oracle."""
+    from rdf_b200 import synth
+    from oracle import numpy_oracle as no
+    depth = synth.depth_frames('dense-noise', 1, 48, 64, seed=4)
+    forest = synth.random_forest(2, 6, 3, seed=8)
+    rng = np.random.default_rng(1)
+    specials = np.array([np.nan, np.inf, -np.inf, 1e-42, -1e-42, 0.0, -0.0, 3e38, -3e38, 0.5, -0.5], np.float32)
+    sel = rng.random(forest[:, :, 0:5].shape) < 0.2
+    forest[:, :, 0:5][sel] = rng.choice(specials, size=int(sel.sum()))
+    ours, _ = _run_ours(forest, depth)
+    exp = np.full(ours.shape, 65535, np.uint16)
+    no.eval_forest(forest, depth, exp)
+    assert np.array_equal(ours, exp)
+
+
+def test_many_trees_uses_canonical_path():
+    from rdf_b200 import synth
+    from oracle import c_oracle as co
+    depth = synth.depth_frames('dense-smooth', 1, 40, 72)
+    forest = synth.random_forest(12, 6, 4, seed=6, ragged=True)
+    ours, _ = _run_ours(forest, depth, labels_reduce=2, scale=0.5)
+    exp = np.full(ours.shape, 65535, np.uint16)
+    co.eval_forest(forest, depth, exp, labels_reduce=2, scale=0.5)
+    assert np.array_equal(ours, exp)
+
+
+@pytest.mark.parametrize('ragged', [False, True])
+def test_single_tree(ragged):
+    import torch
+    from rdf_b200 import synth
+    from oracle import numpy_oracle as no
+    dt = _api()
+    depth = synth.depth_frames('live-mask', 2, 60, 100, seed=5)
+    forest = synth.random_forest(1, 9, 5, seed=3, ragged=ragged)
+    if ragged:
+        forest[0, -64:, 5:7] = -1.0            # some walks fall off the last level: those pixels stay untouched
+    tree = dt.DecisionTree(9, 5)
+    tree.tree_out_cu.set(forest[0])
+    labels = filled_u16((2, 60, 100), 777)
+    dt.DecisionTreeEvaluator().get_labels(tree, to_dev(depth), labels)
+    torch.cuda.synchronize()
+    exp = np.full((2, 60, 100), 777, np.uint16)
+    no.eval_tree(forest[0], depth, exp)
+    assert np.array_equal(to_np(labels), exp)
+
+
+def test_forest_update_after_mutation():
+    """forest_cu.set(...) after first use must be picked up (packed shadow is re-packed)."""
+    import torch
+    from rdf_b200 import synth
+    from oracle import c_oracle as co
+    dt = _api()
+    depth = synth.depth_frames('dense-smooth', 1, 48, 80)
+    f = dt.DecisionForest(3, 8, 4)
+    ev = dt.DecisionTreeEvaluator()
+    for seed in (1, 2):
+        forest = synth.random_forest(3, 8, 4, seed=seed)
+        f.forest_cu.set(forest)
+        labels = filled_u16((1, 48, 80))
+        ev.get_labels_forest(f, to_dev(depth), labels)
+        torch.cuda.synchronize()
+        exp = np.full((1, 48, 80), 65535, np.uint16)
+        co.eval_forest(forest, depth, exp)
+        assert np.array_equal(to_np(labels), exp)
+
+
+def test_cfg1_full_size_vs_c_oracle_and_reference():
+    """BASELINE config 1: one 848x480 frame, 3-tree depth-16 forest, 4 classes."""
+    import torch
+    from rdf_b200 import synth
+    from oracle import c_oracle as co, ref_kernels as rk
+    depth = synth.depth_frames('dense-smooth', 1, 480, 848)
+    forest = synth.random_forest(3, 16, 4)
+    ours, probs = _run_ours(forest, depth, want_probs=True)
+    exp = np.full(ours.shape, 65535, np.uint16)
+    exp_p = np.zeros(ours.shape + (4,), np.float32)
+    co.eval_forest(forest, depth, exp, probs_out=exp_p)
+    assert np.array_equal(ours, exp)
+    assert np.abs(probs - exp_p).max() <= 1e-5
+    assert len(np.unique(ours)) == 4                        # non-degenerate label map
+    if rk.available():
+        ref = filled_u16((1, 480, 848))
+        rk.eval_forest(to_dev(forest), to_dev(depth), ref)
+        torch.cuda.synchronize()
+        assert np.array_equal(to_np(ref), ours)            # bit-exact against the reference's own kernel
+
+
+def test_error_paths():
+    import torch
+    dt = _api()
+    from rdf_b200 import _capi
+    lib = _capi.load()
+    rc = lib.rdf_eval_forest(None, None, 1, 8, 8, None, -1, None, None, 1, 1.0, None)
+    assert rc == -1 and b'NULL' in lib.rdf_last_error()
+    with pytest.raises(ValueError):
+        _capi.check(rc)
+    f = dt.DecisionForest(2, 3, 2)
+    ev = dt.DecisionTreeEvaluator()
+    with pytest.raises(AssertionError):                     # the reference's shape asserts are kept
+        ev.get_labels_forest(f, filled_u16((1, 8, 8), 1000), filled_u16((1, 4, 8)))
+    with pytest.raises(ValueError):
+        ev.get_labels_forest(f, torch.zeros((1, 8, 8), dtype=torch.int16).view(torch.uint16), filled_u16((1, 8, 8)))  # CPU tensor

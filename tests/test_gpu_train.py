@@ -1,0 +1,125 @@
+"""GPU parity of the training split search: histograms bit-exact vs the C oracle, best split / tree vs the NumPy oracle and
+the reference's own training kernels."""
+import numpy as np
+import pytest
+
+from conftest import to_dev, to_np
+
+pytestmark = pytest.mark.gpu
+
+
+def _hist_ours(depth, labels, nodes, node_slot, S, offsets, thresholds, C):
+    import torch
+    from rdf_b200 import _capi
+    lib = _capi.load()
+    N, H, W = depth.shape
+    F, NT = thresholds.shape
+    hist = torch.zeros((S, F, NT + 1, C), dtype=torch.int32, device='cuda')
+    args = [to_dev(depth), to_dev(labels), to_dev(nodes), to_dev(node_slot), to_dev(offsets), to_dev(thresholds)]
+    _capi.check(lib.rdf_train_hist(_capi.dptr(args[0]), _capi.dptr(args[1]), _capi.dptr(args[2]), N, W, H, _capi.dptr(args[3]), S,
+                                   _capi.dptr(args[4]), _capi.dptr(args[5]), F, NT, C, _capi.dptr(hist), _capi.stream_ptr()))
+    torch.cuda.synchronize()
+    return hist.cpu().numpy().view(np.uint32)
+
+
+@pytest.mark.parametrize('level,NT,F', [(0, 64, 24), (3, 64, 20), (6, 8, 40), (9, 1, 64)])
+def test_hist_matches_c_oracle(level, NT, F):
+    from rdf_b200 import synth
+    from oracle import c_oracle as co
+    N, H, W, C = 3, 96, 128, 4
+    depth = synth.depth_frames('dense-smooth', N, H, W, seed=2)
+    depth[0, 10:20, 10:20] = 0                                   # d == 0 -> feature 0.0 (reachable in training)
+    labels = synth.train_labels(N, H, W)
+    labels[1, 40:50, :] = 0                                      # unlabelled pixels are inactive
+    nodes = synth.random_node_assignment(labels, level, seed=5)
+    n_nodes = 1 << level
+    # only every other node gets a slot when there are many (exercises the -1 slot path)
+    node_slot = np.full(n_nodes, -1, np.int32)
+    chosen = np.arange(0, n_nodes, 2 if n_nodes > 4 else 1)
+    node_slot[chosen] = np.arange(len(chosen), dtype=np.int32)
+    S = len(chosen)
+    offsets, thresholds = synth.random_proposals(F, NT, seed=9)
+    got = _hist_ours(depth, labels, nodes, node_slot, S, offsets, thresholds, C)
+    exp = co.train_hist(depth, labels, nodes, node_slot, S, offsets, thresholds, C)
+    assert np.array_equal(got, exp)
+    # conservation (the reference asserts left + right == parent, tree_train.cu:156): every feature sees every pixel once
+    per_slot = np.array([np.count_nonzero((nodes >= 0) & (node_slot[np.maximum(nodes, 0)] == s)) for s in range(S)])
+    assert np.array_equal(got.sum(axis=(2, 3)), np.repeat(per_slot[:, None], F, axis=1))
+
+
+def _proposal_stream(seed, P, blocks, levels):
+    rng = np.random.default_rng(seed)
+    out = {}
+    for lvl in range(levels):
+        out[lvl] = []
+        for _ in range(blocks):
+            from rdf_b200 import synth
+            off, th = synth.random_proposals(P, 1, seed=int(rng.integers(1 << 30)))
+            out[lvl].append(np.concatenate([off, th], axis=1).astype(np.float32))
+    return out
+
+
+@pytest.mark.parametrize('D,P,blocks', [(5, 32, 2), (7, 64, 1)])
+def test_trained_tree_matches_oracle_and_reference(D, P, blocks):
+    """Whole-tree training in reference form (one threshold per proposal): identical canonical tree."""
+    import torch
+    from rdf_b200 import synth
+    from rdf_b200 import decision_tree as dt
+    from oracle import numpy_oracle as no, ref_kernels as rk
+    N, H, W, C = 2, 64, 96, 4
+    depth = synth.depth_frames('dense-smooth', N, H, W, seed=12)
+    labels = synth.train_labels(N, H, W)
+    labels[0, :8, :] = 0
+    stream = _proposal_stream(77, P, blocks, D)
+
+    ds = dt.DecisionTreeDatasetConfig.from_arrays(depth, labels, C)
+    trainer = dt.DecisionTreeTrainer(N, P, proposal_fn=lambda lvl, b: (stream[lvl][b][:, 0:4], stream[lvl][b][:, 4:5]))
+    trainer.allocate(ds, P * blocks, D)
+    tree = dt.DecisionTree(D, C)
+    trainer.train(ds, tree)
+    torch.cuda.synchronize()
+    ours = tree.tree_out_cu.get()
+
+    exp = no.train_tree(depth, labels, C, D, lambda lvl: stream[lvl])
+    _assert_same_tree(ours, exp, 'numpy oracle')
+    if rk.available():
+        ref = rk.train_tree(to_dev(depth), to_dev(labels), C, D, lambda lvl: stream[lvl])
+        _assert_same_tree(ours, ref, 'reference kernels')
+    # the trained tree classifies its own training pixels better than chance
+    out = torch.full((N, H, W), -1, dtype=torch.int16, device='cuda').view(torch.uint16)
+    dt.DecisionTreeEvaluator().get_labels(tree, to_dev(depth), out)
+    acc = (to_np(out) == labels)[labels > 0].mean()
+    assert acc > 0.4                                            # chance is 1/3
+
+
+def _assert_same_tree(a, b, who):
+    same_split = np.array_equal(a[:, 0:7], b[:, 0:7])
+    if not same_split:
+        bad = np.nonzero((a[:, 0:7] != b[:, 0:7]).any(axis=1))[0]
+        raise AssertionError(f'split records differ from {who} at rows {bad[:10]} (of {len(bad)})')
+    assert np.abs(a[:, 7:] - b[:, 7:]).max() <= 1e-6, f'leaf pdfs differ from {who}'
+
+
+def test_multi_threshold_training_runs_and_is_consistent():
+    """cfg-4 form (sorted thresholds per feature): each (feature, threshold) pair scored exactly as a reference proposal."""
+    import torch
+    from rdf_b200 import synth
+    from rdf_b200 import decision_tree as dt
+    from oracle import numpy_oracle as no
+    N, H, W, C, D, F, NT = 2, 48, 64, 4, 4, 16, 8
+    depth = synth.depth_frames('dense-smooth', N, H, W, seed=4)
+    labels = synth.train_labels(N, H, W)
+    props = {lvl: synth.random_proposals(F, NT, seed=100 + lvl) for lvl in range(D)}
+    ds = dt.DecisionTreeDatasetConfig.from_arrays(depth, labels, C)
+    trainer = dt.DecisionTreeTrainer(N, F, thresholds_per_feature=NT, proposal_fn=lambda lvl, b: props[lvl])
+    trainer.allocate(ds, F, D)
+    tree = dt.DecisionTree(D, C)
+    trainer.train(ds, tree)
+    torch.cuda.synchronize()
+    ours = tree.tree_out_cu.get()
+    # equivalent reference-form stream: F*NT proposals, feature-major / threshold-minor
+    def flat(lvl):
+        off, th = props[lvl]
+        return [np.concatenate([np.repeat(off, NT, axis=0), th.reshape(-1, 1)], axis=1).astype(np.float32)]
+    exp = no.train_tree(depth, labels, C, D, flat)
+    _assert_same_tree(ours, exp, 'numpy oracle (flattened proposals)')
