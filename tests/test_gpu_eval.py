@@ -192,3 +192,17 @@ def test_error_paths():
         ev.get_labels_forest(f, filled_u16((1, 8, 8), 1000), filled_u16((1, 4, 8)))
     with pytest.raises(ValueError):
         ev.get_labels_forest(f, torch.zeros((1, 8, 8), dtype=torch.int16).view(torch.uint16), filled_u16((1, 8, 8)))  # CPU tensor
+
+
+def test_device_generators_match_numpy_twins():
+    import torch
+    from rdf_b200 import synth, _capi
+    lib = _capi.load()
+    for kind, kid in (('dense-smooth', 0), ('dense-noise', 1), ('live-mask', 2)):
+        out = torch.zeros((3, 120, 212), dtype=torch.int16, device='cuda').view(torch.uint16)
+        _capi.check(lib.rdf_synth_depth(_capi.dptr(out), kid, 3, 212, 120, 99, 5, _capi.stream_ptr()))
+        assert np.array_equal(to_np(out), synth.depth_frames(kind, 3, 120, 212, seed=99, first_frame=5))
+    canon = torch.zeros((3, 255, 7 + 8), dtype=torch.float32, device='cuda')
+    _capi.check(lib.rdf_synth_forest(_capi.dptr(canon), 3, 8, 4, 4321, _capi.stream_ptr()))
+    exp = synth.hash_forest(3, 8, 4, seed=4321)
+    assert np.array_equal(canon.cpu().numpy().view(np.uint32), exp.view(np.uint32))
