@@ -26,7 +26,10 @@ __global__ void rdf_pack_kernel(const float* __restrict__ canon, rdf_node_hdr* _
         rdf_node_hdr h;
         h.a = make_float4(nd[0], nd[1], nd[2], nd[3]);
         h.thresh = nd[4];
-        h.flags = (__float2int_rd(nd[5]) == -1 ? 1 : 0) | (__float2int_rd(nd[6]) == -1 ? 2 : 0);
+        h.flags = (__float2int_rd(nd[5]) == -1 ? RDF_FLAG_LEFT_CONT : 0) | (__float2int_rd(nd[6]) == -1 ? RDF_FLAG_RIGHT_CONT : 0);
+        // offsets outside the domain of the reciprocal-based divide (rdf_common.cuh) send this node down the exact path
+        if (!(rdf_fastdiv_domain(nd[0]) && rdf_fastdiv_domain(nd[1]) && rdf_fastdiv_domain(nd[2]) && rdf_fastdiv_domain(nd[3])))
+            h.flags |= RDF_FLAG_EXACT_DIV;
         h.pad0 = 0;
         h.pad1 = 0;
         hdr[i] = h;
@@ -106,5 +109,78 @@ extern "C" int rdf_forest_info(const rdf_forest_t* forest, int* num_trees, int* 
     if (max_depth) *max_depth = forest->D;
     if (num_classes) *num_classes = forest->C;
     if (packed_bytes) *packed_bytes = forest->packed_bytes;
+    return RDF_OK;
+}
+
+// ---- self test: reciprocal-based divide == div.rn.f32, bit for bit, on its whole domain ---------------------------------
+__device__ __forceinline__ uint32_t st_mix(uint32_t h) {
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+
+__global__ void __launch_bounds__(256) rdf_selftest_fastdiv_kernel(unsigned cases_per_d, uint32_t seed,
+                                                                   unsigned long long* __restrict__ mismatches,
+                                                                   unsigned long long* __restrict__ floor_mismatches) {
+    const unsigned long long total = 65535ull * cases_per_d;
+    unsigned long long bad = 0, bad_floor = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned d = 1u + (unsigned)(i % 65535ull);
+        const unsigned k = (unsigned)(i / 65535ull);
+        const uint32_t h0 = st_mix(seed ^ (d * 0x9E3779B1u) ^ (k * 0x85EBCA77u));
+        const uint32_t h1 = st_mix(h0 ^ 0xC2B2AE3Du);
+        const float df = (float)d;
+        float a;
+        switch (k & 3u) {
+            case 0: {   // log-uniform magnitude over the whole domain 2^-60 .. 2^60
+                const uint32_t expo = 127u - 60u + (h0 >> 8) % 120u;
+                a = __uint_as_float(((h0 & 1u) << 31) | (expo << 23) | (h1 & 0x7FFFFFu));
+                break;
+            }
+            case 1: {   // adversarial: a within a few ulp of an integer multiple of d (quotient next to an integer)
+                const int n = (int)(h0 % 2097153u) - 1048576;
+                a = (float)n * df;
+                a = __uint_as_float(__float_as_uint(a) + (h1 % 9u) - 4u);
+                break;
+            }
+            case 2: {   // small quotients: |n| <= 512, the range of real probe offsets
+                const int n = (int)(h0 % 1025u) - 512;
+                a = (float)n * df;
+                a = __uint_as_float(__float_as_uint(a) + (h1 % 17u) - 8u);
+                break;
+            }
+            default: {  // reference-like offsets: magnitude e^U(0,14), any sign
+                const float m = __expf(14.f * (float)(h0 >> 8) / 16777216.f);
+                a = (h1 & 1u) ? -m : m;
+                a = __uint_as_float(__float_as_uint(a) ^ ((h1 >> 1) & 0xFFu));
+                break;
+            }
+        }
+        if (!rdf_fastdiv_domain(a)) continue;
+        const float exact = __fdiv_rn(a, df);
+        const float fast = rdf_div_fast(a, df, __frcp_rn(df));
+        if (__float_as_uint(exact) != __float_as_uint(fast)) bad++;
+        if (__float2int_rd(exact) != __float2int_rd(fast)) bad_floor++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+    if (bad_floor) atomicAdd(floor_mismatches, bad_floor);
+}
+
+extern "C" int rdf_selftest_fastdiv(unsigned cases_per_divisor, uint32_t seed, unsigned long long* mismatches_host,
+                                    unsigned long long* floor_mismatches_host) {
+    RDF_REQUIRE(mismatches_host && floor_mismatches_host && cases_per_divisor >= 1, "rdf_selftest_fastdiv: bad argument");
+    unsigned long long* dev = nullptr;
+    RDF_CUDA(cudaMalloc(&dev, 2 * sizeof(unsigned long long)));
+    cudaMemset(dev, 0, 2 * sizeof(unsigned long long));
+    rdf_selftest_fastdiv_kernel<<<148 * 8, 256>>>(cases_per_divisor, seed, dev, dev + 1);
+    unsigned long long host[2] = {~0ull, ~0ull};
+    cudaError_t e = cudaMemcpy(host, dev, sizeof(host), cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    if (e != cudaSuccess) {
+        rdf_set_error("rdf_selftest_fastdiv: %s", cudaGetErrorString(e));
+        return RDF_ERR_CUDA;
+    }
+    *mismatches_host = host[0];
+    *floor_mismatches_host = host[1];
     return RDF_OK;
 }

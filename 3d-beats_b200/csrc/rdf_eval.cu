@@ -18,7 +18,7 @@ struct rdf_eval_params {
     float scale;
 };
 
-template <int T, int WARP_W>
+template <int T, int WARP_W, bool SCALE1, bool FORCE_EXACT>
 __global__ void __launch_bounds__(256) rdf_eval_packed_kernel(const rdf_eval_params p) {
     constexpr int WARP_H = 32 / WARP_W;
     constexpr int WARPS_X = 32 / WARP_W;
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) rdf_eval_packed_kernel(const rdf_eval_par
     const unsigned d = __ldg(img + (size_t)Y * p.W + X);
     if (d == 0u || d == RDF_NO_PIXEL) return;                                            // tree_eval.cu:88-89
     int leaf[T];
-    rdf_walk<T>(p.fv, img, p.W, p.H, X, Y, (float)d, p.scale, leaf);
+    rdf_walk<T, SCALE1, FORCE_EXACT>(p.fv, img, p.W, p.H, X, Y, (float)d, p.scale, leaf);
     const int lab = rdf_vote<T>(p.fv, leaf, p.probs ? p.probs + li * p.fv.C : nullptr);
     p.labels[li] = (uint16_t)lab;
 }
@@ -81,9 +81,9 @@ __global__ void __launch_bounds__(128) rdf_eval_canon_kernel(const rdf_eval_cano
         int64_t row = 0;
         for (int j = 0; j < p.D; j++) {
             const float* nd = tree + row * E;
-            const float f = rdf_feature(img, p.W, p.H, X, Y, df, __fmul_rn(p.scale, __ldg(nd + 0)),
-                                        __fmul_rn(p.scale, __ldg(nd + 1)), __fmul_rn(p.scale, __ldg(nd + 2)),
-                                        __fmul_rn(p.scale, __ldg(nd + 3)));
+            const float f = rdf_feature<true>(img, p.W, p.H, X, Y, df, 0.f, __fmul_rn(p.scale, __ldg(nd + 0)),
+                                              __fmul_rn(p.scale, __ldg(nd + 1)), __fmul_rn(p.scale, __ldg(nd + 2)),
+                                              __fmul_rn(p.scale, __ldg(nd + 3)));
             const int side = (f < __ldg(nd + 4)) ? 0 : 1;
             if (__float2int_rd(__ldg(nd + 5 + side)) == -1) {
                 row = 2 * row + 1 + side;
@@ -133,12 +133,22 @@ static int rdf_warp_w() {
     return v;
 }
 
+template <int T, int WARP_W>
+static void rdf_launch_packed_tw(const rdf_eval_params& p, dim3 grid, cudaStream_t stream) {
+    if (!rdf_scale_fast_ok(p.scale))
+        rdf_eval_packed_kernel<T, WARP_W, false, true><<<grid, 256, 0, stream>>>(p);
+    else if (p.scale == 1.f)
+        rdf_eval_packed_kernel<T, WARP_W, true, false><<<grid, 256, 0, stream>>>(p);
+    else
+        rdf_eval_packed_kernel<T, WARP_W, false, false><<<grid, 256, 0, stream>>>(p);
+}
+
 template <int T>
 static void rdf_launch_packed_t(const rdf_eval_params& p, dim3 grid, cudaStream_t stream) {
     switch (rdf_warp_w()) {
-        case 32: rdf_eval_packed_kernel<T, 32><<<grid, 256, 0, stream>>>(p); break;
-        case 16: rdf_eval_packed_kernel<T, 16><<<grid, 256, 0, stream>>>(p); break;
-        default: rdf_eval_packed_kernel<T, 8><<<grid, 256, 0, stream>>>(p); break;
+        case 32: rdf_launch_packed_tw<T, 32>(p, grid, stream); break;
+        case 16: rdf_launch_packed_tw<T, 16>(p, grid, stream); break;
+        default: rdf_launch_packed_tw<T, 8>(p, grid, stream); break;
     }
 }
 

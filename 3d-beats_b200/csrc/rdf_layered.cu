@@ -54,7 +54,7 @@ struct rdf_layered_params {
     float scale;
 };
 
-template <int WARP_W>
+template <int WARP_W, bool SCALE1, bool FORCE_EXACT>
 __global__ void __launch_bounds__(256) rdf_layered_kernel(const __grid_constant__ rdf_layered_params p) {
     constexpr int WARP_H = 32 / WARP_W;
     constexpr int WARPS_X = 32 / WARP_W;
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) rdf_layered_kernel(const __grid_constant_
         if (fm >= 0 && p.filter_class[i] != -1) run = run && ((int)get_lab(fm) == p.filter_class[i]);
         unsigned l = RDF_NO_PIXEL;
         if (run) {
-            l = (unsigned)rdf_eval_pixel(p.fv[i], p.depth, p.W, p.H, X, Y, df, p.scale, nullptr);
+            l = (unsigned)rdf_eval_pixel<SCALE1, FORCE_EXACT>(p.fv[i], p.depth, p.W, p.H, X, Y, df, p.scale, nullptr);
             set_lab(i, l);
         }
         p.layer_labels[i][li] = (uint16_t)l;
@@ -148,7 +148,13 @@ extern "C" int rdf_layered_run(const rdf_forest_t* const* forests, int num_layer
     p.tiles_x = (p.w + 31) / 32;
     p.scale = scale;
     const int tiles_y = (p.h + 7) / 8;
-    rdf_layered_kernel<8><<<p.tiles_x * tiles_y, 256, 0, rdf_stream(stream)>>>(p);
+    const int nblk = p.tiles_x * tiles_y;
+    if (!rdf_scale_fast_ok(scale))
+        rdf_layered_kernel<8, false, true><<<nblk, 256, 0, rdf_stream(stream)>>>(p);
+    else if (scale == 1.f)
+        rdf_layered_kernel<8, true, false><<<nblk, 256, 0, rdf_stream(stream)>>>(p);
+    else
+        rdf_layered_kernel<8, false, false><<<nblk, 256, 0, rdf_stream(stream)>>>(p);
     RDF_LAUNCH_CHECK("rdf_layered_kernel");
     return RDF_OK;
 }

@@ -71,6 +71,11 @@ __global__ void __launch_bounds__(TH_THREADS) rdf_train_hist_kernel(const rdf_hi
     const int f0 = blockIdx.y * p.FC;
     const int nf = min(p.FC, p.F - f0);
     for (int i = threadIdx.x; i < nf * 4; i += TH_THREADS) off_s[i] = __ldg(p.offsets + (size_t)f0 * 4 + i);
+    __shared__ unsigned char exact_s[TH_MAX_FC];      // feature needs the exact divide (offsets outside the fast domain)
+    for (int j = threadIdx.x; j < nf; j += TH_THREADS) {
+        const float* o = p.offsets + (size_t)(f0 + j) * 4;
+        exact_s[j] = !(rdf_fastdiv_domain(o[0]) && rdf_fastdiv_domain(o[1]) && rdf_fastdiv_domain(o[2]) && rdf_fastdiv_domain(o[3]));
+    }
     for (int i = threadIdx.x; i < nf * p.NT; i += TH_THREADS) thr_s[i] = __ldg(p.thresholds + (size_t)f0 * p.NT + i);
     const int per_slot = p.FC * p.NB * p.C;
     if (p.privatise)
@@ -94,12 +99,16 @@ __global__ void __launch_bounds__(TH_THREADS) rdf_train_hist_kernel(const rdf_hi
         const unsigned label = __ldg(p.labels + i);
         if (label >= (unsigned)p.C) continue;
         const float df = (float)d;
+        const float rcp = __frcp_rn(df);
         uint32_t* dst = p.privatise ? hist_s + (size_t)slot * per_slot
                                     : p.hist + ((size_t)slot * p.F + f0) * p.NB * p.C;
         for (int j = 0; j < nf; j++) {
             const float4 o = *reinterpret_cast<const float4*>(off_s + 4 * j);
             // compute_feature with scale 1 (tree_train.cu:58); d == 0 -> 0.f (decision_tree_common.hpp:12)
-            const float f = d == 0u ? 0.f : rdf_feature(img, p.W, p.H, X, Y, df, o.x, o.y, o.z, o.w);
+            float f = 0.f;
+            if (d != 0u)
+                f = exact_s[j] ? rdf_feature<true>(img, p.W, p.H, X, Y, df, rcp, o.x, o.y, o.z, o.w)
+                               : rdf_feature<false>(img, p.W, p.H, X, Y, df, rcp, o.x, o.y, o.z, o.w);
             // bin = #{k : t_k <= f}: branch-free binary search over the ascending thresholds
             const float* th = thr_s + j * p.NT;
             int lo = 0, len = p.NT;
@@ -453,7 +462,7 @@ __global__ void __launch_bounds__(256) rdf_train_advance_kernel(const uint16_t* 
     const int E = 7 + 2 * C;
     const float* nd = tree + ((((size_t)1 << level) - 1) + g) * E;
     const unsigned d = __ldg(img + rem);
-    const float f = d == 0u ? 0.f : rdf_feature(img, W, H, X, Y, (float)d, __ldg(nd + 0), __ldg(nd + 1), __ldg(nd + 2), __ldg(nd + 3));
+    const float f = d == 0u ? 0.f : rdf_feature<true>(img, W, H, X, Y, (float)d, 0.f, __ldg(nd + 0), __ldg(nd + 1), __ldg(nd + 2), __ldg(nd + 3));
     const bool left = f < __ldg(nd + 4);
     const int status = __float2int_rd(__ldg(nd + (left ? 5 : 6)));
     nodes[i] = status != -1 ? -1 : 2 * g + (left ? 0 : 1);         // tree_train.cu:316-323

@@ -30,7 +30,9 @@ static inline rdf_forest_view rdf_view(const rdf_forest* f) {
 
 // Walk T trees from the root.  leaf[t] = 2*row + side of the reached leaf, or -1 if the walk fell off level D-1
 // with a "continue" flag (adds nothing, src/cuda/tree_eval.cu:95-128).
-template <int T>
+// SCALE1: scale == 1.0f, so scale*u == u exactly and the multiplies are dropped.  FORCE_EXACT: always use __fdiv_rn
+// (scale outside the fast-divide domain); otherwise nodes flagged RDF_FLAG_EXACT_DIV take the exact path per level.
+template <int T, bool SCALE1, bool FORCE_EXACT>
 __device__ __forceinline__ void rdf_walk(const rdf_forest_view& fv, const uint16_t* __restrict__ img, int W, int H, int X,
                                          int Y, float df, float scale, int (&leaf)[T]) {
     int row[T];
@@ -39,25 +41,36 @@ __device__ __forceinline__ void rdf_walk(const rdf_forest_view& fv, const uint16
         row[t] = 0;
         leaf[t] = -1;
     }
+    const float rcp = __frcp_rn(df);                                 // RN(1/d), once per pixel
     unsigned alive = (1u << T) - 1u;
     for (int j = 0; j < fv.D && alive; j++) {
         float4 a[T];
         float th[T];
         int fl[T];
+        int any_flags = 0;
 #pragma unroll
         for (int t = 0; t < T; t++) {
             // dead walks re-read their last node: harmless, keeps the loop branch-free
             const float4* p = reinterpret_cast<const float4*>(fv.hdr + (int64_t)t * fv.nodes_per_tree + row[t]);
             a[t] = __ldg(p);
-            const float4 b = __ldg(p + 1);
+            const float2 b = __ldg(reinterpret_cast<const float2*>(p + 1));
             th[t] = b.x;
             fl[t] = __float_as_int(b.y);
+            any_flags |= fl[t];
+            if (!SCALE1) {
+                a[t].x = __fmul_rn(scale, a[t].x);
+                a[t].y = __fmul_rn(scale, a[t].y);
+                a[t].z = __fmul_rn(scale, a[t].z);
+                a[t].w = __fmul_rn(scale, a[t].w);
+            }
         }
         float f[T];
+        if (FORCE_EXACT || (any_flags & RDF_FLAG_EXACT_DIV)) {
 #pragma unroll
-        for (int t = 0; t < T; t++) {
-            f[t] = rdf_feature(img, W, H, X, Y, df, __fmul_rn(scale, a[t].x), __fmul_rn(scale, a[t].y),
-                               __fmul_rn(scale, a[t].z), __fmul_rn(scale, a[t].w));
+            for (int t = 0; t < T; t++) f[t] = rdf_feature<true>(img, W, H, X, Y, df, rcp, a[t].x, a[t].y, a[t].z, a[t].w);
+        } else {
+#pragma unroll
+            for (int t = 0; t < T; t++) f[t] = rdf_feature<false>(img, W, H, X, Y, df, rcp, a[t].x, a[t].y, a[t].z, a[t].w);
         }
 #pragma unroll
         for (int t = 0; t < T; t++) {
@@ -111,13 +124,14 @@ __device__ __forceinline__ int rdf_vote(const rdf_forest_view& fv, const int (&l
 }
 
 // Evaluate one forest at one pixel (T <= RDF_FAST_MAX_TREES, dispatched on the runtime tree count).
+template <bool SCALE1, bool FORCE_EXACT>
 __device__ __forceinline__ int rdf_eval_pixel(const rdf_forest_view& fv, const uint16_t* __restrict__ img, int W, int H,
                                               int X, int Y, float df, float scale, float* __restrict__ probs) {
-#define RDF_CASE(TT)                                        \
-    case TT: {                                              \
-        int leaf[TT];                                       \
-        rdf_walk<TT>(fv, img, W, H, X, Y, df, scale, leaf); \
-        return rdf_vote<TT>(fv, leaf, probs);               \
+#define RDF_CASE(TT)                                                             \
+    case TT: {                                                                   \
+        int leaf[TT];                                                            \
+        rdf_walk<TT, SCALE1, FORCE_EXACT>(fv, img, W, H, X, Y, df, scale, leaf); \
+        return rdf_vote<TT>(fv, leaf, probs);                                    \
     }
     switch (fv.T) {
         RDF_CASE(1)

@@ -38,6 +38,7 @@ SIGNATURES = {
     'rdf_mean_shift': [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p],
     'rdf_synth_depth': [c_void_p, c_int, c_int, c_int, c_int, c_uint32, c_int, c_void_p],
     'rdf_synth_forest': [c_void_p, c_int, c_int, c_int, c_uint32, c_void_p],
+    'rdf_selftest_fastdiv': [ctypes.c_uint, c_uint32, ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)],
     'rdf_train_init': [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p],
     'rdf_train_hist': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
                        c_int, c_void_p, c_void_p],

@@ -128,6 +128,14 @@ RDF_API int rdf_synth_depth(uint16_t* depth_dev, int kind, int num_images, int d
                     int first_frame, void* stream);
 RDF_API int rdf_synth_forest(float* canon_dev, int num_trees, int max_depth, int num_classes, uint32_t seed, void* stream);
 
+/* ---- self test ---------------------------------------------------------------------------------------------
+ * The kernels replace the four IEEE divides of compute_feature by a correctly rounded reciprocal (once per pixel) plus
+ * one correction step (csrc/rdf_common.cuh).  This entry point compares that sequence against div.rn.f32 bit for bit
+ * over 65535 divisors x cases_per_divisor numerators (uniform-in-exponent, adversarial next-to-integer quotients,
+ * reference-like offsets) and returns the number of differing quotients / differing floors (both must be 0). Synchronous. */
+RDF_API int rdf_selftest_fastdiv(unsigned cases_per_divisor, uint32_t seed, unsigned long long* mismatches_host,
+                         unsigned long long* floor_mismatches_host);
+
 /* ---- training split search --------------------------------------------------------------------------------
  * Level-synchronous training of one tree (DecisionTreeTrainer.train, src/decision_tree.py:444-601).
  *

@@ -206,3 +206,13 @@ def test_device_generators_match_numpy_twins():
     _capi.check(lib.rdf_synth_forest(_capi.dptr(canon), 3, 8, 4, 4321, _capi.stream_ptr()))
     exp = synth.hash_forest(3, 8, 4, seed=4321)
     assert np.array_equal(canon.cpu().numpy().view(np.uint32), exp.view(np.uint32))
+
+
+def test_fast_divide_is_bit_identical_to_div_rn():
+    """2.6e9 (numerator, divisor) pairs: RN(1/d) + one correction step == div.rn.f32 on the kernels' whole domain."""
+    import ctypes
+    from rdf_b200 import _capi
+    lib = _capi.load()
+    bad, bad_floor = ctypes.c_ulonglong(1), ctypes.c_ulonglong(1)
+    _capi.check(lib.rdf_selftest_fastdiv(40000, 20261018, ctypes.byref(bad), ctypes.byref(bad_floor)))
+    assert bad.value == 0 and bad_floor.value == 0
