@@ -1,5 +1,6 @@
 // Stacked ("layered") forests: replaces LayeredDecisionForest.run (reference src/decision_tree.py:233-264) and
 // make_composite_labels_image (src/cuda/tree_eval.cu:214-248).
+#include <stdlib.h>
 #include <string.h>
 
 #include "rdf_traverse.cuh"
@@ -114,6 +115,148 @@ __global__ void __launch_bounds__(256) rdf_layered_kernel(const __grid_constant_
     p.composite[li] = (uint16_t)comp;
 }
 
+// ---- latency path: one thread per (pixel, tree walk) ---------------------------------------------------------------
+// The live product evaluates ONE frame with few valid pixels (a hand blob), so the fused kernel above is bound by the
+// dependent-load chain of a single thread (L layers x D levels, two L2 round trips per level).  Here every tree of
+// every layer is a separate walk running in its own warp (lanes = 32 neighbouring pixels, warp = one tree), layers
+// are evaluated speculatively in parallel and gated afterwards, and each level prefetches BOTH child headers while
+// the depth probes of the current node are in flight, so a level costs about one L2 round trip instead of two.
+// Results are identical: gating only decides which labels are kept.
+#define RL2_MAX_WALKS 32
+
+struct rdf_layered2_params {
+    rdf_layered_params base;
+    int walk_layer[RL2_MAX_WALKS];
+    int walk_tree[RL2_MAX_WALKS];
+    int first_walk[RDF_MAX_LAYERS];
+    int num_walks;
+};
+
+template <bool SCALE1, bool FORCE_EXACT>
+__global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_constant__ rdf_layered2_params q) {
+    const rdf_layered_params& p = q.base;
+    __shared__ int leaf_s[RL2_MAX_WALKS][32];
+    __shared__ unsigned short lab_s[RDF_MAX_LAYERS][32];
+    const int lane = threadIdx.x, walk = threadIdx.y;
+    const int tile_y = blockIdx.x / p.tiles_x, tile_x = blockIdx.x - tile_y * p.tiles_x;
+    const int x = tile_x * 8 + (lane & 7), y = tile_y * 4 + (lane >> 3);     // warp = 8x4 patch of labels pixels
+    const bool inside = x < p.w && y < p.h;
+    const int X = x * p.r, Y = y * p.r;
+    unsigned d = RDF_NO_PIXEL;
+    if (inside) d = __ldg(p.depth + (size_t)Y * p.W + X);
+    const bool valid = inside && d != 0u && d != RDF_NO_PIXEL;
+    const size_t li = (size_t)y * p.w + x;
+    if (__syncthreads_or(valid) == 0) {                                   // nothing to evaluate in this tile: pre-fill only
+        if (walk == 0 && inside) {
+            for (int i = 0; i < p.L; i++) p.layer_labels[i][li] = (uint16_t)RDF_NO_PIXEL;
+            p.composite[li] = (uint16_t)RDF_NO_PIXEL;
+        }
+        return;
+    }
+    const int layer = q.walk_layer[walk], t = q.walk_tree[walk];
+    const rdf_forest_view& fv = p.fv[layer];
+    int leaf = -1;
+    if (valid) {
+        const float df = (float)d;
+        const float rcp = __frcp_rn(df);
+        const rdf_node_hdr* base = fv.hdr + (int64_t)t * fv.nodes_per_tree;
+        int row = 0;
+        float4 a = __ldg(reinterpret_cast<const float4*>(base));
+        float2 b = __ldg(reinterpret_cast<const float2*>(base) + 2);
+        for (int j = 0; j < fv.D; j++) {
+            float4 al = a, ar = a;
+            float2 bl = b, br = b;
+            if (j + 1 < fv.D) {                                                // both children, adjacent rows 2r+1, 2r+2
+                const rdf_node_hdr* c = base + 2 * (int64_t)row + 1;
+                al = __ldg(reinterpret_cast<const float4*>(c));
+                bl = __ldg(reinterpret_cast<const float2*>(c) + 2);
+                ar = __ldg(reinterpret_cast<const float4*>(c + 1));
+                br = __ldg(reinterpret_cast<const float2*>(c + 1) + 2);
+            }
+            const int fl = __float_as_int(b.y);
+            float sx = a.x, sy = a.y, sz = a.z, sw = a.w;
+            if (!SCALE1) {
+                sx = __fmul_rn(p.scale, sx); sy = __fmul_rn(p.scale, sy);
+                sz = __fmul_rn(p.scale, sz); sw = __fmul_rn(p.scale, sw);
+            }
+            float f;
+            if (FORCE_EXACT || (fl & RDF_FLAG_EXACT_DIV)) f = rdf_feature<true>(p.depth, p.W, p.H, X, Y, df, rcp, sx, sy, sz, sw);
+            else f = rdf_feature<false>(p.depth, p.W, p.H, X, Y, df, rcp, sx, sy, sz, sw);
+            const int side = (f < b.x) ? 0 : 1;
+            if (!((fl >> side) & 1)) {
+                leaf = 2 * row + side;
+                break;
+            }
+            row = 2 * row + 1 + side;
+            a = side ? ar : al;
+            b = side ? br : bl;
+        }
+    }
+    leaf_s[walk][lane] = leaf;
+    __syncthreads();
+    // vote of each layer by the thread that owns the layer's first walk (speculative: gating is applied below)
+    if (walk == q.first_walk[layer] && valid) {
+        float best = 0.f;
+        int lab = 0;
+        for (int c = 0; c < fv.CP; c += 4) {
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int tt = 0; tt < fv.T; tt++) {
+                const int lf = leaf_s[walk + tt][lane];
+                if (lf >= 0) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(fv.pdf + ((int64_t)tt * fv.nodes_per_tree * 2 + lf) * fv.CP + c));
+                    s.x = __fadd_rn(s.x, v.x); s.y = __fadd_rn(s.y, v.y); s.z = __fadd_rn(s.z, v.z); s.w = __fadd_rn(s.w, v.w);
+                }
+            }
+            if (s.x > best) { best = s.x; lab = c; }
+            if (s.y > best) { best = s.y; lab = c + 1; }
+            if (s.z > best) { best = s.z; lab = c + 2; }
+            if (s.w > best) { best = s.w; lab = c + 3; }
+        }
+        lab_s[layer][lane] = (unsigned short)lab;
+    }
+    __syncthreads();
+    if (walk != 0 || !inside) return;
+    // gating in layer order + composite walk (tree_eval.cu:232-244), identical to the fused kernel
+    unsigned long long lab_lo = ~0ull, lab_hi = ~0ull;
+    auto get_lab = [&](int i) -> unsigned {
+        const unsigned long long wd = i < 4 ? lab_lo : lab_hi;
+        return (unsigned)(wd >> (16 * (i & 3))) & 0xffffu;
+    };
+    auto set_lab = [&](int i, unsigned v) {
+        const unsigned long long m = 0xffffull << (16 * (i & 3));
+        const unsigned long long bb = (unsigned long long)(v & 0xffffu) << (16 * (i & 3));
+        if (i < 4) lab_lo = (lab_lo & ~m) | bb; else lab_hi = (lab_hi & ~m) | bb;
+    };
+#pragma unroll 1
+    for (int i = 0; i < p.L; i++) {
+        bool run = valid;
+        const int fm = p.filter_model[i];
+        if (fm >= 0 && p.filter_class[i] != -1) run = run && ((int)get_lab(fm) == p.filter_class[i]);
+        unsigned l = RDF_NO_PIXEL;
+        if (run) {
+            l = lab_s[i][lane];
+            set_lab(i, l);
+        }
+        p.layer_labels[i][li] = (uint16_t)l;
+    }
+    unsigned comp = RDF_NO_PIXEL;
+    int off = 0;
+#pragma unroll 1
+    for (int i = 0; i < p.L; i++) {
+        const unsigned l = get_lab(i);
+        if (l == 0u || l == RDF_NO_PIXEL) break;
+        const int idx = off + (int)l - 1;
+        if (idx < 0 || idx >= p.n_cond) break;
+        const int2 tv = __ldg(p.cond + idx);
+        if (tv.x == 0) {
+            comp = (unsigned)tv.y & 0xffffu;
+            break;
+        }
+        off = tv.y;
+    }
+    p.composite[li] = (uint16_t)comp;
+}
+
 extern "C" int rdf_layered_run(const rdf_forest_t* const* forests, int num_layers, const int* filter_model,
                                const int* filter_class, const uint16_t* depth_dev, int dim_x, int dim_y,
                                uint16_t* const* labels_per_layer, const int32_t* conditions_dev, int n_cond,
@@ -148,6 +291,33 @@ extern "C" int rdf_layered_run(const rdf_forest_t* const* forests, int num_layer
     p.tiles_x = (p.w + 31) / 32;
     p.scale = scale;
     const int tiles_y = (p.h + 7) / 8;
+    // latency path: one warp per tree walk (see rdf_layered_walks_kernel)
+    int num_walks = 0;
+    for (int i = 0; i < num_layers; i++) num_walks += forests[i]->T;
+    if (num_walks <= RL2_MAX_WALKS && !getenv("RDF_LAYERED_V1")) {
+        rdf_layered2_params q;
+        q.base = p;
+        q.base.tiles_x = (p.w + 7) / 8;
+        q.num_walks = num_walks;
+        int wi = 0;
+        for (int i = 0; i < num_layers; i++) {
+            q.first_walk[i] = wi;
+            for (int t = 0; t < forests[i]->T; t++, wi++) {
+                q.walk_layer[wi] = i;
+                q.walk_tree[wi] = t;
+            }
+        }
+        const int nb = q.base.tiles_x * ((p.h + 3) / 4);
+        dim3 block(32, num_walks, 1);
+        if (!rdf_scale_fast_ok(scale))
+            rdf_layered_walks_kernel<false, true><<<nb, block, 0, rdf_stream(stream)>>>(q);
+        else if (scale == 1.f)
+            rdf_layered_walks_kernel<true, false><<<nb, block, 0, rdf_stream(stream)>>>(q);
+        else
+            rdf_layered_walks_kernel<false, false><<<nb, block, 0, rdf_stream(stream)>>>(q);
+        RDF_LAUNCH_CHECK("rdf_layered_walks_kernel");
+        return RDF_OK;
+    }
     const int nblk = p.tiles_x * tiles_y;
     if (!rdf_scale_fast_ok(scale))
         rdf_layered_kernel<8, false, true><<<nblk, 256, 0, rdf_stream(stream)>>>(p);

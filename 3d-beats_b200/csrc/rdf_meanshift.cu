@@ -11,6 +11,7 @@
 //      the new means redundantly - no global atomics, no grid relaunch, no host round trip.
 // Results are bitwise reproducible run to run for a given launch shape.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "rdf_common.cuh"
 
@@ -202,6 +203,269 @@ __global__ void __launch_bounds__(MS_THREADS) rdf_mean_shift_kernel(const rdf_ms
     cluster.sync();   // no CTA may exit while peers can still address its shared memory
 }
 
+// =================================================================================================================
+// v2: latency path (the live product shape).  Same algorithm, but everything after the first read of the label image
+// lives in shared memory and the image is read with 128-bit loads issued up front:
+//   * each thread owns up to MS2_GROUPS groups of 8 consecutive pixels (one uint4 each), all loaded before first use;
+//   * the per-class coordinate lists are built with a stable counting sort: per-thread class counts packed four
+//     16-bit counters per 64-bit word, one block-wide exclusive scan per word (deterministic order = thread, then
+//     pixel), entries (x | y << 16) scattered into shared memory;
+//   * rounds run on the shared-memory lists exactly like v1 (items -> warp shuffles -> DSMEM exchange -> barrier).
+// Used when K <= MS2_MAX_K, the image fits MS_MAX_CLUSTER x MS2_CAP pixels and the label pointer is 16-byte aligned.
+// =================================================================================================================
+#define MS2_THREADS 1024
+#define MS2_WARPS 32
+#define MS2_GROUPS 7                      // 56 pixels per thread -> up to 57344 pixels per CTA
+#define MS2_CAP 51200                     // entries per CTA kept in shared memory (200 KB)
+#define MS2_MAX_K 16
+#define MS2_NG (MS2_MAX_K / 4)
+#define MS2_ITEM 256
+#define MS2_MAX_ITEMS (MS2_CAP / MS2_ITEM + MS2_MAX_K)
+
+struct rdf_ms2_params {
+    const uint16_t* labels;
+    const float* variances;
+    double* means_out;
+    int w, h, K, rounds;
+    int chunk;              // pixels per CTA, multiple of 8
+    unsigned long long* trace;   // optional: %globaltimer stamps of rank 0 (workspace head), phase by phase
+};
+
+__device__ __forceinline__ unsigned long long ms_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define MS_TRACE(slot)                                                        \
+    do {                                                                      \
+        if (p.trace && rank == 0 && tid == 0) p.trace[slot] = ms_now();       \
+    } while (0)
+
+__device__ __forceinline__ unsigned long long ms2_block_exscan(unsigned long long v, unsigned long long* warp_tot,
+                                                               unsigned long long* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();                       // warp_tot reuse across calls
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long t = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, t, o);
+            if (lane >= o) t += u;
+        }
+        warp_tot[lane] = t;                // inclusive over warps
+    }
+    __syncthreads();
+    *total = warp_tot[MS2_WARPS - 1];
+    return (warp ? warp_tot[warp - 1] : 0ull) + incl - v;
+}
+
+__global__ void __launch_bounds__(MS2_THREADS, 1) rdf_mean_shift_v2_kernel(const rdf_ms2_params p) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int NC = (int)cluster.num_blocks();
+    const int K = p.K;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    extern __shared__ __align__(16) unsigned char ms_smem[];
+    double* all_partial = reinterpret_cast<double*>(ms_smem);                 // [2][NC][K][3]
+    double* partial = all_partial + 2 * (size_t)NC * K * 3;                   // [MS2_MAX_ITEMS][3]
+    double* means_s = partial + MS2_MAX_ITEMS * 3;                            // [K][2]
+    double* v2_s = means_s + 2 * K;                                           // [K]
+    unsigned long long* warp_tot = reinterpret_cast<unsigned long long*>(v2_s + K);   // [32]
+    int* seg_start = reinterpret_cast<int*>(warp_tot + MS2_WARPS);            // [K+1]
+    int* item_start = seg_start + (MS2_MAX_K + 1);                            // [K+1]
+    uint32_t* entries = reinterpret_cast<uint32_t*>(item_start + (MS2_MAX_K + 1) + 2);   // [chunk]
+
+    const int npx = p.w * p.h;
+    const int p0 = rank * p.chunk;
+    const int p1 = min(npx, p0 + p.chunk);
+    MS_TRACE(0);
+    if (p.trace && rank == 0 && tid == 0) p.trace[16] = (unsigned long long)clock64();
+
+    // ---- issue every load of this thread before anything consumes them ----
+    uint4 px[MS2_GROUPS];
+#pragma unroll
+    for (int g = 0; g < MS2_GROUPS; g++) {
+        const int q = p0 + (g * MS2_THREADS + tid) * 8;
+        px[g] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);      // 65535 = no pixel
+        if (q + 8 <= p1) {
+            px[g] = __ldg(reinterpret_cast<const uint4*>(p.labels + q));
+        } else if (q < p1) {                                                       // ragged tail of the image
+            unsigned short tmp[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) tmp[j] = q + j < p1 ? __ldg(p.labels + q + j) : (unsigned short)0xffff;
+            px[g] = make_uint4(tmp[0] | (tmp[1] << 16), tmp[2] | (tmp[3] << 16), tmp[4] | (tmp[5] << 16), tmp[6] | (tmp[7] << 16));
+        }
+    }
+    for (int k = tid; k < K; k += MS2_THREADS) {
+        means_s[2 * k] = 0.0;
+        means_s[2 * k + 1] = 0.0;
+        const float v = p.variances[k];
+        v2_s[k] = (double)__fmul_rn(v, v);                                    // fp32 product, widened (mean_shift.cu:41)
+    }
+
+    auto label_of = [&](int g, int j) -> unsigned {
+        const unsigned wd = j < 2 ? px[g].x : j < 4 ? px[g].y : j < 6 ? px[g].z : px[g].w;
+        return (j & 1) ? wd >> 16 : wd & 0xffffu;
+    };
+
+    // ---- per-thread class counts, four 16-bit counters per word ----
+    unsigned long long cnt[MS2_NG];
+#pragma unroll
+    for (int c = 0; c < MS2_NG; c++) cnt[c] = 0ull;
+#pragma unroll
+    for (int g = 0; g < MS2_GROUPS; g++) {
+        if ((px[g].x & px[g].y & px[g].z & px[g].w) == 0xffffffffu) continue;       // all background
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const unsigned l = label_of(g, j);
+            if (l != 0u && l != RDF_NO_PIXEL && (int)l <= K) {                       // mean_shift.cu:23
+                const int k = (int)l - 1;
+                const unsigned long long inc = 1ull << (16 * (k & 3));
+#pragma unroll
+                for (int c = 0; c < MS2_NG; c++) cnt[c] += (k >> 2) == c ? inc : 0ull;
+            }
+        }
+    }
+    MS_TRACE(1);
+    // ---- block-wide exclusive scans -> stable positions; totals -> class segments ----
+    unsigned long long pre[MS2_NG], tot[MS2_NG];
+#pragma unroll
+    for (int c = 0; c < MS2_NG; c++) {
+        pre[c] = 0ull; tot[c] = 0ull;
+        if (4 * c < K) pre[c] = ms2_block_exscan(cnt[c], warp_tot, &tot[c]);
+    }
+    if (tid == 0) {
+        seg_start[0] = 0;
+        item_start[0] = 0;
+        for (int k = 0; k < K; k++) {
+            unsigned long long tw = 0ull;
+#pragma unroll
+            for (int c = 0; c < MS2_NG; c++) if ((k >> 2) == c) tw = tot[c];
+            const int len = (int)((tw >> (16 * (k & 3))) & 0xffffull);
+            seg_start[k + 1] = seg_start[k] + len;
+            item_start[k + 1] = item_start[k] + (len + MS2_ITEM - 1) / MS2_ITEM;
+        }
+    }
+    __syncthreads();
+    MS_TRACE(2);
+    // ---- scatter (x | y << 16) into the class-sorted shared-memory list ----
+#pragma unroll
+    for (int g = 0; g < MS2_GROUPS; g++) {
+        if ((px[g].x & px[g].y & px[g].z & px[g].w) == 0xffffffffu) continue;
+        const int q = p0 + (g * MS2_THREADS + tid) * 8;
+        int y = q / p.w, x = q - y * p.w;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const unsigned l = label_of(g, j);
+            if (l != 0u && l != RDF_NO_PIXEL && (int)l <= K) {
+                const int k = (int)l - 1;
+                unsigned long long pw = 0ull;
+#pragma unroll
+                for (int c = 0; c < MS2_NG; c++) if ((k >> 2) == c) pw = pre[c];
+                const int pos = seg_start[k] + (int)((pw >> (16 * (k & 3))) & 0xffffull);
+                entries[pos] = (uint32_t)x | ((uint32_t)y << 16);
+                const unsigned long long inc = 1ull << (16 * (k & 3));
+#pragma unroll
+                for (int c = 0; c < MS2_NG; c++) pre[c] += (k >> 2) == c ? inc : 0ull;
+            }
+            if (++x == p.w) { x = 0; y++; }
+        }
+    }
+    __syncthreads();
+
+    // ---- rounds ----
+    const int n_items = item_start[K];
+    MS_TRACE(3);
+    for (int it = 0; it < p.rounds; it++) {
+        if (it < 10) MS_TRACE(4 + it);
+        for (int item = warp; item < n_items; item += MS2_WARPS) {
+            int lo = 0, hi = K - 1;                                          // class of the item: last k with item_start[k] <= item
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (item_start[mid] <= item) lo = mid; else hi = mid - 1;
+            }
+            const int k = lo;
+            const int e0 = seg_start[k] + (item - item_start[k]) * MS2_ITEM;
+            const int e1 = min(seg_start[k + 1], e0 + MS2_ITEM);
+            const double mx = means_s[2 * k], my = means_s[2 * k + 1];
+            const double two_v2 = 2.0 * v2_s[k];
+            double sx = 0.0, sy = 0.0, sp = 0.0;
+#pragma unroll 4
+            for (int e = e0 + lane; e < e1; e += 32) {
+                const uint32_t c = entries[e];
+                const double cx = (double)(c & 0xffffu), cy = (double)(c >> 16);
+                if (it == 0) {                                               // mean_shift.cu:31-34
+                    sx += cx; sy += cy; sp += 1.0;
+                } else {                                                     // mean_shift.cu:36-46
+                    const double dx = cx - mx, dy = cy - my;
+                    const double pr = exp(-(dx * dx + dy * dy) / two_v2);
+                    sx += dx * pr; sy += dy * pr; sp += pr;
+                }
+            }
+            if (it == 1) MS_TRACE(20);
+            sx = ms_warp_sum(sx);
+            sy = ms_warp_sum(sy);
+            sp = ms_warp_sum(sp);
+            if (it == 1) MS_TRACE(21);
+            if (lane == 0) {
+                partial[item * 3 + 0] = sx;
+                partial[item * 3 + 1] = sy;
+                partial[item * 3 + 2] = sp;
+            }
+        }
+        __syncthreads();
+        if (it == 1) MS_TRACE(22);
+        double* buf = all_partial + (size_t)(it & 1) * NC * K * 3;
+        for (int i = tid; i < 3 * K; i += MS2_THREADS) {
+            const int k = i / 3, comp = i - 3 * k;
+            double s = 0.0;
+            for (int item = item_start[k]; item < item_start[k + 1]; item++) s += partial[item * 3 + comp];
+            for (int r = 0; r < NC; r++) cluster.map_shared_rank(buf, r)[((size_t)rank * K + k) * 3 + comp] = s;
+        }
+        if (it == 1) MS_TRACE(23);
+        cluster.sync();
+        if (it == 1) MS_TRACE(24);
+        for (int k = tid; k < K; k += MS2_THREADS) {
+            double sx = 0.0, sy = 0.0, sp = 0.0;
+            for (int r = 0; r < NC; r++) {
+                sx += buf[((size_t)r * K + k) * 3 + 0];
+                sy += buf[((size_t)r * K + k) * 3 + 1];
+                sp += buf[((size_t)r * K + k) * 3 + 2];
+            }
+            means_s[2 * k] += sx / sp;                                       // mean_shift.py:53-55 (0/0 -> NaN)
+            means_s[2 * k + 1] += sy / sp;
+        }
+        if (it == 1) MS_TRACE(25);
+        __syncthreads();
+    }
+    MS_TRACE(14);
+    if (rank == 0)
+        for (int i = tid; i < 2 * K; i += MS2_THREADS) p.means_out[i] = means_s[i];
+    cluster.sync();   // no CTA may exit while peers can still address its shared memory
+    MS_TRACE(15);
+    if (p.trace && rank == 0 && tid == 0) p.trace[17] = (unsigned long long)clock64();
+}
+
+static size_t ms2_smem_bytes(int K, int NC, int chunk) {
+    size_t b = 0;
+    b += sizeof(double) * 2 * (size_t)NC * K * 3;
+    b += sizeof(double) * MS2_MAX_ITEMS * 3;
+    b += sizeof(double) * 3 * (size_t)K;
+    b += sizeof(unsigned long long) * MS2_WARPS;
+    b += sizeof(int) * (2 * (MS2_MAX_K + 1) + 2);
+    b += sizeof(uint32_t) * (size_t)chunk;
+    return b;
+}
+
 static size_t ms_smem_bytes(int K, int NC) {
     size_t b = 0;
     b += sizeof(double) * 2 * (size_t)NC * K * 3;
@@ -231,6 +495,37 @@ extern "C" int rdf_mean_shift(const uint16_t* labels_dev, int dim_x, int dim_y, 
     RDF_REQUIRE((int64_t)dim_x * dim_y < (1LL << 30), "rdf_mean_shift: image too large");
 
     const int npx = dim_x * dim_y;
+    // latency path: everything in shared memory (see v2 above)
+    if (num_labels <= MS2_MAX_K && npx <= MS_MAX_CLUSTER * MS2_CAP && (reinterpret_cast<uintptr_t>(labels_dev) & 15u) == 0 &&
+        !getenv("RDF_MS_V1")) {
+        int NC = (npx + 8191) / 8192;
+        if (NC > MS_MAX_CLUSTER) NC = MS_MAX_CLUSTER;
+        rdf_ms2_params q;
+        q.labels = labels_dev; q.variances = variances_dev; q.means_out = means_dev;
+        q.w = dim_x; q.h = dim_y; q.K = num_labels; q.rounds = rounds;
+        q.chunk = (((npx + NC - 1) / NC) + 7) / 8 * 8;
+        q.trace = getenv("RDF_MS_TRACE") ? reinterpret_cast<unsigned long long*>(workspace_dev) : nullptr;
+        const size_t smem2 = ms2_smem_bytes(num_labels, NC, q.chunk);
+        static size_t smem2_set = 0;
+        if (smem2 > smem2_set) {
+            RDF_CUDA(cudaFuncSetAttribute(rdf_mean_shift_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            smem2_set = smem2;
+        }
+        cudaLaunchConfig_t cfg2 = {};
+        cfg2.gridDim = dim3(NC, 1, 1);
+        cfg2.blockDim = dim3(MS2_THREADS, 1, 1);
+        cfg2.dynamicSmemBytes = smem2;
+        cfg2.stream = rdf_stream(stream);
+        cudaLaunchAttribute attr2[1];
+        attr2[0].id = cudaLaunchAttributeClusterDimension;
+        attr2[0].val.clusterDim.x = NC;
+        attr2[0].val.clusterDim.y = 1;
+        attr2[0].val.clusterDim.z = 1;
+        cfg2.attrs = attr2;
+        cfg2.numAttrs = 1;
+        RDF_CUDA(cudaLaunchKernelEx(&cfg2, rdf_mean_shift_v2_kernel, q));
+        return RDF_OK;
+    }
     const int gran = 32 * MS_WARPS;
     int NC = (npx + 8191) / 8192;                  // >= 8192 pixels per CTA before adding CTAs
     if (NC > MS_MAX_CLUSTER) NC = MS_MAX_CLUSTER;
