@@ -114,7 +114,8 @@ def main(out_dir):
         ok = (pts[:, 0] >= 0) & (pts[:, 0] < 90) & (pts[:, 1] >= 0) & (pts[:, 1] < 60)
         lab[pts[ok, 1], pts[ok, 0]] = [1, 2, 4][k]           # class index 2 (label 3) stays empty
     lab[0, 0:5] = 0
-    lab[1, 0:5] = 9                                          # > num_labels: ignored (mean_shift.cu:23)
+    # NOTE: labels above num_labels must NOT be fed to the reference kernel: Array2d::get_ptr returns nullptr for them
+    # (cu_utils.hpp:110-114) and the atomicAdd faults.  Our kernel ignores such labels; that case is tested separately.
     var = np.array([3.0, 5.0, 4.0, 6.0], dtype=np.float32)
     out['blobs.labels'] = lab
     out['blobs.variances'] = var
@@ -136,9 +137,9 @@ def main(out_dir):
     n_children = 1 << (level + 1)
     counts = torch.zeros((P, n_children, C), dtype=torch.int64, device='cuda')
     L = rk.lib()
-    import ctypes
-    rk._ok(L.ref_evaluate_random_features(N, W, H, P, C, 6, n_children, 0, n_children, rk._p(to_dev(labels)), rk._p(to_dev(depth)),
-                                          rk._p(to_dev(proposals)), rk._p(to_dev(nodes)), rk._p(counts), rk._st()))
+    labels_d, depth_d, props_d, nodes_d = to_dev(labels), to_dev(depth), to_dev(proposals), to_dev(nodes)   # keep alive
+    rk._ok(L.ref_evaluate_random_features(N, W, H, P, C, 6, n_children, 0, n_children, rk._p(labels_d), rk._p(depth_d),
+                                          rk._p(props_d), rk._p(nodes_d), rk._p(counts), rk._st()))
     torch.cuda.synchronize()
     out['hist.depth'] = depth
     out['hist.labels'] = labels

@@ -1,0 +1,83 @@
+"""CPU gate for the drop-in boundary: librdf_b200.so loads without a GPU, exports every symbol include/rdf_b200.h declares,
+the ctypes binding covers exactly that set, and argument validation works (returns an error code + message; never aborts,
+never computes on the CPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'rdf_b200.h')
+
+
+def _declared():
+    text = open(HEADER).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'RDF_API\s+[\w\s\*]+?\b(rdf_\w+)\s*\(', text)))
+
+
+def test_header_declares_the_path():
+    names = _declared()
+    for must in ['rdf_forest_create', 'rdf_eval_forest', 'rdf_eval_tree', 'rdf_composite', 'rdf_layered_run', 'rdf_mean_shift',
+                 'rdf_train_hist', 'rdf_train_pick_best', 'rdf_train_next_active', 'rdf_train_advance_pixels', 'rdf_last_error']:
+        assert must in names
+    # every entry point cites the reference interface it replaces
+    text = open(HEADER).read()
+    for ref in ['src/cuda/tree_eval.cu:24-137', 'src/cuda/tree_eval.cu:140-212', 'src/cuda/tree_eval.cu:214-248',
+                'src/decision_tree.py:233-264', 'src/cuda/mean_shift.py:19-59', 'src/cuda/tree_train.cu:4-64',
+                'src/cuda/tree_train.cu:99-236']:
+        assert ref in text, ref
+
+
+def test_library_exports_every_declared_symbol():
+    from rdf_b200 import _capi
+    lib = _capi.load()                                   # must work with no GPU present
+    for name in _declared():
+        assert hasattr(lib, name), f'{name} declared in include/rdf_b200.h but not exported by librdf_b200.so'
+    assert sorted(_capi.SIGNATURES) == _declared(), 'ctypes binding and header disagree'
+    assert lib.rdf_version() >= 100
+
+
+def test_no_hidden_exports():
+    """Only rdf_* symbols are public (built with -fvisibility=hidden): the library is a C ABI, not a C++ one."""
+    import subprocess
+    from rdf_b200 import _capi
+    out = subprocess.run(['nm', '-D', '--defined-only', _capi.LIB_PATH], capture_output=True, text=True).stdout
+    mine = [ln.split()[-1] for ln in out.splitlines() if ' T ' in ln]
+    assert mine and all(s.startswith('rdf_') for s in mine), [s for s in mine if not s.startswith('rdf_')][:5]
+
+
+def test_argument_validation_without_gpu():
+    from rdf_b200 import _capi
+    lib = _capi.load()
+    h = ctypes.c_void_p()
+    assert lib.rdf_forest_create(None, 3, 16, 4, None, ctypes.byref(h)) == -1            # RDF_ERR_INVALID
+    assert b'canon_dev' in lib.rdf_last_error()
+    assert lib.rdf_forest_create(ctypes.c_void_p(16), 3, 99, 4, None, ctypes.byref(h)) == -1
+    assert b'max_depth' in lib.rdf_last_error()
+    assert lib.rdf_eval_forest(None, None, 1, 8, 8, None, -1, None, None, 1, 1.0, None) == -1
+    assert lib.rdf_mean_shift(None, 8, 8, 2, None, 1, None, None, 0, None) == -1
+    n = ctypes.c_size_t()
+    assert lib.rdf_mean_shift_workspace_bytes(424, 240, 11, ctypes.byref(n)) == 0 and n.value >= 424 * 240 * 4
+    with pytest.raises(ValueError):
+        _capi.check(-1)
+    with pytest.raises(_capi.RdfError):
+        _capi.check(-2)
+
+
+def test_product_has_no_cpu_path():
+    """The product package never imports the oracle, and refuses host tensors."""
+    import torch
+    from rdf_b200 import _capi
+    pkg = os.path.join(ROOT, '3d-beats_b200', 'rdf_b200')
+    for fn in os.listdir(pkg):
+        if fn.endswith('.py'):
+            src = open(os.path.join(pkg, fn)).read()
+            assert 'import oracle' not in src and 'from oracle' not in src, fn
+    with pytest.raises(ValueError):
+        _capi.dptr(torch.zeros(4))
+    if not torch.cuda.is_available():
+        from rdf_b200 import buffers
+        with pytest.raises(RuntimeError):
+            buffers.GPUArray((4,), dtype='float32')

@@ -1,0 +1,113 @@
+"""world_size-2 `gloo` tests (CPU) of the multi-GPU host logic:
+  * forest eval shards by frame with no collective: the ranks' label maps concatenate to the single-rank result;
+  * the training split search shards images and sum-allreduces the integer histograms: the reduced histogram is identical to
+    the single-rank one (exact integers, order-independent), so every rank picks the same split.
+The per-rank compute stands in with the C oracle here (no GPU in this container); on a GPU box the same rdf_b200.dist helpers
+wrap the CUDA kernels (bench.py, DecisionTreeTrainer)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, '3d-beats_b200')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    import torch
+    import torch.distributed as dist
+    from rdf_b200 import dist as rdist, synth
+    from oracle import c_oracle as co
+    r, w, _ = rdist.init_from_env(backend='gloo')
+    assert (r, w) == (rank, world) and dist.get_world_size() == world
+
+    # ---- frame-sharded eval, no collective ----
+    N, H, W = 5, 40, 56                                    # 5 frames over 2 ranks: uneven shards (3 + 2)
+    forest = synth.random_forest(3, 7, 4, seed=3, ragged=True)
+    f0, f1 = rdist.shard_range(N, rank, world)
+    depth = synth.depth_frames('dense-smooth', f1 - f0, H, W, seed=8, first_frame=f0)
+    labels = np.full((f1 - f0, H, W), 65535, np.uint16)
+    co.eval_forest(forest, depth, labels, nthreads=1)
+    np.save(os.path.join(out_dir, f'labels_{rank}.npy'), labels)
+
+    # ---- image-sharded split histograms + sum-allreduce ----
+    Nt, C, F, NT, level = 4, 4, 6, 8, 2
+    i0, i1 = rdist.shard_range(Nt, rank, world)
+    tdepth = synth.depth_frames('dense-smooth', i1 - i0, H, W, seed=5, first_frame=i0)
+    tlabels = synth.train_labels(i1 - i0, H, W, first_frame=i0)
+    nodes_all = synth.random_node_assignment(synth.train_labels(Nt, H, W), level, seed=2)
+    nodes = nodes_all[i0:i1]
+    off, th = synth.random_proposals(F, NT, seed=4)
+    slot = np.arange(1 << level, dtype=np.int32)
+    hist = co.train_hist(tdepth, tlabels, nodes, slot, 1 << level, off, th, C, nthreads=1)
+    t = torch.from_numpy(hist.view(np.int32).copy())
+    dist.all_reduce(t)                                     # the path's only exchange step
+    np.save(os.path.join(out_dir, f'hist_{rank}.npy'), t.numpy().view(np.uint32))
+
+    # ---- timing helpers ----
+    assert rdist.max_over_ranks(10.0 + rank) == 10.0 + world - 1
+    assert rdist.sum_over_ranks(1.0) == float(world)
+    rdist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    from rdf_b200 import synth
+    from oracle import c_oracle as co
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+
+    N, H, W = 5, 40, 56
+    forest = synth.random_forest(3, 7, 4, seed=3, ragged=True)
+    depth = synth.depth_frames('dense-smooth', N, H, W, seed=8)
+    want = np.full((N, H, W), 65535, np.uint16)
+    co.eval_forest(forest, depth, want)
+    got = np.concatenate([np.load(tmp_path / f'labels_{r}.npy') for r in range(world)])
+    assert np.array_equal(got, want)
+
+    Nt, C, F, NT, level = 4, 4, 6, 8, 2
+    tdepth = synth.depth_frames('dense-smooth', Nt, H, W, seed=5)
+    tlabels = synth.train_labels(Nt, H, W)
+    nodes = synth.random_node_assignment(tlabels, level, seed=2)
+    off, th = synth.random_proposals(F, NT, seed=4)
+    full = co.train_hist(tdepth, tlabels, nodes, np.arange(1 << level, dtype=np.int32), 1 << level, off, th, C)
+    h0, h1 = np.load(tmp_path / 'hist_0.npy'), np.load(tmp_path / 'hist_1.npy')
+    assert np.array_equal(h0, h1), 'ranks disagree after the allreduce'
+    assert np.array_equal(h0, full), 'allreduced shard histograms differ from the single-rank histogram'
+
+
+@pytest.mark.parametrize('total,world', [(4096, 1), (4096, 8), (5, 2), (7, 8), (0, 4), (42, 4)])
+def test_shard_range_partitions(total, world):
+    from rdf_b200.dist import shard_range
+    spans = [shard_range(total, r, world) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == total
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    sizes = [b - a for a, b in spans]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` needs no GPU and prints the contract's JSON line."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '3',
+                          '--workload', 'cfg1', '--ref-frames', '1'], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['unit'] == 'Mpixels/s' and line['value'] > 0
+    assert line['cpu_baseline']['kind'] == 'port' and line['e2e']['h2d_bytes_per_step'] == 0
