@@ -19,19 +19,22 @@ extern "C" const char* rdf_last_error(void) { return g_err; }
 // canonical node = (ux,uy,vx,vy,thresh,l_next,r_next,l_pdf[C],r_pdf[C]) (src/cuda/tree_eval.cu:47).
 // "child continues" is floor(flag) == -1 exactly as the kernels test it (__float2int_rd, tree_eval.cu:101-102).
 __global__ void rdf_pack_kernel(const float* __restrict__ canon, rdf_node_hdr* __restrict__ hdr, float* __restrict__ pdf,
-                                int64_t total_nodes, int C, int CP) {
+                                int64_t total_nodes, int64_t nodes_per_tree, int D, int C, int CP) {
     const int E = 7 + 2 * C;
+    const int64_t first_last_level = ((int64_t)1 << (D - 1)) - 1;      // rows >= this are at level D-1: no children
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_nodes; i += (int64_t)gridDim.x * blockDim.x) {
         const float* nd = canon + i * E;
+        const int64_t t = i / nodes_per_tree, row = i - t * nodes_per_tree;
         rdf_node_hdr h;
         h.a = make_float4(nd[0], nd[1], nd[2], nd[3]);
-        h.thresh = nd[4];
-        h.flags = (__float2int_rd(nd[5]) == -1 ? RDF_FLAG_LEFT_CONT : 0) | (__float2int_rd(nd[6]) == -1 ? RDF_FLAG_RIGHT_CONT : 0);
-        // offsets outside the domain of the reciprocal-based divide (rdf_common.cuh) send this node down the exact path
-        if (!(rdf_fastdiv_domain(nd[0]) && rdf_fastdiv_domain(nd[1]) && rdf_fastdiv_domain(nd[2]) && rdf_fastdiv_domain(nd[3])))
-            h.flags |= RDF_FLAG_EXACT_DIV;
-        h.pad0 = 0;
-        h.pad1 = 0;
+        h.ithresh = rdf_int_thresh(nd[4]);
+        const bool last = row >= first_last_level;
+        const int child = (int)(t * nodes_per_tree + 2 * row + 1);       // left child; right = child + 1
+        h.left = __float2int_rd(nd[5]) == -1 ? (last ? RDF_NO_LEAF : child) : ~(int)(2 * i);
+        h.right = __float2int_rd(nd[6]) == -1 ? (last ? RDF_NO_LEAF : child + 1) : ~(int)(2 * i + 1);
+        // offsets outside the domain of the reciprocal divide + magic-number floor (rdf_common.cuh) -> exact path
+        h.flags = (rdf_fastfloor_domain(nd[0]) && rdf_fastfloor_domain(nd[1]) && rdf_fastfloor_domain(nd[2]) &&
+                   rdf_fastfloor_domain(nd[3])) ? 0 : RDF_FLAG_EXACT_DIV;
         hdr[i] = h;
         float* p = pdf + i * 2 * CP;
         for (int c = 0; c < CP; c++) {
@@ -45,7 +48,7 @@ static int rdf_pack(rdf_forest* f, const float* canon_dev, cudaStream_t stream) 
     const int64_t total = f->nodes_per_tree * f->T;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 32) blocks = 148 * 32;
-    rdf_pack_kernel<<<blocks, 256, 0, stream>>>(canon_dev, f->hdr, f->pdf, total, f->C, f->CP);
+    rdf_pack_kernel<<<blocks, 256, 0, stream>>>(canon_dev, f->hdr, f->pdf, total, f->nodes_per_tree, f->D, f->C, f->CP);
     RDF_LAUNCH_CHECK("rdf_pack_kernel");
     return RDF_OK;
 }
@@ -60,6 +63,8 @@ extern "C" int rdf_forest_create(const float* canon_dev, int num_trees, int max_
                 RDF_MAX_DEPTH);
     RDF_REQUIRE(num_classes >= 1 && num_classes <= RDF_MAX_CLASSES, "rdf_forest_create: num_classes=%d outside 1..%d",
                 num_classes, RDF_MAX_CLASSES);
+    RDF_REQUIRE(((int64_t)num_trees << max_depth) < ((int64_t)1 << 30),
+                "rdf_forest_create: %d trees of depth %d exceed the 2^30 nodes a packed forest can index", num_trees, max_depth);
     rdf_forest* f = new rdf_forest();
     f->T = num_trees;
     f->D = max_depth;

@@ -38,22 +38,33 @@ void rdf_set_error(const char* fmt, ...);
     } while (0)
 
 // ---- packed forest ---------------------------------------------------------------------------------------
-// One 32-byte header per node, in the canonical row order (row = 2^level - 1 + index, src/cuda/cu_utils.hpp:32-39):
-//   a = (ux, uy, vx, vy)      b = (thresh, flags, 0, 0);  flags bit0: left child continues (floor(l_next) == -1),
-//   bit1: right child continues.  Leaf pdfs live in a separate table pdf[t][row][side][CP], CP = C rounded up to 4
-//   floats so each leaf row is 16-byte aligned.
+// One 32-byte header per node (two 128-bit loads), indexed by a GLOBAL node id g = t * nodes_per_tree + row with the
+// canonical row order (row = 2^level - 1 + index, src/cuda/cu_utils.hpp:32-39):
+//   a       = (ux, uy, vx, vy)
+//   ithresh = ceil(thresh) as int32: the feature is an exact integer (difference of two uint16 probes), so
+//             f < thresh  <=>  int(f) < ceil(thresh); NaN -> INT_MIN (never left), +-huge saturate.
+//   left / right = where the walk goes for f < thresh / otherwise:
+//             >= 0        global id of the child node (the reference's flag floor(l_next) == -1, tree_eval.cu:101-102)
+//             <  0        ~leaf_id, leaf_id = 2 * g + side: the walk ends, its pdf row is pdf[leaf_id][CP]
+//             RDF_NO_LEAF the walk falls off level D-1 with a "continue" flag and adds nothing (tree_eval.cu:95-128)
+//   flags   = RDF_FLAG_EXACT_DIV when an offset is outside the domain of the reciprocal-based divide (below).
+// Explicit child ids make a level cost one select instead of index arithmetic + flag tests, and leave the node order
+// free (nodes may later be re-ordered for locality without touching the kernels).
+// Leaf pdfs live in a separate table pdf[T * nodes_per_tree * 2][CP], CP = C rounded up to 4 floats (16-byte rows).
 struct __align__(32) rdf_node_hdr {
     float4 a;
-    float thresh;
+    int ithresh;
+    int left, right;
     int flags;
-    int pad0, pad1;
 };
+
+#define RDF_NO_LEAF ((int)0x80000000)
 
 struct rdf_forest {
     int T, D, C, CP;
     int64_t nodes_per_tree;       // 2^D - 1
-    rdf_node_hdr* hdr;            // [T][nodes_per_tree]
-    float* pdf;                   // [T][nodes_per_tree][2][CP]
+    rdf_node_hdr* hdr;            // [T * nodes_per_tree]
+    float* pdf;                   // [T * nodes_per_tree * 2][CP]
     size_t packed_bytes;
     int device;
 };
@@ -76,8 +87,6 @@ struct rdf_forest {
 // Values outside that domain (NaN, inf, denormal-range or huge offsets) are flagged per node at pack time
 // (RDF_FLAG_EXACT_DIV) and take the exact path.  rdf_selftest_fastdiv() checks the identity on the GPU over billions of
 // (a, d) pairs including the adversarial neighbourhood a ~ n*d +- few ulp.
-#define RDF_FLAG_LEFT_CONT 1
-#define RDF_FLAG_RIGHT_CONT 2
 #define RDF_FLAG_EXACT_DIV 4
 
 __host__ __device__ __forceinline__ bool rdf_fastdiv_domain(float a) {
@@ -95,6 +104,33 @@ __device__ __forceinline__ float rdf_div_fast(float a, float df, float rcp) {
 
 __device__ __forceinline__ int rdf_offset_fast(float su, float df, float rcp) {
     return __float2int_rd(rdf_div_fast(su, df, rcp));
+}
+
+// Packed-forest path: floor + "add the pixel coordinate" in ONE FMA-pipe instruction, no conversion unit.
+// For |q| <= 2^21 and an integer coordinate 0 <= X < 2^16, the exact sum q + X + 1.5*2^23 lies in [2^23, 2^24) where
+// floats are the integers, so add.rm.f32 (round toward -inf) returns exactly floor(q) + X + 1.5*2^23 and the low
+// mantissa bits hold floor(q) + X: identical to cvt.rmi.s32.f32(q) + X of the reference.  (F2I runs on the
+// quarter-rate XU pipe: four of them per node-step were 49 % XU utilisation in profiles/r01_ncu_eval_v1.md.)
+#define RDF_MAGIC_F 12582912.0f          // 1.5 * 2^23
+#define RDF_MAGIC_BITS 0x4B400000        // __float_as_int(RDF_MAGIC_F)
+#define RDF_FASTFLOOR_MAX 2097152.0f     // 2^21: bound on |scale * u| for the path above
+
+__host__ __device__ __forceinline__ bool rdf_fastfloor_domain(float a) {
+    const float m = fabsf(a);
+    return a == 0.f || (m >= 8.6736174e-19f && m <= RDF_FASTFLOOR_MAX);   // 2^-60 .. 2^21; false for NaN / inf
+}
+
+// coordinate + floor(RN(su / d)), cm = (float)coordinate + RDF_MAGIC_F
+__device__ __forceinline__ int rdf_coord_fast(float su, float df, float rcp, float cm) {
+    return __float_as_int(__fadd_rd(rdf_div_fast(su, df, rcp), cm)) - RDF_MAGIC_BITS;
+}
+
+// ceil(thresh) for the integer compare of the packed path (see rdf_node_hdr)
+__host__ __device__ __forceinline__ int rdf_int_thresh(float t) {
+    if (!(t == t)) return (int)0x80000000;                   // NaN: f < NaN is false for every f
+    if (t >= 2147483648.f) return 0x7fffffff;
+    if (t <= -2147483648.f) return (int)0x80000000;
+    return (int)ceilf(t);
 }
 
 // Array3d<uint16>::get with default 65535 (src/cuda/cu_utils.hpp:58-62,79-86): bounds are per image.
@@ -125,10 +161,47 @@ __device__ __forceinline__ float rdf_feature(const uint16_t* __restrict__ img, i
     return __fsub_rn(pu, pv);
 }
 
+// img[idx] through the read-only path with ONE address instruction (mad.wide.u32): the image base stays in a register
+// pair and the 32-bit pixel index is scaled and added in the FMA pipe (the compiler's own lowering spent five integer
+// instructions per probe on 64-bit adds).
+__device__ __forceinline__ unsigned rdf_ldg_u16(const uint16_t* __restrict__ img, unsigned idx) {
+    unsigned short v;
+    asm("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, 2, %2;\n\tld.global.nc.u16 %0, [a];\n\t}" : "=h"(v) : "r"(idx), "l"(img));
+    return v;
+}
+
+// Packed path: the feature as an exact integer, int(pu) - int(pv).  xm / ym = (float)X / Y + RDF_MAGIC_F.
+template <bool EXACT>
+__device__ __forceinline__ int rdf_feature_i(const uint16_t* __restrict__ img, int W, int H, int X, int Y, float df, float rcp,
+                                             float xm, float ym, float sux, float suy, float svx, float svy) {
+    int ux, uy, vx, vy;
+    if (EXACT) {
+        ux = (int)((unsigned)X + (unsigned)rdf_offset_exact(sux, df));
+        uy = (int)((unsigned)Y + (unsigned)rdf_offset_exact(suy, df));
+        vx = (int)((unsigned)X + (unsigned)rdf_offset_exact(svx, df));
+        vy = (int)((unsigned)Y + (unsigned)rdf_offset_exact(svy, df));
+    } else {
+        ux = rdf_coord_fast(sux, df, rcp, xm);
+        uy = rdf_coord_fast(suy, df, rcp, ym);
+        vx = rdf_coord_fast(svx, df, rcp, xm);
+        vy = rdf_coord_fast(svy, df, rcp, ym);
+    }
+    unsigned pu = RDF_NO_PIXEL, pv = RDF_NO_PIXEL;
+    if ((unsigned)ux < (unsigned)W && (unsigned)uy < (unsigned)H) pu = rdf_ldg_u16(img, (unsigned)(uy * W + ux));
+    if ((unsigned)vx < (unsigned)W && (unsigned)vy < (unsigned)H) pv = rdf_ldg_u16(img, (unsigned)(vy * W + vx));
+    return (int)pu - (int)pv;
+}
+
 // scale domain for the fast path: |scale*u| stays normal when 2^-30 <= |scale| <= 2^30 and u is in its own domain
 static inline bool rdf_scale_fast_ok(float s) {
     const float m = s < 0 ? -s : s;
     return m >= 9.3132257e-10f && m <= 1.0737418e9f;
+}
+
+// packed path (rdf_coord_fast): nodes are flagged for |u| <= 2^21 at pack time, so |scale| <= 1 keeps |scale*u| <= 2^21
+static inline bool rdf_scale_fastfloor_ok(float s) {
+    const float m = s < 0 ? -s : s;
+    return m >= 9.3132257e-10f && m <= 1.0f;
 }
 
 static inline cudaStream_t rdf_stream(void* s) { return (cudaStream_t)s; }

@@ -31,12 +31,13 @@ __global__ void __launch_bounds__(256) rdf_eval_packed_kernel(const rdf_eval_par
     const size_t li = ((size_t)n * p.h + y) * p.w + x;
     if (p.filter_class != -1 && (int)__ldg(p.filter + li) != p.filter_class) return;   // tree_eval.cu:81-85
     const uint16_t* img = p.depth + (size_t)n * p.H * p.W;
+    asm volatile("" : "+l"(img));                 // keep the image base in registers (do not rematerialise it per probe)
     const int X = x * p.r, Y = y * p.r;
     const unsigned d = __ldg(img + (size_t)Y * p.W + X);
     if (d == 0u || d == RDF_NO_PIXEL) return;                                            // tree_eval.cu:88-89
-    int leaf[T];
-    rdf_walk<T, SCALE1, FORCE_EXACT>(p.fv, img, p.W, p.H, X, Y, (float)d, p.scale, leaf);
-    const int lab = rdf_vote<T>(p.fv, leaf, p.probs ? p.probs + li * p.fv.C : nullptr);
+    int state[T];
+    rdf_walk<T, SCALE1, FORCE_EXACT>(p.fv, img, p.W, p.H, X, Y, d, p.scale, state);
+    const int lab = rdf_vote<T>(p.fv, state, p.probs ? p.probs + li * p.fv.C : nullptr);
     p.labels[li] = (uint16_t)lab;
 }
 
@@ -135,7 +136,8 @@ static int rdf_warp_w() {
 
 template <int T, int WARP_W>
 static void rdf_launch_packed_tw(const rdf_eval_params& p, dim3 grid, cudaStream_t stream) {
-    if (!rdf_scale_fast_ok(p.scale))
+    // fast path (reciprocal divide + magic-number floor): |scale| in [2^-30, 1] and coordinates below 2^16
+    if (!rdf_scale_fastfloor_ok(p.scale) || p.W > 65535 || p.H > 65535)
         rdf_eval_packed_kernel<T, WARP_W, false, true><<<grid, 256, 0, stream>>>(p);
     else if (p.scale == 1.f)
         rdf_eval_packed_kernel<T, WARP_W, true, false><<<grid, 256, 0, stream>>>(p);
@@ -158,6 +160,7 @@ extern "C" int rdf_eval_forest(const rdf_forest_t* forest, const uint16_t* depth
     RDF_REQUIRE(forest && depth_dev && labels_dev, "rdf_eval_forest: NULL argument");
     RDF_REQUIRE(num_images >= 0 && dim_x > 0 && dim_y > 0 && labels_reduce >= 1, "rdf_eval_forest: bad shape N=%d W=%d H=%d r=%d",
                 num_images, dim_x, dim_y, labels_reduce);
+    RDF_REQUIRE((int64_t)dim_x * dim_y < ((int64_t)1 << 31), "rdf_eval_forest: image of %dx%d pixels is too large", dim_x, dim_y);
     const int w = dim_x / labels_reduce, h = dim_y / labels_reduce;
     if (num_images == 0 || w == 0 || h == 0) return RDF_OK;
     if (!filter_dev) filter_class = -1;

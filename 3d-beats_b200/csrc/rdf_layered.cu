@@ -68,7 +68,6 @@ __global__ void __launch_bounds__(256) rdf_layered_kernel(const __grid_constant_
     const int X = x * p.r, Y = y * p.r;
     const unsigned d = __ldg(p.depth + (size_t)Y * p.W + X);
     const bool valid = !(d == 0u || d == RDF_NO_PIXEL);
-    const float df = (float)d;
 
     // per-layer labels of this pixel, 16 bits each, packed so the layer loop can stay rolled (RDF_MAX_LAYERS == 8)
     unsigned long long lab_lo = ~0ull, lab_hi = ~0ull;              // all 65535 = the reference's pre-fill
@@ -90,7 +89,7 @@ __global__ void __launch_bounds__(256) rdf_layered_kernel(const __grid_constant_
         if (fm >= 0 && p.filter_class[i] != -1) run = run && ((int)get_lab(fm) == p.filter_class[i]);
         unsigned l = RDF_NO_PIXEL;
         if (run) {
-            l = (unsigned)rdf_eval_pixel<SCALE1, FORCE_EXACT>(p.fv[i], p.depth, p.W, p.H, X, Y, df, p.scale, nullptr);
+            l = (unsigned)rdf_eval_pixel<SCALE1, FORCE_EXACT>(p.fv[i], p.depth, p.W, p.H, X, Y, d, p.scale, nullptr);
             set_lab(i, l);
         }
         p.layer_labels[i][li] = (uint16_t)l;
@@ -155,41 +154,32 @@ __global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_co
     }
     const int layer = q.walk_layer[walk], t = q.walk_tree[walk];
     const rdf_forest_view& fv = p.fv[layer];
-    int leaf = -1;
+    int leaf = RDF_NO_LEAF;                                                  // ~leaf_id once the walk has ended
     if (valid) {
         const float df = (float)d;
         const float rcp = __frcp_rn(df);
-        const rdf_node_hdr* base = fv.hdr + (int64_t)t * fv.nodes_per_tree;
-        int row = 0;
-        float4 a = __ldg(reinterpret_cast<const float4*>(base));
-        float2 b = __ldg(reinterpret_cast<const float2*>(base) + 2);
+        const float xm = (float)X + RDF_MAGIC_F, ym = (float)Y + RDF_MAGIC_F;
+        rdf_hdr_regs h = rdf_load_hdr(fv.hdr, t * fv.nodes_per_tree);
         for (int j = 0; j < fv.D; j++) {
-            float4 al = a, ar = a;
-            float2 bl = b, br = b;
-            if (j + 1 < fv.D) {                                                // both children, adjacent rows 2r+1, 2r+2
-                const rdf_node_hdr* c = base + 2 * (int64_t)row + 1;
-                al = __ldg(reinterpret_cast<const float4*>(c));
-                bl = __ldg(reinterpret_cast<const float2*>(c) + 2);
-                ar = __ldg(reinterpret_cast<const float4*>(c + 1));
-                br = __ldg(reinterpret_cast<const float2*>(c + 1) + 2);
-            }
-            const int fl = __float_as_int(b.y);
-            float sx = a.x, sy = a.y, sz = a.z, sw = a.w;
+            // both children (when they are nodes) are requested while the probes of this node are in flight
+            rdf_hdr_regs hl = h, hr = h;
+            if (h.b.y >= 0) hl = rdf_load_hdr(fv.hdr, h.b.y);
+            if (h.b.z >= 0) hr = rdf_load_hdr(fv.hdr, h.b.z);
+            float sx = h.a.x, sy = h.a.y, sz = h.a.z, sw = h.a.w;
             if (!SCALE1) {
                 sx = __fmul_rn(p.scale, sx); sy = __fmul_rn(p.scale, sy);
                 sz = __fmul_rn(p.scale, sz); sw = __fmul_rn(p.scale, sw);
             }
-            float f;
-            if (FORCE_EXACT || (fl & RDF_FLAG_EXACT_DIV)) f = rdf_feature<true>(p.depth, p.W, p.H, X, Y, df, rcp, sx, sy, sz, sw);
-            else f = rdf_feature<false>(p.depth, p.W, p.H, X, Y, df, rcp, sx, sy, sz, sw);
-            const int side = (f < b.x) ? 0 : 1;
-            if (!((fl >> side) & 1)) {
-                leaf = 2 * row + side;
+            int f;
+            if (FORCE_EXACT || (h.b.w & RDF_FLAG_EXACT_DIV)) f = rdf_feature_i<true>(p.depth, p.W, p.H, X, Y, df, rcp, xm, ym, sx, sy, sz, sw);
+            else f = rdf_feature_i<false>(p.depth, p.W, p.H, X, Y, df, rcp, xm, ym, sx, sy, sz, sw);
+            const bool go_left = f < h.b.x;
+            const int next = go_left ? h.b.y : h.b.z;
+            if (next < 0) {
+                leaf = next;
                 break;
             }
-            row = 2 * row + 1 + side;
-            a = side ? ar : al;
-            b = side ? br : bl;
+            h = go_left ? hl : hr;
         }
     }
     leaf_s[walk][lane] = leaf;
@@ -202,8 +192,8 @@ __global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_co
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int tt = 0; tt < fv.T; tt++) {
                 const int lf = leaf_s[walk + tt][lane];
-                if (lf >= 0) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(fv.pdf + ((int64_t)tt * fv.nodes_per_tree * 2 + lf) * fv.CP + c));
+                if (lf != RDF_NO_LEAF) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(fv.pdf + (size_t)(unsigned)(~lf) * fv.CP + c));
                     s.x = __fadd_rn(s.x, v.x); s.y = __fadd_rn(s.y, v.y); s.z = __fadd_rn(s.z, v.z); s.w = __fadd_rn(s.w, v.w);
                 }
             }
@@ -291,6 +281,8 @@ extern "C" int rdf_layered_run(const rdf_forest_t* const* forests, int num_layer
     p.tiles_x = (p.w + 31) / 32;
     p.scale = scale;
     const int tiles_y = (p.h + 7) / 8;
+    RDF_REQUIRE((int64_t)dim_x * dim_y < ((int64_t)1 << 31), "rdf_layered_run: image of %dx%d pixels is too large", dim_x, dim_y);
+    const bool fast = rdf_scale_fastfloor_ok(scale) && dim_x <= 65535 && dim_y <= 65535;   // see rdf_common.cuh
     // latency path: one warp per tree walk (see rdf_layered_walks_kernel)
     int num_walks = 0;
     for (int i = 0; i < num_layers; i++) num_walks += forests[i]->T;
@@ -309,7 +301,7 @@ extern "C" int rdf_layered_run(const rdf_forest_t* const* forests, int num_layer
         }
         const int nb = q.base.tiles_x * ((p.h + 3) / 4);
         dim3 block(32, num_walks, 1);
-        if (!rdf_scale_fast_ok(scale))
+        if (!fast)
             rdf_layered_walks_kernel<false, true><<<nb, block, 0, rdf_stream(stream)>>>(q);
         else if (scale == 1.f)
             rdf_layered_walks_kernel<true, false><<<nb, block, 0, rdf_stream(stream)>>>(q);
@@ -319,7 +311,7 @@ extern "C" int rdf_layered_run(const rdf_forest_t* const* forests, int num_layer
         return RDF_OK;
     }
     const int nblk = p.tiles_x * tiles_y;
-    if (!rdf_scale_fast_ok(scale))
+    if (!fast)
         rdf_layered_kernel<8, false, true><<<nblk, 256, 0, rdf_stream(stream)>>>(p);
     else if (scale == 1.f)
         rdf_layered_kernel<8, true, false><<<nblk, 256, 0, rdf_stream(stream)>>>(p);

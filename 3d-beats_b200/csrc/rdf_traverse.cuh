@@ -4,6 +4,10 @@
 // node-header loads back to back, then the 2T depth probes, then the T compares.  The T walks are independent
 // dependency chains, so a single thread keeps T header loads / 2T probes in flight (memory-level parallelism
 // without needing T times the warps), and the summation order of leaf pdfs stays tree 0..T-1 (SURVEY note N1).
+//
+// Instruction budget per node-step (the kernel is issue-bound, profiles/r01_ncu_eval_v1.md): explicit child ids (one
+// select per level), integer thresholds (no int->float conversions), magic-number floor (no float->int conversions),
+// 32-bit image indices (no 64-bit address arithmetic per probe).
 #pragma once
 #include "rdf_common.cuh"
 
@@ -12,7 +16,7 @@
 struct rdf_forest_view {
     const rdf_node_hdr* hdr;
     const float* pdf;
-    int64_t nodes_per_tree;
+    int nodes_per_tree;
     int T, D, C, CP;
 };
 
@@ -20,7 +24,7 @@ static inline rdf_forest_view rdf_view(const rdf_forest* f) {
     rdf_forest_view v;
     v.hdr = f->hdr;
     v.pdf = f->pdf;
-    v.nodes_per_tree = f->nodes_per_tree;
+    v.nodes_per_tree = (int)f->nodes_per_tree;
     v.T = f->T;
     v.D = f->D;
     v.C = f->C;
@@ -28,71 +32,79 @@ static inline rdf_forest_view rdf_view(const rdf_forest* f) {
     return v;
 }
 
-// Walk T trees from the root.  leaf[t] = 2*row + side of the reached leaf, or -1 if the walk fell off level D-1
-// with a "continue" flag (adds nothing, src/cuda/tree_eval.cu:95-128).
+// One node-step of one walk: header (two 128-bit loads) -> feature -> next node id (>= 0) or ~leaf_id / RDF_NO_LEAF (< 0).
+struct rdf_hdr_regs {
+    float4 a;
+    int4 b;          // ithresh, left, right, flags
+};
+
+// one 256-bit load per header (LDG.E.256, new with sm_100): half the L1 tag lookups of two 128-bit loads
+__device__ __forceinline__ rdf_hdr_regs rdf_load_hdr(const rdf_node_hdr* __restrict__ hdr, int node) {
+    rdf_hdr_regs h;
+    asm("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %8, 32, %9;\n\t"
+        "ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [a];\n\t}"
+        : "=f"(h.a.x), "=f"(h.a.y), "=f"(h.a.z), "=f"(h.a.w), "=r"(h.b.x), "=r"(h.b.y), "=r"(h.b.z), "=r"(h.b.w)
+        : "r"(node), "l"(hdr));
+    return h;
+}
+
+// Walk T trees from their roots.  On return state[t] < 0: ~leaf_id of the reached leaf, or RDF_NO_LEAF if the walk fell
+// off level D-1 with a "continue" flag (adds nothing, src/cuda/tree_eval.cu:95-128).
 // SCALE1: scale == 1.0f, so scale*u == u exactly and the multiplies are dropped.  FORCE_EXACT: always use __fdiv_rn
-// (scale outside the fast-divide domain); otherwise nodes flagged RDF_FLAG_EXACT_DIV take the exact path per level.
+// (scale outside the fast domain); otherwise nodes flagged RDF_FLAG_EXACT_DIV take the exact path per level.
 template <int T, bool SCALE1, bool FORCE_EXACT>
 __device__ __forceinline__ void rdf_walk(const rdf_forest_view& fv, const uint16_t* __restrict__ img, int W, int H, int X,
-                                         int Y, float df, float scale, int (&leaf)[T]) {
-    int row[T];
-#pragma unroll
-    for (int t = 0; t < T; t++) {
-        row[t] = 0;
-        leaf[t] = -1;
-    }
+                                         int Y, unsigned d, float scale, int (&state)[T]) {
+    const float df = (float)d;
     const float rcp = __frcp_rn(df);                                 // RN(1/d), once per pixel
-    unsigned alive = (1u << T) - 1u;
-    for (int j = 0; j < fv.D && alive; j++) {
-        float4 a[T];
-        float th[T];
-        int fl[T];
+    const float xm = (float)X + RDF_MAGIC_F, ym = (float)Y + RDF_MAGIC_F;   // exact: X, Y < 2^16
+#pragma unroll
+    for (int t = 0; t < T; t++) state[t] = t * fv.nodes_per_tree;
+    for (int j = 0; j < fv.D; j++) {
+        int all = state[0];
+#pragma unroll
+        for (int t = 1; t < T; t++) all &= state[t];
+        if (all < 0) break;                                          // every walk of this pixel has ended
+        rdf_hdr_regs h[T];
         int any_flags = 0;
 #pragma unroll
         for (int t = 0; t < T; t++) {
-            // dead walks re-read their last node: harmless, keeps the loop branch-free
-            const float4* p = reinterpret_cast<const float4*>(fv.hdr + (int64_t)t * fv.nodes_per_tree + row[t]);
-            a[t] = __ldg(p);
-            const float2 b = __ldg(reinterpret_cast<const float2*>(p + 1));
-            th[t] = b.x;
-            fl[t] = __float_as_int(b.y);
-            any_flags |= fl[t];
+            // ended walks re-read their tree's root (cached): harmless, keeps the loop branch-free
+            h[t] = rdf_load_hdr(fv.hdr, max(state[t], t * fv.nodes_per_tree));
+            any_flags |= h[t].b.w;
             if (!SCALE1) {
-                a[t].x = __fmul_rn(scale, a[t].x);
-                a[t].y = __fmul_rn(scale, a[t].y);
-                a[t].z = __fmul_rn(scale, a[t].z);
-                a[t].w = __fmul_rn(scale, a[t].w);
+                h[t].a.x = __fmul_rn(scale, h[t].a.x);
+                h[t].a.y = __fmul_rn(scale, h[t].a.y);
+                h[t].a.z = __fmul_rn(scale, h[t].a.z);
+                h[t].a.w = __fmul_rn(scale, h[t].a.w);
             }
         }
-        float f[T];
+        int f[T];
         if (FORCE_EXACT || (any_flags & RDF_FLAG_EXACT_DIV)) {
 #pragma unroll
-            for (int t = 0; t < T; t++) f[t] = rdf_feature<true>(img, W, H, X, Y, df, rcp, a[t].x, a[t].y, a[t].z, a[t].w);
+            for (int t = 0; t < T; t++)
+                f[t] = rdf_feature_i<true>(img, W, H, X, Y, df, rcp, xm, ym, h[t].a.x, h[t].a.y, h[t].a.z, h[t].a.w);
         } else {
 #pragma unroll
-            for (int t = 0; t < T; t++) f[t] = rdf_feature<false>(img, W, H, X, Y, df, rcp, a[t].x, a[t].y, a[t].z, a[t].w);
+            for (int t = 0; t < T; t++)
+                f[t] = rdf_feature_i<false>(img, W, H, X, Y, df, rcp, xm, ym, h[t].a.x, h[t].a.y, h[t].a.z, h[t].a.w);
         }
 #pragma unroll
         for (int t = 0; t < T; t++) {
-            const int side = (f[t] < th[t]) ? 0 : 1;                // NaN threshold -> right (tree_eval.cu:106)
-            const bool is_alive = (alive >> t) & 1u;
-            const bool cont = (fl[t] >> side) & 1;
-            if (is_alive) {
-                if (cont) {
-                    row[t] = 2 * row[t] + 1 + side;                  // (2^(j+1)-1) + 2g + side
-                } else {
-                    leaf[t] = 2 * row[t] + side;
-                    alive &= ~(1u << t);
-                }
-            }
+            const int next = (f[t] < h[t].b.x) ? h[t].b.y : h[t].b.z;   // NaN threshold -> INT_MIN -> right (tree_eval.cu:106)
+            state[t] = state[t] < 0 ? state[t] : next;
         }
     }
+#pragma unroll
+    for (int t = 0; t < T; t++)
+        if (state[t] >= 0) state[t] = RDF_NO_LEAF;                   // D levels done and still on a node (cannot happen
+                                                                     // with a packed forest, kept as a guard)
 }
 
 // get_best_pdf_chance over the tree-ordered sum of the reached leaf pdfs (src/cuda/tree_eval.cu:7-21,125).
 // probs (optional): receives sum / T per class.
 template <int T>
-__device__ __forceinline__ int rdf_vote(const rdf_forest_view& fv, const int (&leaf)[T], float* __restrict__ probs) {
+__device__ __forceinline__ int rdf_vote(const rdf_forest_view& fv, const int (&state)[T], float* __restrict__ probs) {
     float best = 0.f;
     int lab = 0;
     const float inv_t = (float)fv.T;
@@ -100,9 +112,8 @@ __device__ __forceinline__ int rdf_vote(const rdf_forest_view& fv, const int (&l
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int t = 0; t < T; t++) {
-            if (leaf[t] >= 0) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(
-                    fv.pdf + ((int64_t)t * fv.nodes_per_tree * 2 + leaf[t]) * fv.CP + c));
+            if (state[t] != RDF_NO_LEAF) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(fv.pdf + (size_t)(unsigned)(~state[t]) * fv.CP + c));
                 s.x = __fadd_rn(s.x, v.x);
                 s.y = __fadd_rn(s.y, v.y);
                 s.z = __fadd_rn(s.z, v.z);
@@ -126,12 +137,12 @@ __device__ __forceinline__ int rdf_vote(const rdf_forest_view& fv, const int (&l
 // Evaluate one forest at one pixel (T <= RDF_FAST_MAX_TREES, dispatched on the runtime tree count).
 template <bool SCALE1, bool FORCE_EXACT>
 __device__ __forceinline__ int rdf_eval_pixel(const rdf_forest_view& fv, const uint16_t* __restrict__ img, int W, int H,
-                                              int X, int Y, float df, float scale, float* __restrict__ probs) {
-#define RDF_CASE(TT)                                                             \
-    case TT: {                                                                   \
-        int leaf[TT];                                                            \
-        rdf_walk<TT, SCALE1, FORCE_EXACT>(fv, img, W, H, X, Y, df, scale, leaf); \
-        return rdf_vote<TT>(fv, leaf, probs);                                    \
+                                              int X, int Y, unsigned d, float scale, float* __restrict__ probs) {
+#define RDF_CASE(TT)                                                            \
+    case TT: {                                                                  \
+        int st[TT];                                                             \
+        rdf_walk<TT, SCALE1, FORCE_EXACT>(fv, img, W, H, X, Y, d, scale, st);   \
+        return rdf_vote<TT>(fv, st, probs);                                     \
     }
     switch (fv.T) {
         RDF_CASE(1)
