@@ -123,13 +123,14 @@ static int rdf_launch_canon(const rdf_eval_canon_params& p, cudaStream_t stream)
     return RDF_OK;
 }
 
-// warp footprint: 8x4 patches by default (2-D locality), overridable for experiments: RDF_WARP_W in {8,16,32}
+// warp footprint: 16x2 patches by default (8x4 / 16x2 / 32x1 measured within 2 % of each other on cfg3: the probe gathers
+// are scattered by path divergence, not by the patch shape), overridable for experiments: RDF_WARP_W in {8,16,32}
 static int rdf_warp_w() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("RDF_WARP_W");
-        v = e ? atoi(e) : 8;
-        if (v != 8 && v != 16 && v != 32) v = 8;
+        v = e ? atoi(e) : 16;
+        if (v != 8 && v != 16 && v != 32) v = 16;
     }
     return v;
 }

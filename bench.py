@@ -384,10 +384,11 @@ def main():
         except Exception:
             pass
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
-                'kernel': f'rdf_eval_packed_kernel<{T},8>', 'algorithmic_bytes_per_pixel': b_alg, 'peak_source': peak_src,
+                'kernel': f'rdf_eval_packed_kernel<{T},*,true,false>', 'algorithmic_bytes_per_pixel': b_alg, 'peak_source': peak_src,
                 'compulsory_hbm_frac': 4.0 * px_per_launch / (kernel_ms * 1e-3) / 1e9 / peak,
                 'node_steps_per_s': T * D * px_per_launch / (kernel_ms * 1e-3),
-                'note': 'logical-traffic roofline (SURVEY 8d): can exceed 1.0 when the forest is cache-resident'}
+                'note': 'logical-traffic roofline (SURVEY 8d): exceeds 1.0 because the forest is cache-resident; the binding '
+                        'resource is the L1 data pipe (90 % of peak under ncu, profiles/r01_ncu_eval_v2.md)'}
 
     line = {
         'metric': 'forest_eval_mpixels_per_s', 'value': value, 'unit': 'Mpixels/s', 'n_gpus': world, 'steps': args.steps,
