@@ -492,6 +492,8 @@ class DecisionTreeTrainer():
         return offsets, thresholds
 
     def _dist(self):
+        if self.process_group is False:                     # explicitly local, even inside an initialised process group
+            return None
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1:
             return dist
