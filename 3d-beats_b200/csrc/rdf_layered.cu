@@ -134,6 +134,9 @@ struct rdf_layered2_params {
 template <bool SCALE1, bool FORCE_EXACT>
 __global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_constant__ rdf_layered2_params q) {
     const rdf_layered_params& p = q.base;
+    // let a dependent grid (the mean shift that follows in the live pipeline) be scheduled now; it waits for this grid's
+    // completion itself (griddepcontrol.wait) before reading the label images
+    asm volatile("griddepcontrol.launch_dependents;");
     __shared__ int leaf_s[RL2_MAX_WALKS][32];
     __shared__ unsigned short lab_s[RDF_MAX_LAYERS][32];
     const int lane = threadIdx.x, walk = threadIdx.y;

@@ -21,6 +21,7 @@ namespace cg = cooperative_groups;
 #define MS_WARPS (MS_THREADS / 32)
 #define MS_MAX_ITEMS 1024
 #define MS_MAX_CLUSTER 8
+#define MS2_MAX_CLUSTER 16                // non-portable cluster size (opt-in attribute), latency path only
 
 struct rdf_ms_params {
     const uint16_t* labels;
@@ -216,11 +217,12 @@ __global__ void __launch_bounds__(MS_THREADS) rdf_mean_shift_kernel(const rdf_ms
 #define MS2_THREADS 1024
 #define MS2_WARPS 32
 #define MS2_GROUPS 7                      // 56 pixels per thread -> up to 57344 pixels per CTA
-#define MS2_CAP 51200                     // entries per CTA kept in shared memory (200 KB)
+#define MS2_CAP 50944                     // entries per CTA kept in shared memory (199 KB): 8 CTAs cover 848x480
 #define MS2_MAX_K 16
 #define MS2_NG (MS2_MAX_K / 4)
-#define MS2_ITEM 256
+#define MS2_ITEM 64
 #define MS2_MAX_ITEMS (MS2_CAP / MS2_ITEM + MS2_MAX_K)
+#define MS2_ITEM_CLASS_BYTES ((MS2_MAX_ITEMS + 15) / 16 * 16)
 
 struct rdf_ms2_params {
     const uint16_t* labels;
@@ -241,30 +243,66 @@ __device__ __forceinline__ unsigned long long ms_now() {
         if (p.trace && rank == 0 && tid == 0) p.trace[slot] = ms_now();       \
     } while (0)
 
-__device__ __forceinline__ unsigned long long ms2_block_exscan(unsigned long long v, unsigned long long* warp_tot,
-                                                               unsigned long long* total) {
+// exp(x) for x <= 0 (or NaN), straight-line: the libdevice exp is ~60 dependent fp64 instructions with branches, and the
+// rounds of the latency path are one long dependency chain per lane.  Cody-Waite reduction x = k ln2 + r, |r| <= ln2/2,
+// degree-13 Taylor polynomial in Estrin form (truncation 4e-18, ~11 dependent operations), 2^k applied in two factors so that
+// results below 2^-1022 underflow gradually like exp() does.  Differs from exp() by a few ulp at most (centroids are compared
+// at 1e-5); NaN stays NaN (a zero variance with a pixel on the mean gives 0/0, as in the reference).
+__device__ __forceinline__ double ms_exp_nonpos(double x) {
+    x = x < -746.0 ? -746.0 : x;                                            // exp(-746) == 0 in fp64; keeps NaN
+    const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);    // 1.5 * 2^52: low word of t = rint(x log2 e)
+    const int k = __double2loint(t);
+    const double kf = t - 6755399441055744.0;
+    double r = fma(kf, -6.93147180369123816490e-01, x);
+    r = fma(kf, -1.90821492927058770002e-10, r);
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double a0 = fma(1.0, r, 1.0);
+    const double a1 = fma(1.0 / 6.0, r, 0.5);
+    const double a2 = fma(1.0 / 120.0, r, 1.0 / 24.0);
+    const double a3 = fma(1.0 / 5040.0, r, 1.0 / 720.0);
+    const double a4 = fma(1.0 / 362880.0, r, 1.0 / 40320.0);
+    const double a5 = fma(1.0 / 39916800.0, r, 1.0 / 3628800.0);
+    const double a6 = fma(1.0 / 6227020800.0, r, 1.0 / 479001600.0);
+    const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
+    const double d0 = fma(b1, r4, b0), d1 = fma(a6, r4, b2);
+    const double pl = fma(d1, r8, d0);
+    const int k1 = k >> 1, k2 = k - k1;
+    return (pl * __hiloint2double((k1 + 1023) << 20, 0)) * __hiloint2double((k2 + 1023) << 20, 0);
+}
+
+// Block-wide exclusive scan of MS2_NG 64-bit words per thread at once (each word = four 16-bit class counters): one
+// pass of warp shuffles per word, ONE shared-memory exchange and two barriers for all words together.
+// warp_tot: [MS2_NG][MS2_WARPS].  pre[c] <- exclusive prefix of v[c] over the block, tot[c] <- block total.
+__device__ __forceinline__ void ms2_block_exscan(const unsigned long long (&v)[MS2_NG], unsigned long long* warp_tot,
+                                                 unsigned long long (&pre)[MS2_NG], unsigned long long (&tot)[MS2_NG]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long incl = v;
+    unsigned long long incl[MS2_NG];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+    for (int c = 0; c < MS2_NG; c++) {
+        incl[c] = v[c];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl[c], o);
+            if (lane >= o) incl[c] += t;
+        }
+        if (lane == 31) warp_tot[c * MS2_WARPS + warp] = incl[c];
     }
-    __syncthreads();                       // warp_tot reuse across calls
-    if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    if (warp == 0) {
-        unsigned long long t = warp_tot[lane];
+    if (warp < MS2_NG) {                    // warp c scans the 32 warp totals of word c
+        unsigned long long t = warp_tot[warp * MS2_WARPS + lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned long long u = __shfl_up_sync(0xffffffffu, t, o);
             if (lane >= o) t += u;
         }
-        warp_tot[lane] = t;                // inclusive over warps
+        warp_tot[warp * MS2_WARPS + lane] = t;            // inclusive over warps
     }
     __syncthreads();
-    *total = warp_tot[MS2_WARPS - 1];
-    return (warp ? warp_tot[warp - 1] : 0ull) + incl - v;
+#pragma unroll
+    for (int c = 0; c < MS2_NG; c++) {
+        tot[c] = warp_tot[c * MS2_WARPS + MS2_WARPS - 1];
+        pre[c] = (warp ? warp_tot[c * MS2_WARPS + warp - 1] : 0ull) + incl[c] - v[c];
+    }
 }
 
 __global__ void __launch_bounds__(MS2_THREADS, 1) rdf_mean_shift_v2_kernel(const rdf_ms2_params p) {
@@ -278,15 +316,20 @@ __global__ void __launch_bounds__(MS2_THREADS, 1) rdf_mean_shift_v2_kernel(const
     double* all_partial = reinterpret_cast<double*>(ms_smem);                 // [2][NC][K][3]
     double* partial = all_partial + 2 * (size_t)NC * K * 3;                   // [MS2_MAX_ITEMS][3]
     double* means_s = partial + MS2_MAX_ITEMS * 3;                            // [K][2]
-    double* v2_s = means_s + 2 * K;                                           // [K]
-    unsigned long long* warp_tot = reinterpret_cast<unsigned long long*>(v2_s + K);   // [32]
-    int* seg_start = reinterpret_cast<int*>(warp_tot + MS2_WARPS);            // [K+1]
+    double* ninv_s = means_s + 2 * K;                                         // [K]  -1 / (2 sigma^2)
+    unsigned long long* warp_tot = reinterpret_cast<unsigned long long*>(ninv_s + K);   // [MS2_NG][32]
+    int* seg_start = reinterpret_cast<int*>(warp_tot + MS2_NG * MS2_WARPS);   // [K+1]
     int* item_start = seg_start + (MS2_MAX_K + 1);                            // [K+1]
-    uint32_t* entries = reinterpret_cast<uint32_t*>(item_start + (MS2_MAX_K + 1) + 2);   // [chunk]
+    unsigned char* item_class = reinterpret_cast<unsigned char*>(item_start + (MS2_MAX_K + 1) + 2);   // [MS2_MAX_ITEMS]
+    uint32_t* entries = reinterpret_cast<uint32_t*>(item_class + MS2_ITEM_CLASS_BYTES);   // [chunk]
 
     const int npx = p.w * p.h;
-    const int p0 = rank * p.chunk;
-    const int p1 = min(npx, p0 + p.chunk);
+    // 8-pixel groups are dealt round-robin to the CTAs of the cluster (group G -> CTA G % NC), so every CTA sees a uniform
+    // sample of the image: a hand blob in the middle of the frame no longer lands on one or two CTAs (the per-round
+    // cluster barrier used to wait ~3 us for the most loaded CTA, profiles/r01_latency.md).
+    // Programmatic dependent launch: this grid may be scheduled while the kernel before it in the stream (the layered
+    // forest) is still running; nothing produced by that kernel is touched before this wait.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     MS_TRACE(0);
     if (p.trace && rank == 0 && tid == 0) p.trace[16] = (unsigned long long)clock64();
 
@@ -294,14 +337,14 @@ __global__ void __launch_bounds__(MS2_THREADS, 1) rdf_mean_shift_v2_kernel(const
     uint4 px[MS2_GROUPS];
 #pragma unroll
     for (int g = 0; g < MS2_GROUPS; g++) {
-        const int q = p0 + (g * MS2_THREADS + tid) * 8;
+        const int q = ((g * MS2_THREADS + tid) * NC + rank) * 8;
         px[g] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);      // 65535 = no pixel
-        if (q + 8 <= p1) {
+        if (q + 8 <= npx) {
             px[g] = __ldg(reinterpret_cast<const uint4*>(p.labels + q));
-        } else if (q < p1) {                                                       // ragged tail of the image
+        } else if (q < npx) {                                                      // ragged tail of the image
             unsigned short tmp[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) tmp[j] = q + j < p1 ? __ldg(p.labels + q + j) : (unsigned short)0xffff;
+            for (int j = 0; j < 8; j++) tmp[j] = q + j < npx ? __ldg(p.labels + q + j) : (unsigned short)0xffff;
             px[g] = make_uint4(tmp[0] | (tmp[1] << 16), tmp[2] | (tmp[3] << 16), tmp[4] | (tmp[5] << 16), tmp[6] | (tmp[7] << 16));
         }
     }
@@ -309,7 +352,7 @@ __global__ void __launch_bounds__(MS2_THREADS, 1) rdf_mean_shift_v2_kernel(const
         means_s[2 * k] = 0.0;
         means_s[2 * k + 1] = 0.0;
         const float v = p.variances[k];
-        v2_s[k] = (double)__fmul_rn(v, v);                                    // fp32 product, widened (mean_shift.cu:41)
+        ninv_s[k] = -1.0 / (2.0 * (double)__fmul_rn(v, v));                   // sigma^2 = fp32 product, widened (mean_shift.cu:41)
     }
 
     auto label_of = [&](int g, int j) -> unsigned {
@@ -338,11 +381,7 @@ __global__ void __launch_bounds__(MS2_THREADS, 1) rdf_mean_shift_v2_kernel(const
     MS_TRACE(1);
     // ---- block-wide exclusive scans -> stable positions; totals -> class segments ----
     unsigned long long pre[MS2_NG], tot[MS2_NG];
-#pragma unroll
-    for (int c = 0; c < MS2_NG; c++) {
-        pre[c] = 0ull; tot[c] = 0ull;
-        if (4 * c < K) pre[c] = ms2_block_exscan(cnt[c], warp_tot, &tot[c]);
-    }
+    ms2_block_exscan(cnt, warp_tot, pre, tot);
     if (tid == 0) {
         seg_start[0] = 0;
         item_start[0] = 0;
@@ -361,7 +400,7 @@ __global__ void __launch_bounds__(MS2_THREADS, 1) rdf_mean_shift_v2_kernel(const
 #pragma unroll
     for (int g = 0; g < MS2_GROUPS; g++) {
         if ((px[g].x & px[g].y & px[g].z & px[g].w) == 0xffffffffu) continue;
-        const int q = p0 + (g * MS2_THREADS + tid) * 8;
+        const int q = ((g * MS2_THREADS + tid) * NC + rank) * 8;
         int y = q / p.w, x = q - y * p.w;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
@@ -384,32 +423,46 @@ __global__ void __launch_bounds__(MS2_THREADS, 1) rdf_mean_shift_v2_kernel(const
 
     // ---- rounds ----
     const int n_items = item_start[K];
+    for (int item = tid; item < n_items; item += MS2_THREADS) {              // class of each item, once
+        int lo = 0, hi = K - 1;                                              // last k with item_start[k] <= item
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (item_start[mid] <= item) lo = mid; else hi = mid - 1;
+        }
+        item_class[item] = (unsigned char)lo;
+    }
+    __syncthreads();
     MS_TRACE(3);
     for (int it = 0; it < p.rounds; it++) {
         if (it < 10) MS_TRACE(4 + it);
         for (int item = warp; item < n_items; item += MS2_WARPS) {
-            int lo = 0, hi = K - 1;                                          // class of the item: last k with item_start[k] <= item
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (item_start[mid] <= item) lo = mid; else hi = mid - 1;
-            }
-            const int k = lo;
+            const int k = item_class[item];
             const int e0 = seg_start[k] + (item - item_start[k]) * MS2_ITEM;
             const int e1 = min(seg_start[k + 1], e0 + MS2_ITEM);
-            const double mx = means_s[2 * k], my = means_s[2 * k + 1];
-            const double two_v2 = 2.0 * v2_s[k];
-            double sx = 0.0, sy = 0.0, sp = 0.0;
-#pragma unroll 4
-            for (int e = e0 + lane; e < e1; e += 32) {
-                const uint32_t c = entries[e];
-                const double cx = (double)(c & 0xffffu), cy = (double)(c >> 16);
-                if (it == 0) {                                               // mean_shift.cu:31-34
-                    sx += cx; sy += cy; sp += 1.0;
-                } else {                                                     // mean_shift.cu:36-46
-                    const double dx = cx - mx, dy = cy - my;
-                    const double pr = exp(-(dx * dx + dy * dy) / two_v2);
-                    sx += dx * pr; sy += dy * pr; sp += pr;
-                }
+            // MS2_ITEM == 64: two entries per lane, evaluated as two independent chains
+            const int ea = e0 + lane, eb = ea + 32;
+            const bool va = ea < e1, vb = eb < e1;
+            const uint32_t ca = va ? entries[ea] : 0u, cb = vb ? entries[eb] : 0u;
+            const double cxa = (double)(ca & 0xffffu), cya = (double)(ca >> 16);
+            const double cxb = (double)(cb & 0xffffu), cyb = (double)(cb >> 16);
+            double sx, sy, sp;
+            if (it == 0) {                                                   // mean_shift.cu:31-34
+                const double wa = va ? 1.0 : 0.0, wb = vb ? 1.0 : 0.0;
+                sx = cxa * wa + cxb * wb;
+                sy = cya * wa + cyb * wb;
+                sp = wa + wb;
+            } else {                                                         // mean_shift.cu:36-46
+                const double mx = means_s[2 * k], my = means_s[2 * k + 1];
+                // -1 / (2 sigma^2) once per class instead of one fp64 divide per pixel (a 1-ulp change of the exponent)
+                const double nis = ninv_s[k];
+                const double dxa = cxa - mx, dya = cya - my, dxb = cxb - mx, dyb = cyb - my;
+                double pa = ms_exp_nonpos((dxa * dxa + dya * dya) * nis);
+                double pb = ms_exp_nonpos((dxb * dxb + dyb * dyb) * nis);
+                pa = va ? pa : 0.0;
+                pb = vb ? pb : 0.0;
+                sx = dxa * pa + dxb * pb;
+                sy = dya * pa + dyb * pb;
+                sp = pa + pb;
             }
             if (it == 1) MS_TRACE(20);
             sx = ms_warp_sum(sx);
@@ -434,15 +487,14 @@ __global__ void __launch_bounds__(MS2_THREADS, 1) rdf_mean_shift_v2_kernel(const
         if (it == 1) MS_TRACE(23);
         cluster.sync();
         if (it == 1) MS_TRACE(24);
-        for (int k = tid; k < K; k += MS2_THREADS) {
-            double sx = 0.0, sy = 0.0, sp = 0.0;
+        for (int i = tid; i < 2 * K; i += MS2_THREADS) {                     // thread (k, x|y): its own sum and the weight sum
+            const int k = i >> 1, comp = i & 1;
+            double sv = 0.0, sp = 0.0;
             for (int r = 0; r < NC; r++) {
-                sx += buf[((size_t)r * K + k) * 3 + 0];
-                sy += buf[((size_t)r * K + k) * 3 + 1];
+                sv += buf[((size_t)r * K + k) * 3 + comp];
                 sp += buf[((size_t)r * K + k) * 3 + 2];
             }
-            means_s[2 * k] += sx / sp;                                       // mean_shift.py:53-55 (0/0 -> NaN)
-            means_s[2 * k + 1] += sy / sp;
+            means_s[i] += sv / sp;                                           // mean_shift.py:53-55 (0/0 -> NaN)
         }
         if (it == 1) MS_TRACE(25);
         __syncthreads();
@@ -460,8 +512,9 @@ static size_t ms2_smem_bytes(int K, int NC, int chunk) {
     b += sizeof(double) * 2 * (size_t)NC * K * 3;
     b += sizeof(double) * MS2_MAX_ITEMS * 3;
     b += sizeof(double) * 3 * (size_t)K;
-    b += sizeof(unsigned long long) * MS2_WARPS;
+    b += sizeof(unsigned long long) * MS2_NG * MS2_WARPS;
     b += sizeof(int) * (2 * (MS2_MAX_K + 1) + 2);
+    b += MS2_ITEM_CLASS_BYTES;
     b += sizeof(uint32_t) * (size_t)chunk;
     return b;
 }
@@ -496,14 +549,41 @@ extern "C" int rdf_mean_shift(const uint16_t* labels_dev, int dim_x, int dim_y, 
 
     const int npx = dim_x * dim_y;
     // latency path: everything in shared memory (see v2 above)
-    if (num_labels <= MS2_MAX_K && npx <= MS_MAX_CLUSTER * MS2_CAP && (reinterpret_cast<uintptr_t>(labels_dev) & 15u) == 0 &&
+    if (num_labels <= MS2_MAX_K && npx <= MS_MAX_CLUSTER * MS2_CAP &&   /* capacity at the portable cluster size */ (reinterpret_cast<uintptr_t>(labels_dev) & 15u) == 0 &&
         !getenv("RDF_MS_V1")) {
-        int NC = (npx + 8191) / 8192;
-        if (NC > MS_MAX_CLUSTER) NC = MS_MAX_CLUSTER;
+        // cluster size: 16 CTAs (non-portable size, opt-in) when the device can co-schedule such a cluster with the kernel's
+        // full shared-memory footprint, else the portable 8.  RDF_MS_CLUSTER overrides (experiments).
+        static int nc_cap = 0;
+        if (!nc_cap) {
+            const char* e = getenv("RDF_MS_CLUSTER");
+            int want = e ? atoi(e) : MS2_MAX_CLUSTER;
+            if (want < 1 || want > MS2_MAX_CLUSTER) want = MS2_MAX_CLUSTER;
+            nc_cap = want < MS_MAX_CLUSTER ? want : MS_MAX_CLUSTER;
+            if (want > MS_MAX_CLUSTER) {
+                const int max_smem = (int)ms2_smem_bytes(MS2_MAX_K, MS2_MAX_CLUSTER, MS2_CAP / 2);   // largest image at 16 CTAs
+                cudaLaunchConfig_t probe = {};
+                probe.gridDim = dim3(want, 1, 1);
+                probe.blockDim = dim3(MS2_THREADS, 1, 1);
+                probe.dynamicSmemBytes = max_smem;
+                cudaLaunchAttribute pa[1];
+                pa[0].id = cudaLaunchAttributeClusterDimension;
+                pa[0].val.clusterDim.x = want; pa[0].val.clusterDim.y = 1; pa[0].val.clusterDim.z = 1;
+                probe.attrs = pa; probe.numAttrs = 1;
+                int n_clusters = 0;
+                if (cudaFuncSetAttribute(rdf_mean_shift_v2_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                    cudaFuncSetAttribute(rdf_mean_shift_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) == cudaSuccess &&
+                    cudaOccupancyMaxActiveClusters(&n_clusters, rdf_mean_shift_v2_kernel, &probe) == cudaSuccess && n_clusters >= 1)
+                    nc_cap = want;
+                cudaGetLastError();                                     // a failed probe is not an error of this call
+            }
+        }
+        int NC = (npx + 4095) / 4096;                                  // >= 4096 pixels per CTA before adding CTAs
+        if (NC > nc_cap) NC = nc_cap;
         rdf_ms2_params q;
         q.labels = labels_dev; q.variances = variances_dev; q.means_out = means_dev;
         q.w = dim_x; q.h = dim_y; q.K = num_labels; q.rounds = rounds;
-        q.chunk = (((npx + NC - 1) / NC) + 7) / 8 * 8;
+        const int ngroups = (npx + 7) / 8;
+        q.chunk = ((ngroups + NC - 1) / NC) * 8;                  // entries a CTA may hold (its share of 8-pixel groups)
         q.trace = getenv("RDF_MS_TRACE") ? reinterpret_cast<unsigned long long*>(workspace_dev) : nullptr;
         const size_t smem2 = ms2_smem_bytes(num_labels, NC, q.chunk);
         static size_t smem2_set = 0;
@@ -516,13 +596,15 @@ extern "C" int rdf_mean_shift(const uint16_t* labels_dev, int dim_x, int dim_y, 
         cfg2.blockDim = dim3(MS2_THREADS, 1, 1);
         cfg2.dynamicSmemBytes = smem2;
         cfg2.stream = rdf_stream(stream);
-        cudaLaunchAttribute attr2[1];
+        cudaLaunchAttribute attr2[2];
         attr2[0].id = cudaLaunchAttributeClusterDimension;
         attr2[0].val.clusterDim.x = NC;
         attr2[0].val.clusterDim.y = 1;
         attr2[0].val.clusterDim.z = 1;
+        attr2[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see griddepcontrol.wait in the kernel
+        attr2[1].val.programmaticStreamSerializationAllowed = 1;
         cfg2.attrs = attr2;
-        cfg2.numAttrs = 1;
+        cfg2.numAttrs = getenv("RDF_NO_PDL") ? 1 : 2;
         RDF_CUDA(cudaLaunchKernelEx(&cfg2, rdf_mean_shift_v2_kernel, q));
         return RDF_OK;
     }

@@ -5,6 +5,7 @@ K x 2 float64 result, where the reference makes 2 blocking D2H + 1 H2D copies pe
 import ctypes
 
 import numpy as np
+import torch
 
 from . import _capi
 from .buffers import GPUArray, as_gpuarray
@@ -25,8 +26,10 @@ class MeanShift:
         if self._workspace is None or self._workspace.nbytes < need.value:
             self._workspace = GPUArray(((need.value + 3) // 4,), dtype=np.uint32)
 
-    def run_async(self, num_rounds, labels, num_labels, variances):
-        """Enqueue the whole mean shift on the current stream; returns the device array float64[num_labels,2]."""
+    def run_async(self, num_rounds, labels, num_labels, variances, means_out=None):
+        """Enqueue the whole mean shift on the current stream; returns the device array float64[num_labels,2].
+        means_out: optional pinned-host torch tensor float64[num_labels,2]; the kernel then writes the centroids straight into
+        host memory (zero-copy over PCIe, 16 bytes per class), which saves the D2H copy node of a per-frame pipeline."""
         labels = as_gpuarray(labels)
         assert labels.dtype == np.uint16
         dim_y, dim_x = labels.shape[-2:]
@@ -38,10 +41,15 @@ class MeanShift:
         variances = as_gpuarray(variances)
         assert variances.dtype == np.float32 and variances.size >= num_labels
         self._ensure(num_labels, dim_x, dim_y)
+        if means_out is not None:
+            assert means_out.is_pinned() and means_out.dtype == torch.float64 and means_out.numel() == 2 * num_labels
+            out_ptr = ctypes.c_void_p(means_out.data_ptr())          # unified addressing: pinned host memory is device-visible
+        else:
+            out_ptr = _capi.dptr(self.means)
         _capi.check(self._lib.rdf_mean_shift(_capi.dptr(labels), dim_x, dim_y, int(num_labels), _capi.dptr(variances),
-                                             int(num_rounds), _capi.dptr(self.means), _capi.dptr(self._workspace),
+                                             int(num_rounds), out_ptr, _capi.dptr(self._workspace),
                                              self._workspace.nbytes, _capi.stream_ptr()))
-        return self.means
+        return self.means if means_out is None else means_out
 
     def run(self, num_rounds, labels, num_labels, variances):
         """src/cuda/mean_shift.py:19-59: returns np.float64[num_labels, 2] = (x, y); NaN rows for classes without pixels."""

@@ -76,7 +76,11 @@ class HostBatchEvaluator:
 class LiveFramePipeline:
     """One frame in, fingertip centroids out.  All device work of a frame is one CUDA-graph replay."""
 
-    def __init__(self, layered_forest, num_rounds, variances, scale_factor=1., use_graph=True):
+    def __init__(self, layered_forest, num_rounds, variances, scale_factor=1., use_graph=True, upload=True, zero_copy_out=True):
+        """upload=False: the frame is already in `depth_dev` (device-resident producer, e.g. a pre-processing kernel);
+        zero_copy_out: the mean-shift kernel writes the K x 2 centroids straight into pinned host memory."""
+        self.upload = upload
+        self.zero_copy_out = zero_copy_out
         self.ldf = layered_forest
         self.rounds = int(num_rounds)
         self.scale = float(scale_factor)
@@ -92,7 +96,7 @@ class LiveFramePipeline:
         self.variances.set(np.ascontiguousarray(variances, dtype=np.float32))
         self.stream = torch.cuda.Stream()
         self.graph = None
-        self.h2d_bytes = H * W * 2
+        self.h2d_bytes = H * W * 2 if upload else 0
         self.d2h_bytes = self.K * 2 * 8
         # one eager pass: loads kernels, sets function attributes, allocates mean-shift scratch (nothing may allocate
         # during capture)
@@ -105,10 +109,14 @@ class LiveFramePipeline:
                 self._enqueue()
 
     def _enqueue(self):
-        self.depth_dev.cu().tensor.view(torch.int16).copy_(self.depth_host.view(torch.int16), non_blocking=True)
+        if self.upload:
+            self.depth_dev.cu().tensor.view(torch.int16).copy_(self.depth_host.view(torch.int16), non_blocking=True)
         self.ldf.run(self.depth_dev, self.labels_dev, self.scale)
-        means = self.ms.run_async(self.rounds, self.labels_dev.cu(), self.K, self.variances)
-        self.means_host.copy_(means.tensor, non_blocking=True)
+        if self.zero_copy_out:
+            self.ms.run_async(self.rounds, self.labels_dev.cu(), self.K, self.variances, means_out=self.means_host)
+        else:
+            means = self.ms.run_async(self.rounds, self.labels_dev.cu(), self.K, self.variances)
+            self.means_host.copy_(means.tensor, non_blocking=True)
 
     def submit(self):
         """Enqueue one frame (depth already written into self.depth_host)."""
@@ -123,6 +131,8 @@ class LiveFramePipeline:
         if depth_frame is not None:
             self.depth_host.view(torch.int16).numpy()[...] = np.asarray(depth_frame, dtype=np.uint16).reshape(
                 self.depth_host.shape).view(np.int16)
+            if not self.upload:
+                self.depth_dev.cu().tensor.view(torch.int16).copy_(self.depth_host.view(torch.int16))
         self.submit()
         self.stream.synchronize()
         return self.means_host.numpy().copy()

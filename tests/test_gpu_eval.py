@@ -216,3 +216,26 @@ def test_fast_divide_is_bit_identical_to_div_rn():
     bad, bad_floor = ctypes.c_ulonglong(1), ctypes.c_ulonglong(1)
     _capi.check(lib.rdf_selftest_fastdiv(40000, 20261018, ctypes.byref(bad), ctypes.byref(bad_floor)))
     assert bad.value == 0 and bad_floor.value == 0
+
+
+def test_golden_fixtures_from_reference_kernels():
+    """CUDA path against the committed reference-kernel outputs (tests/golden/eval_forest.npz, eval_tree.npz)."""
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    z = np.load(os.path.join(gold, 'eval_forest.npz'))
+    for name in [str(n) for n in z['names']]:
+        r, scale, has_filter, fclass = z[f'{name}.params']
+        filt = z[f'{name}.filter'] if has_filter else None
+        got, _ = _run_ours(z[f'{name}.forest'], z[f'{name}.depth'], int(r), filt, int(fclass) if has_filter else None, float(scale))
+        assert np.array_equal(got, z[f'{name}.labels']), name
+    import torch
+    from rdf_b200 import decision_tree as dt
+    z = np.load(os.path.join(gold, 'eval_tree.npz'))
+    for name in [str(n) for n in z['names']]:
+        tree_np, depth, want = z[f'{name}.tree'], z[f'{name}.depth'], z[f'{name}.labels']
+        tree = dt.DecisionTree(int(np.log2(tree_np.shape[0] + 1)), (tree_np.shape[1] - 7) // 2)
+        tree.tree_out_cu.set(tree_np)
+        out = filled_u16(want.shape, 65535)
+        dt.DecisionTreeEvaluator().get_labels(tree, to_dev(depth), out)
+        torch.cuda.synchronize()
+        assert np.array_equal(to_np(out), want), name

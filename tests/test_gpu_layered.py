@@ -116,6 +116,55 @@ def test_mean_shift_dense_labels():
     assert np.abs(got - exp).max() <= 1e-5
 
 
+def test_mean_shift_ignores_labels_above_num_labels():
+    """labels above num_labels: the reference kernel dereferences a null pointer for them (cu_utils.hpp:110-114, found when
+    generating tests/golden); here they are ignored, like 0 and 65535.  Also the golden blobs fixture (reference output)."""
+    import os
+    from rdf_b200.mean_shift import MeanShift
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'layered_meanshift.npz'))
+    lab, var, want = z['blobs.labels'].copy(), z['blobs.variances'], z['blobs.means']
+    got = MeanShift().run(5, to_dev(lab[None]), 4, var)
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and np.nanmax(np.abs(got - want)) <= 1e-5
+    lab[1, 0:5] = 9
+    lab[2, 0:5] = 5
+    got2 = MeanShift().run(5, to_dev(lab[None]), 4, var)
+    assert np.array_equal(np.nan_to_num(got2, nan=-1.0), np.nan_to_num(got, nan=-1.0))
+
+
+@pytest.mark.parametrize('name', ['layered_240x424_r2', 'layered_97x131_r1'])
+def test_layered_golden_fixture(tmp_path, name):
+    """CUDA path against the committed reference-kernel outputs (tests/golden/layered_meanshift.npz)."""
+    import os
+    import torch
+    from rdf_b200 import decision_tree as dt
+    from rdf_b200.buffers import GpuBuffer
+    from rdf_b200.mean_shift import MeanShift
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'layered_meanshift.npz'))
+    depth = z[f'{name}.depth']
+    r, scale = int(z[f'{name}.params'][0]), float(z[f'{name}.params'][1])
+    H, W = depth.shape[1:]
+    layers = []
+    for i in range(2):
+        f = z[f'{name}.forest{i}']
+        m = dt.DecisionForest(f.shape[0], int(np.log2(f.shape[1] + 1)), (f.shape[2] - 7) // 2)
+        m.forest_cu.set(f)
+        layers.append(m)
+    cfg = {'layers': [{'model': layers[0]}, {'model': layers[1], 'filter_model': 0, 'filter_model_class': 1}],
+           'conditions': z[f'{name}.conditions'].tolist(), 'label_colors': [[0, 0, 0, 255]] * 11, 'root': '.'}
+    ldf = dt.LayeredDecisionForest(cfg, (H, W), r)
+    d = GpuBuffer((1, H, W), np.uint16)
+    d.cu().set(depth)
+    out = GpuBuffer((1, H // r, W // r), np.uint16)
+    ldf.run(d, out, scale)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cu().get()[0], z[f'{name}.composite'])
+    assert np.array_equal(ldf.label_images[0].cu().get(), z[f'{name}.layer0'])
+    assert np.array_equal(ldf.label_images[1].cu().get(), z[f'{name}.layer1'])
+    means = MeanShift().run(6, out.cu(), 11, z[f'{name}.variances'])
+    want = z[f'{name}.means']
+    assert np.array_equal(np.isnan(means), np.isnan(want)) and np.nanmax(np.abs(means - want)) <= 1e-5
+
+
 def test_composite_standalone_untouched_pixels():
     import torch
     from rdf_b200 import decision_tree as dt
