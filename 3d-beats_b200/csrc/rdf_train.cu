@@ -181,6 +181,327 @@ extern "C" int rdf_train_hist(const uint16_t* depth_dev, const uint16_t* labels_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// split histograms, bucketed: pixels grouped by node first
+// ---------------------------------------------------------------------------------------------------------------
+// The raster kernel above privatises [slots x feature chunk] histograms, so the feature chunk shrinks as 1 / slots and, past
+// ~100 slots, every update is a global atomic (cfg4 on a B200: 311 / 418 / 207 / 210 ms per level at 1 / 16 / 256 / 4096 nodes,
+// profiles/r01_train_cfg4.md).  Here the active pixels are first grouped by histogram slot (counting sort of pixel indices:
+// rdf_train_bucket, once per level and node block, reused by every proposal block), so a CTA works on pixels of ONE node at
+// a time: its shared-memory histogram is [feature chunk][NT+1][C] whatever the number of nodes, flushed with one global
+// atomic per non-zero counter when the node changes.  Lanes of a warp are consecutive pixels of the same node evaluating the
+// same feature: probes of neighbouring pixels share sectors, thresholds are shared-memory broadcasts, and updates are
+// warp-aggregated (match.all when every lane hits the same counter, else match.any), so no shared-memory atomic ever
+// collides within a warp.
+#define TB_THREADS 1024
+#define TB_TILE 8192            // sorted pixels per CTA
+#define TB_MAX_FC 256
+#define TB_U 4                  // features evaluated together by one thread (independent load chains)
+
+struct rdf_bucket_ws {           // layout of the caller-provided workspace
+    int total;                   // number of bucketed pixels (device-side value, never read by the host)
+    int pad[3];
+    // int starts[S + 1]; int cursor[S]; int list[num_pixels];
+};
+
+static size_t tb_align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+extern "C" int rdf_train_bucket_workspace_bytes(int64_t num_pixels, int num_slots, size_t* bytes) {
+    RDF_REQUIRE(bytes && num_pixels >= 0 && num_slots >= 1, "rdf_train_bucket_workspace_bytes: bad argument");
+    *bytes = sizeof(rdf_bucket_ws) + tb_align16(sizeof(int) * ((size_t)num_slots + 1)) + tb_align16(sizeof(int) * (size_t)num_slots) +
+             sizeof(int) * (size_t)num_pixels;
+    return RDF_OK;
+}
+
+__device__ __forceinline__ int tb_slot_of(const int32_t* __restrict__ nodes, const int32_t* __restrict__ node_slot, int64_t i) {
+    const int g = __ldg(nodes + i);
+    return g < 0 ? -1 : __ldg(node_slot + g);
+}
+
+// counts[slot] += 1 per active pixel (MODE 0) / list[cursor[slot]++] = pixel (MODE 1), one atomic per (warp, slot)
+template <int MODE>
+__global__ void __launch_bounds__(256) rdf_train_bucket_kernel(const int32_t* __restrict__ nodes, const int32_t* __restrict__ node_slot,
+                                                               int64_t n, int* __restrict__ counts_or_cursor, int* __restrict__ list) {
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_round = (n + 31) / 32 * 32;                              // whole warps stay converged for match.any
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const int slot = i < n ? tb_slot_of(nodes, node_slot, i) : -1;
+        const unsigned grp = __match_any_sync(0xffffffffu, slot);
+        if (slot >= 0) {
+            const int leader = __ffs(grp) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(counts_or_cursor + slot, __popc(grp));
+            if (MODE == 1) {
+                base = __shfl_sync(grp, base, leader);
+                list[base + __popc(grp & ((1u << lane) - 1u))] = (int)i;
+            }
+        }
+    }
+}
+
+// single CTA: exclusive scan of counts[S] (held in starts[]) -> starts[0..S], cursor[s] = starts[s], total
+__global__ void __launch_bounds__(1024) rdf_train_bucket_scan_kernel(int* __restrict__ starts, int* __restrict__ cursor, int S,
+                                                                      int* __restrict__ total) {
+    __shared__ int warp_tot[32];
+    __shared__ int running;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    for (int base = 0; base < S; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < S ? starts[i] : 0;
+        int incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int t = warp_tot[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t += u;
+            }
+            warp_tot[lane] = t;
+        }
+        __syncthreads();
+        const int excl = running + (warp ? warp_tot[warp - 1] : 0) + incl - v;
+        if (i < S) {
+            starts[i] = excl;
+            cursor[i] = excl;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) running += warp_tot[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        starts[S] = running;
+        *total = running;
+    }
+}
+
+extern "C" int rdf_train_bucket(const int32_t* nodes_by_pixel_dev, int64_t num_pixels, const int32_t* node_slot_dev, int num_slots,
+                                void* workspace_dev, size_t workspace_bytes, void* stream) {
+    RDF_REQUIRE(nodes_by_pixel_dev && node_slot_dev && workspace_dev, "rdf_train_bucket: NULL argument");
+    RDF_REQUIRE(num_pixels >= 0 && num_pixels < ((int64_t)1 << 31) && num_slots >= 1, "rdf_train_bucket: bad shape");
+    size_t need = 0;
+    rdf_train_bucket_workspace_bytes(num_pixels, num_slots, &need);
+    RDF_REQUIRE(workspace_bytes >= need, "rdf_train_bucket: workspace %zu < %zu bytes", workspace_bytes, need);
+    cudaStream_t st = rdf_stream(stream);
+    unsigned char* ws = reinterpret_cast<unsigned char*>(workspace_dev);
+    int* total = reinterpret_cast<int*>(ws);
+    int* starts = reinterpret_cast<int*>(ws + sizeof(rdf_bucket_ws));
+    int* cursor = reinterpret_cast<int*>(ws + sizeof(rdf_bucket_ws) + tb_align16(sizeof(int) * ((size_t)num_slots + 1)));
+    int* list = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(cursor) + tb_align16(sizeof(int) * (size_t)num_slots));
+    RDF_CUDA(cudaMemsetAsync(starts, 0, sizeof(int) * ((size_t)num_slots + 1), st));
+    int blocks = (int)((num_pixels + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    rdf_train_bucket_kernel<0><<<blocks, 256, 0, st>>>(nodes_by_pixel_dev, node_slot_dev, num_pixels, starts, nullptr);
+    rdf_train_bucket_scan_kernel<<<1, 1024, 0, st>>>(starts, cursor, num_slots, total);
+    rdf_train_bucket_kernel<1><<<blocks, 256, 0, st>>>(nodes_by_pixel_dev, node_slot_dev, num_pixels, cursor, list);
+    RDF_LAUNCH_CHECK("rdf_train_bucket kernels");
+    return RDF_OK;
+}
+
+struct rdf_histb_params {
+    const uint16_t* depth;
+    const uint16_t* labels;
+    const int* total;
+    const int* starts;           // [S + 1]
+    const int* list;             // [total] pixel indices grouped by slot
+    const float* offsets;        // [F][4]
+    const float* thresholds;     // [F][NT]
+    uint32_t* hist;              // [S][F][NB][C]
+    int W, H, S, F, NT, NB, C, FC;
+};
+
+// ceil(t) for "t <= f" against an integer-valued feature: t <= f  <=>  ceil(t) <= f.  NaN never counts (-> INT_MAX).
+__device__ __forceinline__ int tb_int_thresh(float t) {
+    if (!(t == t)) return 0x7fffffff;
+    if (t >= 2147483648.f) return 0x7fffffff;
+    if (t <= -2147483648.f) return (int)0x80000000;
+    return __float2int_ru(t);
+}
+
+__global__ void __launch_bounds__(TB_THREADS, 1) rdf_train_hist_bucketed_kernel(const rdf_histb_params p) {
+    extern __shared__ __align__(16) unsigned char tb_smem[];
+    float4* off_s = reinterpret_cast<float4*>(tb_smem);                          // [FC]
+    int* thr_s = reinterpret_cast<int*>(off_s + p.FC);                           // [FC][NT]
+    uint32_t* hist_s = reinterpret_cast<uint32_t*>(thr_s + (size_t)p.FC * p.NT); // [FC][NB][C]
+    unsigned char* exact_s = reinterpret_cast<unsigned char*>(hist_s + (size_t)p.FC * p.NB * p.C);   // [FC]
+    __shared__ int s_slot;
+
+    const int total = __ldg(p.total);
+    const int tile0 = blockIdx.x * TB_TILE;
+    if (tile0 >= total) return;
+    const int tile1 = min(total, tile0 + TB_TILE);
+    const int f0 = blockIdx.y * p.FC;
+    const int nf = min(p.FC, p.F - f0);
+    const int lane = threadIdx.x & 31;
+
+    for (int j = threadIdx.x; j < nf; j += TB_THREADS) {
+        const float4 o = __ldg(reinterpret_cast<const float4*>(p.offsets) + f0 + j);
+        off_s[j] = o;
+        exact_s[j] = !(rdf_fastfloor_domain(o.x) && rdf_fastfloor_domain(o.y) && rdf_fastfloor_domain(o.z) && rdf_fastfloor_domain(o.w));
+    }
+    for (int i = threadIdx.x; i < nf * p.NT; i += TB_THREADS) thr_s[i] = tb_int_thresh(__ldg(p.thresholds + (size_t)f0 * p.NT + i));
+    const int per_chunk = nf * p.NB * p.C;
+    for (int i = threadIdx.x; i < per_chunk; i += TB_THREADS) hist_s[i] = 0u;
+    if (threadIdx.x == 0) {                                                      // slot of the first pixel of the tile
+        int lo = 0, hi = p.S - 1;                                               // last s with starts[s] <= tile0
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (__ldg(p.starts + mid) <= tile0) lo = mid; else hi = mid - 1;
+        }
+        s_slot = lo;
+    }
+    __syncthreads();
+
+    const int per_img = p.W * p.H;
+    const bool fast_ok = p.W <= 65535 && p.H <= 65535;
+    int p2 = 1;
+    while (p2 * 2 <= p.NT) p2 *= 2;                                              // largest power of two <= NT
+    int cur = tile0;
+    int slot = s_slot;
+    while (cur < tile1) {
+        while (__ldg(p.starts + slot + 1) <= cur) slot++;                        // skip empty slots (uniform across the CTA)
+        const int run1 = min(tile1, __ldg(p.starts + slot + 1));
+        for (int e0 = cur; e0 < run1; e0 += TB_THREADS) {
+            const int e = e0 + threadIdx.x;
+            const bool have = e < run1;
+            int X = 0, Y = 0;
+            unsigned d = 0, label = 0xffffffffu;
+            const uint16_t* img = p.depth;
+            if (have) {
+                const int i = __ldg(p.list + e);
+                const int n = i / per_img;
+                const int rem = i - n * per_img;
+                Y = rem / p.W;
+                X = rem - Y * p.W;
+                img = p.depth + (size_t)n * per_img;
+                d = __ldg(img + rem);
+                label = __ldg(p.labels + i);
+            }
+            const bool use = have && label < (unsigned)p.C;                      // labels outside 0..C-1 cannot be counted
+            const unsigned am = __ballot_sync(0xffffffffu, use);
+            if (!use) continue;
+            const float df = (float)d;
+            const float rcp = __frcp_rn(df);
+            const float xm = (float)X + RDF_MAGIC_F, ym = (float)Y + RDF_MAGIC_F;
+            const int leader = __ffs(am) - 1;
+            const unsigned am_cnt = (unsigned)__popc(am);
+            // TB_U features per trip: their 2 * TB_U probes are issued before any is consumed and the TB_U threshold searches
+            // advance in lock step, so one warp keeps several independent load chains in flight (the loop is bound by
+            // latency, not by issue: 8 warps per scheduler, each step a dependent L2 or shared-memory access).
+            for (int j0 = 0; j0 < nf; j0 += TB_U) {
+                int f[TB_U];
+#pragma unroll
+                for (int u = 0; u < TB_U; u++) {
+                    const int j = min(j0 + u, nf - 1);                          // tail: recompute the last feature, not counted
+                    const float4 o = off_s[j];
+                    // compute_feature with scale 1 (tree_train.cu:58); d == 0 -> 0.f (decision_tree_common.hpp:12)
+                    f[u] = 0;
+                    if (d != 0u) {
+                        if (exact_s[j] || !fast_ok) f[u] = rdf_feature_i<true>(img, p.W, p.H, X, Y, df, rcp, xm, ym, o.x, o.y, o.z, o.w);
+                        else f[u] = rdf_feature_i<false>(img, p.W, p.H, X, Y, df, rcp, xm, ym, o.x, o.y, o.z, o.w);
+                    }
+                }
+                // bin = #{k : t_k <= f}: binary lifting over the ascending integer thresholds, same trip count for every lane
+                int pos[TB_U];
+#pragma unroll
+                for (int u = 0; u < TB_U; u++) pos[u] = 0;
+                for (int step = p2; step > 0; step >>= 1) {
+#pragma unroll
+                    for (int u = 0; u < TB_U; u++) {
+                        const int* th = thr_s + min(j0 + u, nf - 1) * p.NT;
+                        const int q = pos[u] + step;
+                        if (q <= p.NT && th[q - 1] <= f[u]) pos[u] = q;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < TB_U; u++) {
+                    if (j0 + u < nf) {
+                        const int key = pos[u] * p.C + (int)label;
+                        uint32_t* dst = hist_s + (size_t)(j0 + u) * p.NB * p.C;
+                        int all_same;
+                        __match_all_sync(am, key, &all_same);
+                        if (all_same) {
+                            if (lane == leader) atomicAdd(dst + key, am_cnt);
+                        } else {
+                            const unsigned grp = __match_any_sync(am, key);
+                            if (lane == __ffs(grp) - 1) atomicAdd(dst + key, (unsigned)__popc(grp));
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // flush this node's counters and clear them for the next node
+        uint32_t* out = p.hist + ((size_t)slot * p.F + f0) * p.NB * p.C;
+        for (int i = threadIdx.x; i < per_chunk; i += TB_THREADS) {
+            const uint32_t v = hist_s[i];
+            if (v) {
+                atomicAdd(out + i, v);
+                hist_s[i] = 0u;
+            }
+        }
+        __syncthreads();
+        cur = run1;
+    }
+}
+
+extern "C" int rdf_train_hist_bucketed(const uint16_t* depth_dev, const uint16_t* labels_dev, int num_images, int dim_x, int dim_y,
+                                       const void* bucket_workspace_dev, int num_slots, const float* offsets_dev,
+                                       const float* thresholds_dev, int num_features, int num_thresholds, int num_classes,
+                                       uint32_t* hist_dev, void* stream) {
+    RDF_REQUIRE(depth_dev && labels_dev && bucket_workspace_dev && offsets_dev && thresholds_dev && hist_dev,
+                "rdf_train_hist_bucketed: NULL argument");
+    RDF_REQUIRE(num_images >= 0 && dim_x > 0 && dim_y > 0 && num_slots >= 1 && num_features >= 1 && num_thresholds >= 1 &&
+                    num_classes >= 1 && num_classes <= RDF_MAX_CLASSES,
+                "rdf_train_hist_bucketed: bad shape");
+    const int64_t num_pixels = (int64_t)num_images * dim_x * dim_y;
+    RDF_REQUIRE(num_pixels < ((int64_t)1 << 31), "rdf_train_hist_bucketed: too many pixels");
+    if (num_pixels == 0) return RDF_OK;
+    const unsigned char* ws = reinterpret_cast<const unsigned char*>(bucket_workspace_dev);
+    rdf_histb_params p;
+    p.depth = depth_dev; p.labels = labels_dev;
+    p.total = reinterpret_cast<const int*>(ws);
+    p.starts = reinterpret_cast<const int*>(ws + sizeof(rdf_bucket_ws));
+    p.list = reinterpret_cast<const int*>(ws + sizeof(rdf_bucket_ws) + tb_align16(sizeof(int) * ((size_t)num_slots + 1)) +
+                                          tb_align16(sizeof(int) * (size_t)num_slots));
+    p.offsets = offsets_dev; p.thresholds = thresholds_dev; p.hist = hist_dev;
+    p.W = dim_x; p.H = dim_y; p.S = num_slots; p.F = num_features; p.NT = num_thresholds; p.NB = num_thresholds + 1;
+    p.C = num_classes;
+    const size_t smem_budget = 220 * 1024;
+    const size_t per_feature = sizeof(float4) + sizeof(int) * (size_t)p.NT + sizeof(uint32_t) * (size_t)p.NB * p.C + 1;
+    int fc = (int)((smem_budget - 64) / per_feature);
+    if (fc > TB_MAX_FC) fc = TB_MAX_FC;
+    if (fc > p.F) fc = p.F;
+    if (fc < 1) {
+        rdf_set_error("rdf_train_hist_bucketed: %d thresholds x %d classes per feature do not fit shared memory", p.NT, p.C);
+        return RDF_ERR_UNSUPPORTED;
+    }
+    const int chunks = (p.F + fc - 1) / fc;
+    fc = (p.F + chunks - 1) / chunks;                                            // equal chunks
+    fc = (fc + 3) & ~3;                                                          // keeps the arrays behind off_s 16-byte aligned
+    p.FC = fc;
+    const size_t smem = per_feature * fc + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RDF_CUDA(cudaFuncSetAttribute(rdf_train_hist_bucketed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget + 4096));
+        attr_set = true;
+    }
+    const int64_t tiles = (num_pixels + TB_TILE - 1) / TB_TILE;
+    const int chunks2 = (p.F + fc - 1) / fc;
+    RDF_REQUIRE(chunks2 <= 65535, "rdf_train_hist_bucketed: too many feature chunks (%d)", chunks2);
+    rdf_train_hist_bucketed_kernel<<<dim3((unsigned)tiles, (unsigned)chunks2), TB_THREADS, smem, rdf_stream(stream)>>>(p);
+    RDF_LAUNCH_CHECK("rdf_train_hist_bucketed_kernel");
+    return RDF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // pick best split per active node
 // ---------------------------------------------------------------------------------------------------------------
 // fp32 operation order = what nvcc 12.9 emits for the reference's gini helpers on sm_100a (checked in PTX):

@@ -42,6 +42,10 @@ SIGNATURES = {
     'rdf_train_init': [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p],
     'rdf_train_hist': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
                        c_int, c_void_p, c_void_p],
+    'rdf_train_bucket_workspace_bytes': [c_int64, c_int, ctypes.POINTER(c_size_t)],
+    'rdf_train_bucket': [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_size_t, c_void_p],
+    'rdf_train_hist_bucketed': [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                                c_void_p, c_void_p],
     'rdf_train_pick_best': [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                             c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     'rdf_train_next_active': [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p],

@@ -470,6 +470,10 @@ class DecisionTreeTrainer():
         per_slot = P * (NT + 1) * C * 4
         self.MAX_SLOTS_PER_BLOCK = int(max(1, min(self.MAX_LEAF_NODES // 2 or 1, self.hist_budget_bytes // per_slot)))
         self.hist_cu = GPUArray((self.MAX_SLOTS_PER_BLOCK, P, NT + 1, C), dtype=np.uint32)
+        need = ctypes.c_size_t()
+        _capi.check(self._lib.rdf_train_bucket_workspace_bytes(int(np.prod(dataset.images_shape())), self.MAX_SLOTS_PER_BLOCK,
+                                                               ctypes.byref(need)))
+        self.bucket_ws = GPUArray(((need.value + 3) // 4,), dtype=np.int32)
 
     # -- proposal stream -------------------------------------------------------------------------------------
     def _next_proposals(self, level, block):
@@ -530,20 +534,26 @@ class DecisionTreeTrainer():
             slot_blocks = [active_host[i:i + self.MAX_SLOTS_PER_BLOCK] for i in range(0, num_active_nodes, self.MAX_SLOTS_PER_BLOCK)]
             num_nodes_level = 1 << current_level
 
+            single_block = len(slot_blocks) == 1
             for proposal_block_idx in range(self.NUM_PROPOSAL_BLOCKS):
                 offsets, thresholds = self._next_proposals(current_level, proposal_block_idx)
                 self.current_offsets.set(offsets)
                 self.current_thresholds.set(thresholds)
                 for nodes_in_block in slot_blocks:
                     S = len(nodes_in_block)
-                    slot_host = np.full((num_nodes_level,), -1, dtype=np.int32)
-                    slot_host[nodes_in_block] = np.arange(S, dtype=np.int32)
-                    self.node_slot_cu[:num_nodes_level].set(slot_host)
+                    if not (single_block and proposal_block_idx > 0):
+                        # group the active pixels by histogram slot: once per (level, node block), reused by every proposal
+                        # block when the level fits one node block (the common case with 180 GB of HBM)
+                        slot_host = np.full((num_nodes_level,), -1, dtype=np.int32)
+                        slot_host[nodes_in_block] = np.arange(S, dtype=np.int32)
+                        self.node_slot_cu[:num_nodes_level].set(slot_host)
+                        _capi.check(lib.rdf_train_bucket(_capi.dptr(self.nodes_by_pixel), N * H * W, _capi.dptr(self.node_slot_cu), S,
+                                                         _capi.dptr(self.bucket_ws), self.bucket_ws.nbytes, st()))
                     hist = self.hist_cu[:S]
                     hist.fill(0)
-                    _capi.check(lib.rdf_train_hist(_capi.dptr(depth), _capi.dptr(labels), _capi.dptr(self.nodes_by_pixel),
-                                                   N, W, H, _capi.dptr(self.node_slot_cu), S, _capi.dptr(self.current_offsets),
-                                                   _capi.dptr(self.current_thresholds), P, NT, C, _capi.dptr(hist), st()))
+                    _capi.check(lib.rdf_train_hist_bucketed(_capi.dptr(depth), _capi.dptr(labels), N, W, H, _capi.dptr(self.bucket_ws), S,
+                                                            _capi.dptr(self.current_offsets), _capi.dptr(self.current_thresholds),
+                                                            P, NT, C, _capi.dptr(hist), st()))
                     if dist is not None:                                       # the path's only exchange step
                         dist.all_reduce(hist.tensor.view(torch.int32), group=self.process_group)
                     _capi.check(lib.rdf_train_pick_best(num_active_nodes, _capi.dptr(self.active_nodes_cu),

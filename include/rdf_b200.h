@@ -155,6 +155,16 @@ RDF_API int rdf_train_hist(const uint16_t* depth_dev, const uint16_t* labels_dev
                    int num_images, int dim_x, int dim_y, const int32_t* node_slot_dev, int num_slots,
                    const float* offsets_dev, const float* thresholds_dev, int num_features, int num_thresholds,
                    int num_classes, uint32_t* hist_dev, void* stream);
+/* Bucketed form of rdf_train_hist (same histogram, bit for bit): rdf_train_bucket groups the active pixels by histogram
+ * slot once per (level, node block) into a caller-provided workspace; rdf_train_hist_bucketed then builds the histogram of
+ * any proposal block from it with a shared-memory histogram per node whatever the number of nodes. */
+RDF_API int rdf_train_bucket_workspace_bytes(int64_t num_pixels, int num_slots, size_t* bytes);
+RDF_API int rdf_train_bucket(const int32_t* nodes_by_pixel_dev, int64_t num_pixels, const int32_t* node_slot_dev, int num_slots,
+                     void* workspace_dev, size_t workspace_bytes, void* stream);
+RDF_API int rdf_train_hist_bucketed(const uint16_t* depth_dev, const uint16_t* labels_dev, int num_images, int dim_x, int dim_y,
+                            const void* bucket_workspace_dev, int num_slots, const float* offsets_dev,
+                            const float* thresholds_dev, int num_features, int num_thresholds, int num_classes,
+                            uint32_t* hist_dev, void* stream);
 RDF_API int rdf_train_pick_best(int num_active, const int32_t* active_nodes_dev, const int32_t* node_slot_dev,
                         const uint64_t* parent_counts_dev, const uint32_t* hist_dev, int num_slots,
                         const float* offsets_dev, const float* thresholds_dev, int num_features, int num_thresholds,

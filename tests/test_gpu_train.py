@@ -1,5 +1,7 @@
 """GPU parity of the training split search: histograms bit-exact vs the C oracle, best split / tree vs the NumPy oracle and
 the reference's own training kernels."""
+import ctypes
+
 import numpy as np
 import pytest
 
@@ -19,10 +21,21 @@ def _hist_ours(depth, labels, nodes, node_slot, S, offsets, thresholds, C):
     _capi.check(lib.rdf_train_hist(_capi.dptr(args[0]), _capi.dptr(args[1]), _capi.dptr(args[2]), N, W, H, _capi.dptr(args[3]), S,
                                    _capi.dptr(args[4]), _capi.dptr(args[5]), F, NT, C, _capi.dptr(hist), _capi.stream_ptr()))
     torch.cuda.synchronize()
-    return hist.cpu().numpy().view(np.uint32)
+    raster = hist.cpu().numpy().view(np.uint32)
+    # bucketed form (pixels grouped by slot first): must give the identical histogram
+    need = ctypes.c_size_t()
+    _capi.check(lib.rdf_train_bucket_workspace_bytes(N * H * W, S, ctypes.byref(need)))
+    ws = torch.zeros(((need.value + 3) // 4,), dtype=torch.int32, device='cuda')
+    hist2 = torch.zeros((S, F, NT + 1, C), dtype=torch.int32, device='cuda')
+    _capi.check(lib.rdf_train_bucket(_capi.dptr(args[2]), N * H * W, _capi.dptr(args[3]), S, _capi.dptr(ws), need.value, _capi.stream_ptr()))
+    _capi.check(lib.rdf_train_hist_bucketed(_capi.dptr(args[0]), _capi.dptr(args[1]), N, W, H, _capi.dptr(ws), S, _capi.dptr(args[4]),
+                                            _capi.dptr(args[5]), F, NT, C, _capi.dptr(hist2), _capi.stream_ptr()))
+    torch.cuda.synchronize()
+    assert np.array_equal(hist2.cpu().numpy().view(np.uint32), raster), 'bucketed histogram differs from the raster kernel'
+    return raster
 
 
-@pytest.mark.parametrize('level,NT,F', [(0, 64, 24), (3, 64, 20), (6, 8, 40), (9, 1, 64)])
+@pytest.mark.parametrize('level,NT,F', [(0, 64, 24), (3, 64, 20), (6, 8, 40), (9, 1, 64), (2, 64, 400), (11, 5, 7)])
 def test_hist_matches_c_oracle(level, NT, F):
     from rdf_b200 import synth
     from oracle import c_oracle as co

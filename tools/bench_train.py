@@ -5,6 +5,7 @@ F candidate features x 64 sorted thresholds, C = 4; one full histogram pass at l
 the ranks and the histograms are NCCL sum-allreduced (the path's only exchange step); time = max over ranks.
 Prints one JSON line per level on rank 0.  `--check` compares a feature sub-block with the C oracle (level 4, 2 frames)."""
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -27,6 +28,7 @@ def main():
     ap.add_argument('--feature-block', type=int, default=0, help='features per rdf_train_hist call (0 = pick by memory)')
     ap.add_argument('--iters', type=int, default=3)
     ap.add_argument('--check', action='store_true')
+    ap.add_argument('--raster', action='store_true', help='use the un-bucketed rdf_train_hist kernel')
     args = ap.parse_args()
     from rdf_b200 import _capi, synth, dist as rdist
     import torch.distributed as dist
@@ -55,12 +57,23 @@ def main():
         hist = torch.zeros((S, fb, NT + 1, C), dtype=torch.int32, device='cuda')
         blocks = [(f0, min(F, f0 + fb)) for f0 in range(0, F, fb)]
 
+        need = ctypes.c_size_t()
+        _capi.check(lib.rdf_train_bucket_workspace_bytes(N * H * W, S, ctypes.byref(need)))
+        ws = torch.zeros(((need.value + 3) // 4,), dtype=torch.int32, device='cuda')
+
         def sweep(do_allreduce=True):
+            if not args.raster:                              # counting sort of the active pixels by node: once per level
+                _capi.check(lib.rdf_train_bucket(_capi.dptr(nodes), N * H * W, _capi.dptr(slot), S, _capi.dptr(ws), need.value, st()))
             for f0, f1 in blocks:
                 h = hist if f1 - f0 == fb else hist.view(-1)[:S * (f1 - f0) * (NT + 1) * C].view(S, f1 - f0, NT + 1, C)
                 h.zero_()
-                _capi.check(lib.rdf_train_hist(_capi.dptr(depth), _capi.dptr(labels), _capi.dptr(nodes), N, W, H, _capi.dptr(slot), S,
-                                               _capi.dptr(offsets[f0:f1]), _capi.dptr(thresholds[f0:f1]), f1 - f0, NT, C, _capi.dptr(h), st()))
+                if args.raster:
+                    _capi.check(lib.rdf_train_hist(_capi.dptr(depth), _capi.dptr(labels), _capi.dptr(nodes), N, W, H, _capi.dptr(slot), S,
+                                                   _capi.dptr(offsets[f0:f1]), _capi.dptr(thresholds[f0:f1]), f1 - f0, NT, C, _capi.dptr(h), st()))
+                else:
+                    _capi.check(lib.rdf_train_hist_bucketed(_capi.dptr(depth), _capi.dptr(labels), N, W, H, _capi.dptr(ws), S,
+                                                            _capi.dptr(offsets[f0:f1]), _capi.dptr(thresholds[f0:f1]), f1 - f0, NT, C,
+                                                            _capi.dptr(h), st()))
                 if do_allreduce and world > 1:
                     dist.all_reduce(h)
         sweep()
@@ -86,7 +99,7 @@ def main():
             b_alg = px * 8 + px * F * 8                      # 8 B/px/level + 8 B per (px x feature)
             print(json.dumps({'cfg4_level': level, 'active_nodes': S, 'n_gpus': world, 'ms_per_level': ms, 'ms_compute_only': ms_compute,
                               'g_feature_evals_per_s': px * F / ms / 1e6, 'feature_block': fb, 'hist_bytes_per_block': S * fb * (NT + 1) * C * 4,
-                              'algorithmic_GBps': b_alg / ms / 1e6, 'labelled_pixels': px, 'features': F, 'thresholds': NT}), flush=True)
+                              'algorithmic_GBps': b_alg / ms / 1e6, 'kernel': 'raster' if args.raster else 'bucketed', 'labelled_pixels': px, 'features': F, 'thresholds': NT}), flush=True)
         del hist, nodes
     if args.check and rank == 0:
         from oracle import c_oracle as co
@@ -95,8 +108,12 @@ def main():
         hist = torch.zeros((S, nf, NT + 1, C), dtype=torch.int32, device='cuda')
         d2, l2, nd2 = depth[:2].contiguous(), labels[:2].contiguous(), torch.from_numpy(np.ascontiguousarray(nodes_np)).cuda()
         slot = torch.arange(S, dtype=torch.int32, device='cuda')
-        _capi.check(lib.rdf_train_hist(_capi.dptr(d2), _capi.dptr(l2), _capi.dptr(nd2), 2, W, H, _capi.dptr(slot), S,
-                                       _capi.dptr(offsets[:nf]), _capi.dptr(thresholds[:nf]), nf, NT, C, _capi.dptr(hist), st()))
+        need = ctypes.c_size_t()
+        _capi.check(lib.rdf_train_bucket_workspace_bytes(2 * H * W, S, ctypes.byref(need)))
+        ws = torch.zeros(((need.value + 3) // 4,), dtype=torch.int32, device='cuda')
+        _capi.check(lib.rdf_train_bucket(_capi.dptr(nd2), 2 * H * W, _capi.dptr(slot), S, _capi.dptr(ws), need.value, st()))
+        _capi.check(lib.rdf_train_hist_bucketed(_capi.dptr(d2), _capi.dptr(l2), 2, W, H, _capi.dptr(ws), S,
+                                                _capi.dptr(offsets[:nf]), _capi.dptr(thresholds[:nf]), nf, NT, C, _capi.dptr(hist), st()))
         torch.cuda.synchronize()
         exp = co.train_hist(depth_np[:2], labels_np[:2], nodes_np, np.arange(S, dtype=np.int32), S, offsets_np[:nf], thresholds_np[:nf], C)
         print(json.dumps({'cfg4_check_vs_c_oracle': bool(np.array_equal(hist.cpu().numpy().view(np.uint32), exp))}), flush=True)
