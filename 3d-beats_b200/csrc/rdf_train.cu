@@ -325,11 +325,25 @@ __device__ __forceinline__ int tb_int_thresh(float t) {
     return __float2int_ru(t);
 }
 
+// shared-memory u32 add through the .shared window (a generic-address atomic costs an address-space conversion per use)
+__device__ __forceinline__ void tb_red_shared(unsigned smem_addr, unsigned v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int tb_lds(unsigned smem_addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_addr));
+    return v;
+}
+
+// LOG2NTP: thresholds of a feature are padded in shared memory to NTP = 2^LOG2NTP entries with INT_MAX, so the search is a
+// fixed, fully unrolled sequence of LOG2NTP + 1 loads without bound checks.
+template <int LOG2NTP>
 __global__ void __launch_bounds__(TB_THREADS, 1) rdf_train_hist_bucketed_kernel(const rdf_histb_params p) {
+    constexpr int NTP = 1 << LOG2NTP;
     extern __shared__ __align__(16) unsigned char tb_smem[];
     float4* off_s = reinterpret_cast<float4*>(tb_smem);                          // [FC]
-    int* thr_s = reinterpret_cast<int*>(off_s + p.FC);                           // [FC][NT]
-    uint32_t* hist_s = reinterpret_cast<uint32_t*>(thr_s + (size_t)p.FC * p.NT); // [FC][NB][C]
+    int* thr_s = reinterpret_cast<int*>(off_s + p.FC);                           // [FC][NTP]
+    uint32_t* hist_s = reinterpret_cast<uint32_t*>(thr_s + (size_t)p.FC * NTP);  // [FC][NB][C]
     unsigned char* exact_s = reinterpret_cast<unsigned char*>(hist_s + (size_t)p.FC * p.NB * p.C);   // [FC]
     __shared__ int s_slot;
 
@@ -346,7 +360,10 @@ __global__ void __launch_bounds__(TB_THREADS, 1) rdf_train_hist_bucketed_kernel(
         off_s[j] = o;
         exact_s[j] = !(rdf_fastfloor_domain(o.x) && rdf_fastfloor_domain(o.y) && rdf_fastfloor_domain(o.z) && rdf_fastfloor_domain(o.w));
     }
-    for (int i = threadIdx.x; i < nf * p.NT; i += TB_THREADS) thr_s[i] = tb_int_thresh(__ldg(p.thresholds + (size_t)f0 * p.NT + i));
+    for (int i = threadIdx.x; i < nf * NTP; i += TB_THREADS) {
+        const int j = i >> LOG2NTP, k = i & (NTP - 1);
+        thr_s[i] = k < p.NT ? tb_int_thresh(__ldg(p.thresholds + (size_t)(f0 + j) * p.NT + k)) : 0x7fffffff;
+    }
     const int per_chunk = nf * p.NB * p.C;
     for (int i = threadIdx.x; i < per_chunk; i += TB_THREADS) hist_s[i] = 0u;
     if (threadIdx.x == 0) {                                                      // slot of the first pixel of the tile
@@ -361,8 +378,9 @@ __global__ void __launch_bounds__(TB_THREADS, 1) rdf_train_hist_bucketed_kernel(
 
     const int per_img = p.W * p.H;
     const bool fast_ok = p.W <= 65535 && p.H <= 65535;
-    int p2 = 1;
-    while (p2 * 2 <= p.NT) p2 *= 2;                                              // largest power of two <= NT
+    const unsigned thr_base = (unsigned)__cvta_generic_to_shared(thr_s);
+    const unsigned hist_base = (unsigned)__cvta_generic_to_shared(hist_s);
+    const unsigned row_bytes = (unsigned)(p.NB * p.C) * 4u;                      // one feature's histogram
     int cur = tile0;
     int slot = s_slot;
     while (cur < tile1) {
@@ -390,17 +408,20 @@ __global__ void __launch_bounds__(TB_THREADS, 1) rdf_train_hist_bucketed_kernel(
             const float df = (float)d;
             const float rcp = __frcp_rn(df);
             const float xm = (float)X + RDF_MAGIC_F, ym = (float)Y + RDF_MAGIC_F;
-            const int leader = __ffs(am) - 1;
+            const bool is_leader = lane == __ffs(am) - 1;
             const unsigned am_cnt = (unsigned)__popc(am);
+            const unsigned label4 = label * 4u;
+            const unsigned c4 = (unsigned)p.C * 4u;
             // TB_U features per trip: their 2 * TB_U probes are issued before any is consumed and the TB_U threshold searches
-            // advance in lock step, so one warp keeps several independent load chains in flight (the loop is bound by
-            // latency, not by issue: 8 warps per scheduler, each step a dependent L2 or shared-memory access).
+            // advance in lock step, so one warp keeps several independent load chains in flight.
             for (int j0 = 0; j0 < nf; j0 += TB_U) {
                 int f[TB_U];
+                unsigned tha[TB_U];                                              // shared address of the feature's thresholds
 #pragma unroll
                 for (int u = 0; u < TB_U; u++) {
                     const int j = min(j0 + u, nf - 1);                          // tail: recompute the last feature, not counted
                     const float4 o = off_s[j];
+                    tha[u] = thr_base + (unsigned)j * (NTP * 4u);
                     // compute_feature with scale 1 (tree_train.cu:58); d == 0 -> 0.f (decision_tree_common.hpp:12)
                     f[u] = 0;
                     if (d != 0u) {
@@ -408,33 +429,39 @@ __global__ void __launch_bounds__(TB_THREADS, 1) rdf_train_hist_bucketed_kernel(
                         else f[u] = rdf_feature_i<false>(img, p.W, p.H, X, Y, df, rcp, xm, ym, o.x, o.y, o.z, o.w);
                     }
                 }
-                // bin = #{k : t_k <= f}: binary lifting over the ascending integer thresholds, same trip count for every lane
-                int pos[TB_U];
+                // bin = #{k : t_k <= f}: binary search by halving steps on byte offsets, then one last compare
+                unsigned pos[TB_U];
 #pragma unroll
-                for (int u = 0; u < TB_U; u++) pos[u] = 0;
-                for (int step = p2; step > 0; step >>= 1) {
+                for (int u = 0; u < TB_U; u++) pos[u] = 0u;
+#pragma unroll
+                for (int lg = LOG2NTP - 1; lg >= 0; lg--) {
 #pragma unroll
                     for (int u = 0; u < TB_U; u++) {
-                        const int* th = thr_s + min(j0 + u, nf - 1) * p.NT;
-                        const int q = pos[u] + step;
-                        if (q <= p.NT && th[q - 1] <= f[u]) pos[u] = q;
+                        const int t = tb_lds(tha[u] + pos[u] + ((4u << lg) - 4u));      // thresholds[pos + step - 1]
+                        pos[u] += t <= f[u] ? (4u << lg) : 0u;
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < TB_U; u++) {
+                    const int t = tb_lds(tha[u] + pos[u]);                              // pos <= NTP - 1
+                    pos[u] += t <= f[u] ? 4u : 0u;                                      // pos = 4 * bin, bin in 0..NT
+                }
+#pragma unroll
+                for (int u = 0; u < TB_U; u++) {
                     if (j0 + u < nf) {
-                        const int key = pos[u] * p.C + (int)label;
-                        uint32_t* dst = hist_s + (size_t)(j0 + u) * p.NB * p.C;
+                        const unsigned key = pos[u] * (unsigned)p.C + label4;           // byte offset of [bin][label]
+                        const unsigned dst = hist_base + (unsigned)(j0 + u) * row_bytes + key;
                         int all_same;
                         __match_all_sync(am, key, &all_same);
                         if (all_same) {
-                            if (lane == leader) atomicAdd(dst + key, am_cnt);
+                            if (is_leader) tb_red_shared(dst, am_cnt);
                         } else {
                             const unsigned grp = __match_any_sync(am, key);
-                            if (lane == __ffs(grp) - 1) atomicAdd(dst + key, (unsigned)__popc(grp));
+                            if (lane == __ffs(grp) - 1) tb_red_shared(dst, (unsigned)__popc(grp));
                         }
                     }
                 }
+                (void)c4;
             }
         }
         __syncthreads();
@@ -474,8 +501,11 @@ extern "C" int rdf_train_hist_bucketed(const uint16_t* depth_dev, const uint16_t
     p.offsets = offsets_dev; p.thresholds = thresholds_dev; p.hist = hist_dev;
     p.W = dim_x; p.H = dim_y; p.S = num_slots; p.F = num_features; p.NT = num_thresholds; p.NB = num_thresholds + 1;
     p.C = num_classes;
+    int log2ntp = 0;
+    while ((1 << log2ntp) < p.NT) log2ntp++;
+    RDF_REQUIRE(log2ntp <= 10, "rdf_train_hist_bucketed: at most 1024 thresholds per feature (got %d)", p.NT);
     const size_t smem_budget = 220 * 1024;
-    const size_t per_feature = sizeof(float4) + sizeof(int) * (size_t)p.NT + sizeof(uint32_t) * (size_t)p.NB * p.C + 1;
+    const size_t per_feature = sizeof(float4) + sizeof(int) * ((size_t)1 << log2ntp) + sizeof(uint32_t) * (size_t)p.NB * p.C + 1;
     int fc = (int)((smem_budget - 64) / per_feature);
     if (fc > TB_MAX_FC) fc = TB_MAX_FC;
     if (fc > p.F) fc = p.F;
@@ -488,15 +518,24 @@ extern "C" int rdf_train_hist_bucketed(const uint16_t* depth_dev, const uint16_t
     fc = (fc + 3) & ~3;                                                          // keeps the arrays behind off_s 16-byte aligned
     p.FC = fc;
     const size_t smem = per_feature * fc + 64;
-    static bool attr_set = false;
-    if (!attr_set) {
-        RDF_CUDA(cudaFuncSetAttribute(rdf_train_hist_bucketed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget + 4096));
-        attr_set = true;
-    }
     const int64_t tiles = (num_pixels + TB_TILE - 1) / TB_TILE;
     const int chunks2 = (p.F + fc - 1) / fc;
     RDF_REQUIRE(chunks2 <= 65535, "rdf_train_hist_bucketed: too many feature chunks (%d)", chunks2);
-    rdf_train_hist_bucketed_kernel<<<dim3((unsigned)tiles, (unsigned)chunks2), TB_THREADS, smem, rdf_stream(stream)>>>(p);
+    const dim3 grid((unsigned)tiles, (unsigned)chunks2);
+    static bool attr_set[11] = {false};
+#define TB_CASE(L)                                                                                                      \
+    case L:                                                                                                             \
+        if (!attr_set[L]) {                                                                                             \
+            RDF_CUDA(cudaFuncSetAttribute(rdf_train_hist_bucketed_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)smem_budget + 4096));                                                   \
+            attr_set[L] = true;                                                                                         \
+        }                                                                                                               \
+        rdf_train_hist_bucketed_kernel<L><<<grid, TB_THREADS, smem, rdf_stream(stream)>>>(p);                           \
+        break;
+    switch (log2ntp) {
+        TB_CASE(0) TB_CASE(1) TB_CASE(2) TB_CASE(3) TB_CASE(4) TB_CASE(5) TB_CASE(6) TB_CASE(7) TB_CASE(8) TB_CASE(9) TB_CASE(10)
+    }
+#undef TB_CASE
     RDF_LAUNCH_CHECK("rdf_train_hist_bucketed_kernel");
     return RDF_OK;
 }
