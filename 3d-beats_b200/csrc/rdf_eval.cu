@@ -18,8 +18,11 @@ struct rdf_eval_params {
     float scale;
 };
 
+#ifndef RDF_EVAL_MIN_BLOCKS
+#define RDF_EVAL_MIN_BLOCKS 4      // CTAs per SM the register allocation aims for (experiments: -DRDF_EVAL_MIN_BLOCKS=5)
+#endif
 template <int T, int WARP_W, bool SCALE1, bool FORCE_EXACT>
-__global__ void __launch_bounds__(256) rdf_eval_packed_kernel(const rdf_eval_params p) {
+__global__ void __launch_bounds__(256, RDF_EVAL_MIN_BLOCKS) rdf_eval_packed_kernel(const rdf_eval_params p) {
     constexpr int WARP_H = 32 / WARP_W;
     constexpr int WARPS_X = 32 / WARP_W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

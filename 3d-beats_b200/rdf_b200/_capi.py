@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'librdf_b200.so')
+LIB_PATH = os.environ.get('RDF_B200_LIB') or os.path.join(_HERE, 'librdf_b200.so')   # override: kernel-variant experiments
 
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int
