@@ -355,17 +355,25 @@ __global__ void __launch_bounds__(TB_THREADS, 1) rdf_train_hist_bucketed_kernel(
     const int nf = min(p.FC, p.F - f0);
     const int lane = threadIdx.x & 31;
 
-    for (int j = threadIdx.x; j < nf; j += TB_THREADS) {
-        const float4 o = __ldg(reinterpret_cast<const float4*>(p.offsets) + f0 + j);
+    // the chunk is padded to a multiple of TB_U features (zero offsets, INT_MAX thresholds): padded rows are evaluated and
+    // counted into their own (never flushed) histogram rows, which keeps the inner loop free of tail tests
+    const int nfp = (nf + TB_U - 1) / TB_U * TB_U;                                // <= FC (FC is a multiple of 4)
+    __shared__ int s_any_exact;
+    if (threadIdx.x == 0) s_any_exact = (p.W > 65535 || p.H > 65535) ? 1 : 0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < nfp; j += TB_THREADS) {
+        const float4 o = j < nf ? __ldg(reinterpret_cast<const float4*>(p.offsets) + f0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
         off_s[j] = o;
-        exact_s[j] = !(rdf_fastfloor_domain(o.x) && rdf_fastfloor_domain(o.y) && rdf_fastfloor_domain(o.z) && rdf_fastfloor_domain(o.w));
+        const bool ex = !(rdf_fastfloor_domain(o.x) && rdf_fastfloor_domain(o.y) && rdf_fastfloor_domain(o.z) && rdf_fastfloor_domain(o.w));
+        exact_s[j] = ex;
+        if (ex) s_any_exact = 1;
     }
-    for (int i = threadIdx.x; i < nf * NTP; i += TB_THREADS) {
+    for (int i = threadIdx.x; i < nfp * NTP; i += TB_THREADS) {
         const int j = i >> LOG2NTP, k = i & (NTP - 1);
-        thr_s[i] = k < p.NT ? tb_int_thresh(__ldg(p.thresholds + (size_t)(f0 + j) * p.NT + k)) : 0x7fffffff;
+        thr_s[i] = (j < nf && k < p.NT) ? tb_int_thresh(__ldg(p.thresholds + (size_t)(f0 + j) * p.NT + k)) : 0x7fffffff;
     }
     const int per_chunk = nf * p.NB * p.C;
-    for (int i = threadIdx.x; i < per_chunk; i += TB_THREADS) hist_s[i] = 0u;
+    for (int i = threadIdx.x; i < nfp * p.NB * p.C; i += TB_THREADS) hist_s[i] = 0u;
     if (threadIdx.x == 0) {                                                      // slot of the first pixel of the tile
         int lo = 0, hi = p.S - 1;                                               // last s with starts[s] <= tile0
         while (lo < hi) {
@@ -377,7 +385,8 @@ __global__ void __launch_bounds__(TB_THREADS, 1) rdf_train_hist_bucketed_kernel(
     __syncthreads();
 
     const int per_img = p.W * p.H;
-    const bool fast_ok = p.W <= 65535 && p.H <= 65535;
+    const bool any_exact = s_any_exact != 0;                                     // uniform: some feature needs __fdiv_rn
+    const unsigned lanemask_lt = (1u << lane) - 1u;
     const unsigned thr_base = (unsigned)__cvta_generic_to_shared(thr_s);
     const unsigned hist_base = (unsigned)__cvta_generic_to_shared(hist_s);
     const unsigned row_bytes = (unsigned)(p.NB * p.C) * 4u;                      // one feature's histogram
@@ -408,26 +417,21 @@ __global__ void __launch_bounds__(TB_THREADS, 1) rdf_train_hist_bucketed_kernel(
             const float df = (float)d;
             const float rcp = __frcp_rn(df);
             const float xm = (float)X + RDF_MAGIC_F, ym = (float)Y + RDF_MAGIC_F;
-            const bool is_leader = lane == __ffs(am) - 1;
-            const unsigned am_cnt = (unsigned)__popc(am);
             const unsigned label4 = label * 4u;
-            const unsigned c4 = (unsigned)p.C * 4u;
             // TB_U features per trip: their 2 * TB_U probes are issued before any is consumed and the TB_U threshold searches
             // advance in lock step, so one warp keeps several independent load chains in flight.
-            for (int j0 = 0; j0 < nf; j0 += TB_U) {
+            for (int j0 = 0; j0 < nfp; j0 += TB_U) {
                 int f[TB_U];
                 unsigned tha[TB_U];                                              // shared address of the feature's thresholds
 #pragma unroll
                 for (int u = 0; u < TB_U; u++) {
-                    const int j = min(j0 + u, nf - 1);                          // tail: recompute the last feature, not counted
+                    const int j = j0 + u;
                     const float4 o = off_s[j];
                     tha[u] = thr_base + (unsigned)j * (NTP * 4u);
                     // compute_feature with scale 1 (tree_train.cu:58); d == 0 -> 0.f (decision_tree_common.hpp:12)
-                    f[u] = 0;
-                    if (d != 0u) {
-                        if (exact_s[j] || !fast_ok) f[u] = rdf_feature_i<true>(img, p.W, p.H, X, Y, df, rcp, xm, ym, o.x, o.y, o.z, o.w);
-                        else f[u] = rdf_feature_i<false>(img, p.W, p.H, X, Y, df, rcp, xm, ym, o.x, o.y, o.z, o.w);
-                    }
+                    if (any_exact && exact_s[j]) f[u] = rdf_feature_i<true>(img, p.W, p.H, X, Y, df, rcp, xm, ym, o.x, o.y, o.z, o.w);
+                    else f[u] = rdf_feature_i<false>(img, p.W, p.H, X, Y, df, rcp, xm, ym, o.x, o.y, o.z, o.w);
+                    f[u] = d != 0u ? f[u] : 0;
                 }
                 // bin = #{k : t_k <= f}: binary search by halving steps on byte offsets, then one last compare
                 unsigned pos[TB_U];
@@ -448,20 +452,12 @@ __global__ void __launch_bounds__(TB_THREADS, 1) rdf_train_hist_bucketed_kernel(
                 }
 #pragma unroll
                 for (int u = 0; u < TB_U; u++) {
-                    if (j0 + u < nf) {
-                        const unsigned key = pos[u] * (unsigned)p.C + label4;           // byte offset of [bin][label]
-                        const unsigned dst = hist_base + (unsigned)(j0 + u) * row_bytes + key;
-                        int all_same;
-                        __match_all_sync(am, key, &all_same);
-                        if (all_same) {
-                            if (is_leader) tb_red_shared(dst, am_cnt);
-                        } else {
-                            const unsigned grp = __match_any_sync(am, key);
-                            if (lane == __ffs(grp) - 1) tb_red_shared(dst, (unsigned)__popc(grp));
-                        }
-                    }
+                    const unsigned key = pos[u] * (unsigned)p.C + label4;               // byte offset of [bin][label]
+                    const unsigned dst = hist_base + (unsigned)(j0 + u) * row_bytes + key;
+                    // one shared-memory reduction per distinct counter of the warp (lowest lane of each group)
+                    const unsigned grp = __match_any_sync(am, key);
+                    if ((grp & lanemask_lt) == 0u) tb_red_shared(dst, (unsigned)__popc(grp));
                 }
-                (void)c4;
             }
         }
         __syncthreads();
