@@ -81,3 +81,32 @@ def test_product_has_no_cpu_path():
         from rdf_b200 import buffers
         with pytest.raises(RuntimeError):
             buffers.GPUArray((4,), dtype='float32')
+
+
+def _build_c_smoke(tmp_path):
+    import subprocess
+    from rdf_b200 import _capi
+    exe = str(tmp_path / 'abi_smoke')
+    libdir = os.path.dirname(_capi.LIB_PATH)
+    cmd = ['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), '-I', '/usr/local/cuda/include',
+           os.path.join(ROOT, 'tests', 'c', 'abi_smoke.c'), '-o', exe, '-L', libdir, '-lrdf_b200', '-L', '/usr/local/cuda/lib64', '-lcudart',
+           '-Wl,-rpath,' + libdir, '-Wl,-rpath,/usr/local/cuda/lib64']
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-3000:]
+    return exe
+
+
+def test_plain_c_program_links_and_gets_the_error_contract(tmp_path):
+    """A C99 program compiled with gcc consumes include/rdf_b200.h and librdf_b200.so directly (no C++, no torch)."""
+    import subprocess
+    exe = _build_c_smoke(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and 'abi_smoke ok' in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_plain_c_program_device_path(tmp_path):
+    import subprocess
+    exe = _build_c_smoke(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and 'device path' in out.stdout, out.stdout + out.stderr
