@@ -552,7 +552,8 @@ __device__ __forceinline__ float rdf_gini(const unsigned long long* c, int C, un
     return __fsub_rn(1.f, p);
 }
 
-#define PB_THREADS 256
+#define PB_WARPS 16
+#define PB_THREADS (PB_WARPS * 32)
 
 struct rdf_pick_params {
     const int32_t* active_nodes;
@@ -567,8 +568,22 @@ struct rdf_pick_params {
     int num_active, S, F, NT, NB, C, level, D;
 };
 
-// one block per active node; threads stride over features, each scanning its feature's NT thresholds with a running
-// prefix of the bin histogram.  Winner = greatest gain, ties -> smallest candidate index (= first in proposal order).
+__device__ __forceinline__ unsigned pb_warp_incl_scan(unsigned v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// One CTA per active node; each WARP takes whole features (f = warp, warp + PB_WARPS, ...) with lanes across the threshold
+// bins, so a feature's [NT+1][C] histogram (1040 B at NT=64, C=4) is read with coalesced loads; left counts per threshold come
+// from warp prefix sums over the bins.  (The first version gave each thread a feature and walked its 1040 bytes serially:
+// 32 different cache lines per load instruction, 285 GB/s at 4096 nodes - profiles/r01_train_cfg4.md.)
+// Per class the Gini terms are accumulated in class order exactly as the reference's compiled helpers do
+// (cvt.rn.f32.u64, div.rn, fma; tree_train.cu:72-89).  Winner = greatest gain, ties -> smallest candidate index
+// (= first in proposal order: feature-major, threshold-minor).
 __global__ void __launch_bounds__(PB_THREADS) rdf_train_pick_best_kernel(const rdf_pick_params p) {
     const int a = blockIdx.x;
     if (a >= p.num_active) return;
@@ -576,12 +591,16 @@ __global__ void __launch_bounds__(PB_THREADS) rdf_train_pick_best_kernel(const r
     const int slot = p.node_slot[node];
     if (slot < 0) return;                                          // not in this node block (tree_train.cu:135)
     const int C = p.C;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     extern __shared__ unsigned long long pb_smem[];
     unsigned long long* par = pb_smem;                             // [C]
-    unsigned long long* scratch = par + C;                         // [PB_THREADS][2][C] left/right of the running candidate
-    __shared__ float red_g[PB_THREADS];
-    __shared__ int red_i[PB_THREADS];
+    unsigned long long* left = par + C;                            // [C]  (winner's child counts, thread 0)
+    unsigned long long* right = left + C;                          // [C]
+    unsigned* tot_w = reinterpret_cast<unsigned*>(right + C) + (size_t)warp * 2 * C;   // [C] class totals of the warp's feature
+    unsigned* carry_w = tot_w + C;                                 // [C] running prefix per class
+    __shared__ float red_g[PB_WARPS];
+    __shared__ int red_i[PB_WARPS];
     __shared__ float s_gini_parent;
     __shared__ unsigned long long s_parent_sum;
 
@@ -598,56 +617,84 @@ __global__ void __launch_bounds__(PB_THREADS) rdf_train_pick_best_kernel(const r
     const float p_sum_f = __ull2float_rn(parent_sum);
     const float gini_parent = s_gini_parent;
 
-    unsigned long long* left = scratch + (size_t)threadIdx.x * 2 * C;
-    unsigned long long* right = left + C;
     float best_g = -1.f;
     int best_i = 0x7fffffff;
-    for (int f = threadIdx.x; f < p.F; f += PB_THREADS) {
+    for (int f = warp; f < p.F; f += PB_WARPS) {
         const uint32_t* h = p.hist + ((size_t)slot * p.F + f) * p.NB * C;
+        // class totals over all NT + 1 bins
+        unsigned T = 0;
         for (int c = 0; c < C; c++) {
-            unsigned long long tot = 0;
-            for (int b = 0; b < p.NB; b++) tot += h[b * C + c];
-            left[c] = 0;
-            right[c] = tot;
-        }
-        for (int k = 0; k < p.NT; k++) {
-            unsigned long long ls = 0, rs = 0;
-            for (int c = 0; c < C; c++) {                          // left = bins 0..k  (f < t_k)
-                const unsigned long long v = h[k * C + c];
-                left[c] += v;
-                right[c] -= v;
-                ls += left[c];
-                rs += right[c];
+            unsigned sum = 0;
+            for (int b = lane; b < p.NB; b += 32) sum += __ldg(h + b * C + c);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane == 0) {
+                tot_w[c] = sum;
+                carry_w[c] = 0u;
             }
+            T += sum;
+        }
+        __syncwarp();
+        unsigned l_carry = 0;
+        for (int b0 = 0; b0 < p.NT; b0 += 32) {                    // candidates k = b0 + lane: left = bins 0..k  (f < t_k)
+            const int k = b0 + lane;
+            const bool cand = k < p.NT;
+            unsigned n = 0;
+            if (cand)
+                for (int c = 0; c < C; c++) n += __ldg(h + k * C + c);
+            const unsigned n_incl = pb_warp_incl_scan(n, lane);
+            const unsigned ls = l_carry + n_incl, rs = T - ls;
+            l_carry += __shfl_sync(0xffffffffu, n_incl, 31);
+            const float lsf = __uint2float_rn(ls), rsf = __uint2float_rn(rs);
+            float pl = 0.f, pr = 0.f;
+            for (int c = 0; c < C; c++) {
+                const unsigned v = cand ? __ldg(h + k * C + c) : 0u;
+                const unsigned v_incl = pb_warp_incl_scan(v, lane);
+                const unsigned base = carry_w[c];
+                const unsigned lc = base + v_incl, rc = tot_w[c] - lc;
+                const unsigned chunk = __shfl_sync(0xffffffffu, v_incl, 31);
+                __syncwarp();
+                if (lane == 0) carry_w[c] = base + chunk;
+                const float pil = __fdiv_rn(__uint2float_rn(lc), lsf);
+                pl = __fmaf_rn(pil, pil, pl);
+                const float pir = __fdiv_rn(__uint2float_rn(rc), rsf);
+                pr = __fmaf_rn(pir, pir, pr);
+            }
+            __syncwarp();
             float g = 0.f;                                         // a side empty -> 0 (tree_train.cu:158-160)
             if (ls && rs) {
-                const float lt = __fmul_rn(__fdiv_rn(__ull2float_rn(ls), p_sum_f), rdf_gini(left, C, ls));
-                const float rem = __fmaf_rn(__fdiv_rn(__ull2float_rn(rs), p_sum_f), rdf_gini(right, C, rs), lt);
+                const float lt = __fmul_rn(__fdiv_rn(lsf, p_sum_f), __fsub_rn(1.f, pl));
+                const float rem = __fmaf_rn(__fdiv_rn(rsf, p_sum_f), __fsub_rn(1.f, pr), lt);
                 g = __fsub_rn(gini_parent, rem);
             }
-            if (g > best_g) {                                      // strict >, candidates visited in ascending index
+            if (cand && g > best_g) {                              // strict >: a lane sees its candidates in ascending index
                 best_g = g;
                 best_i = f * p.NT + k;
             }
         }
     }
-    red_g[threadIdx.x] = best_g;
-    red_i[threadIdx.x] = best_i;
-    __syncthreads();
-    for (int s = PB_THREADS / 2; s > 0; s >>= 1) {
-        if (threadIdx.x < s) {
-            const float g2 = red_g[threadIdx.x + s];
-            const int i2 = red_i[threadIdx.x + s];
-            const float g1 = red_g[threadIdx.x];
-            const int i1 = red_i[threadIdx.x];
-            if (g2 > g1 || (g2 == g1 && i2 < i1)) {
-                red_g[threadIdx.x] = g2;
-                red_i[threadIdx.x] = i2;
-            }
+    // greatest gain, ties -> smallest candidate index: across lanes, then across warps
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float g2 = __shfl_xor_sync(0xffffffffu, best_g, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (g2 > best_g || (g2 == best_g && i2 < best_i)) {
+            best_g = g2;
+            best_i = i2;
         }
-        __syncthreads();
     }
+    if (lane == 0) {
+        red_g[warp] = best_g;
+        red_i[warp] = best_i;
+    }
+    __syncthreads();
     if (threadIdx.x != 0) return;
+    for (int wv = 1; wv < PB_WARPS; wv++) {
+        if (red_g[wv] > red_g[0] || (red_g[wv] == red_g[0] && red_i[wv] < red_i[0])) {
+            red_g[0] = red_g[wv];
+            red_i[0] = red_i[wv];
+        }
+    }
     best_g = red_g[0];
     best_i = red_i[0];
     if (!(best_g > -1.f)) return;                                  // the reference asserts best_g > -1 (tree_train.cu:170)
@@ -728,7 +775,7 @@ extern "C" int rdf_train_pick_best(int num_active, const int32_t* active_nodes_d
     p.best_gain = best_gain_dev;
     p.num_active = num_active; p.S = num_slots; p.F = num_features; p.NT = num_thresholds; p.NB = num_thresholds + 1;
     p.C = num_classes; p.level = level; p.D = max_depth;
-    const size_t smem = sizeof(unsigned long long) * ((size_t)num_classes + (size_t)PB_THREADS * 2 * num_classes);
+    const size_t smem = sizeof(unsigned long long) * 3 * (size_t)num_classes + sizeof(unsigned) * (size_t)PB_WARPS * 2 * num_classes;
     static size_t smem_set = 0;
     if (smem > 48 * 1024 && smem > smem_set) {
         RDF_CUDA(cudaFuncSetAttribute(rdf_train_pick_best_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
