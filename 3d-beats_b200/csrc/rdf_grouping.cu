@@ -1,0 +1,173 @@
+// Hand grouping on the device: replaces the reference's D2H copy -> C++ BFS flood fill -> H2D copy -> scatter kernel
+// (src/3d_bz.py:222-250, src/cpp_grouping/grouping.cpp:80-191, write_pixel_groups_to_stencil_image) by ONE launch on the
+// 1/8-resolution depth image (106 x 60 pixels for the product): 4-connected components of the non-zero pixels with a
+// shared-memory union-find whose roots are the smallest raster index of each component, component sizes and x-sums by
+// shared-memory atomics, then the reference's selection rule - components above the size threshold, centroid x < w/2 ->
+// "right" candidate else "left", per side the largest component, ties -> the one met first in raster order (= smallest root).
+// Output is the stencil image the reference builds from the coordinate list (1 = right group, 2 = left group, 0 elsewhere) and
+// g_info[2][3] = (size, centroid x, centroid y).  SURVEY 8(f) rank 2: the only native C++ component of the reference and the
+// only mandatory host round trip of the live frame.
+#include "rdf_common.cuh"
+
+#define GR_THREADS 1024
+#define GR_MAX_PIXELS 16384
+
+// find with path halving: chains stay short although roots are chosen by smallest index, not by rank
+__device__ __forceinline__ int gr_find(volatile int* parent, int i) {
+    int p = parent[i];
+    while (p != i) {
+        const int gp = parent[p];
+        if (gp != p) parent[i] = gp;        // benign race: any ancestor is a valid parent
+        i = p;
+        p = gp;
+    }
+    return i;
+}
+
+__device__ __forceinline__ void gr_unite(int* parent, int a, int b) {
+    bool done;
+    do {
+        a = gr_find(parent, a);
+        b = gr_find(parent, b);
+        if (a < b) {
+            const int old = atomicMin(&parent[b], a);
+            done = old == b;
+            b = old;
+        } else if (b < a) {
+            const int old = atomicMin(&parent[a], b);
+            done = old == a;
+            a = old;
+        } else {
+            done = true;
+        }
+    } while (!done);
+}
+
+// Phases (one CTA):
+//   1. one thread per ROW: horizontal runs of non-zero pixels; every pixel of a run points at the run's first pixel, which
+//      holds the run's length and x-sum (so later statistics cost one atomic per run, not per pixel: a 1500-pixel hand blob
+//      would otherwise serialise 1500 shared-memory atomics on one address);
+//   2. vertical unions between runs of neighbouring rows (only where an overlap segment starts);
+//   3. run statistics are added to their component's root; 4. every pixel is pointed at its root;
+//   5. selection over roots; 6. y-sums of the two selected components (one thread per row); 7. stencil + g_info.
+__global__ void __launch_bounds__(GR_THREADS) rdf_group_hands_kernel(const uint16_t* __restrict__ img, int w, int h, float pct_thresh,
+                                                                     uint16_t* __restrict__ stencil, float* __restrict__ g_info) {
+    extern __shared__ int gr_smem[];
+    const int N = w * h;
+    int* parent = gr_smem;              // [N]  -1 = background
+    int* cnt = parent + N;              // [N]  run length at run starts, then component size at roots
+    int* sumx = cnt + N;                // [N]  run x-sum at run starts, then component x-sum at roots
+    __shared__ unsigned long long best[2];      // per side: size << 32 | ~root
+    __shared__ int sumy[2];
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < N; i += GR_THREADS) {
+        parent[i] = __ldg(img + i) != 0 ? i : -1;                  // grouping.cpp:107-108
+        cnt[i] = 0;
+        sumx[i] = 0;
+    }
+    if (tid < 2) {
+        best[tid] = 0ull;
+        sumy[tid] = 0;
+    }
+    __syncthreads();
+    for (int y = tid; y < h; y += GR_THREADS) {                    // 1. runs
+        int start = -1;
+        for (int x = 0; x <= w; x++) {
+            const bool fg = x < w && parent[y * w + x] >= 0;
+            if (fg) {
+                if (start < 0) start = x;
+                parent[y * w + x] = y * w + start;
+            } else if (start >= 0) {
+                const int len = x - start;
+                cnt[y * w + start] = len;
+                sumx[y * w + start] = (start + x - 1) * len / 2;   // start + ... + (x - 1)
+                start = -1;
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < N - w; i += GR_THREADS) {                // 2. 4-connectivity (grouping.cpp:82-87): down edges between runs
+        if (parent[i] < 0 || parent[i + w] < 0) continue;
+        const int x = i % w;
+        if (x > 0 && parent[i - 1] >= 0 && parent[i + w - 1] >= 0) continue;   // same pair of runs as the pixel to the left
+        gr_unite(parent, i, i + w);
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += GR_THREADS) {                    // 3. run statistics -> root (roots keep their own run in place)
+        const int len = cnt[i];
+        if (len == 0) continue;
+        const int r = gr_find(parent, i);
+        if (r != i) {
+            atomicAdd(&cnt[r], len);
+            atomicAdd(&sumx[r], sumx[i]);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += GR_THREADS) parent[i] = parent[i] < 0 ? -1 : gr_find(parent, i);   // 4. flatten
+    __syncthreads();
+    for (int i = tid; i < N; i += GR_THREADS) {                    // 5. selection
+        if (parent[i] != i) continue;                              // roots only, one per component
+        const int n = cnt[i];
+        if (__fdiv_rn((float)n, (float)N) <= pct_thresh) continue;            // grouping.cpp:137
+        const float cx = __fdiv_rn((float)sumx[i], (float)n);                 // grouping.cpp:148
+        const int side = cx < __fdiv_rn((float)w, 2.f) ? 0 : 1;              // grouping.cpp:150
+        // strictly largest wins, so among equal sizes the component met first in raster order = smallest root (grouping.cpp:151,157)
+        atomicMax(&best[side], ((unsigned long long)(unsigned)n << 32) | (unsigned long long)(0xffffffffu - (unsigned)i));
+    }
+    __syncthreads();
+    int sel[2], seln[2];
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        seln[s] = (int)(best[s] >> 32);
+        sel[s] = seln[s] ? (int)(0xffffffffu - (unsigned)(best[s] & 0xffffffffull)) : -2;
+    }
+    for (int y = tid; y < h; y += GR_THREADS) {                    // 6. y-sums
+        int c0 = 0, c1 = 0;
+        for (int x = 0; x < w; x++) {
+            const int r = parent[y * w + x];
+            c0 += r == sel[0];
+            c1 += r == sel[1];
+        }
+        if (c0) atomicAdd(&sumy[0], y * c0);
+        if (c1) atomicAdd(&sumy[1], y * c1);
+    }
+    for (int i = tid; i < N; i += GR_THREADS) {                    // 7. stencil (src/3d_bz.py:243-250)
+        const int r = parent[i];
+        stencil[i] = (unsigned short)(r < 0 ? 0 : r == sel[0] ? 1 : r == sel[1] ? 2 : 0);
+    }
+    __syncthreads();
+    if (tid < 2) {
+        const int s = tid;
+        float n = 0.f, cx = 0.f, cy = 0.f;
+        if (seln[s]) {
+            n = (float)seln[s];
+            cx = __fdiv_rn((float)sumx[sel[s]], n);
+            cy = __fdiv_rn((float)sumy[s], n);                                // grouping.cpp:147
+        }
+        g_info[3 * s + 0] = n;
+        g_info[3 * s + 1] = cx;
+        g_info[3 * s + 2] = cy;
+    }
+}
+
+extern "C" int rdf_group_hands(const uint16_t* img_dev, int dim_x, int dim_y, float pct_thresh, uint16_t* stencil_dev,
+                               float* g_info_dev, void* stream) {
+    RDF_REQUIRE(img_dev && stencil_dev && g_info_dev, "rdf_group_hands: NULL argument");
+    RDF_REQUIRE(dim_x > 0 && dim_y > 0, "rdf_group_hands: bad shape %dx%d", dim_x, dim_y);
+    const int64_t n = (int64_t)dim_x * dim_y;
+    if (n > GR_MAX_PIXELS) {
+        rdf_set_error("rdf_group_hands: %dx%d exceeds the %d pixels of the shared-memory union-find (the product runs it on the "
+                      "1/8-resolution image)", dim_x, dim_y, GR_MAX_PIXELS);
+        return RDF_ERR_UNSUPPORTED;
+    }
+    const size_t smem = sizeof(int) * 3 * (size_t)n;
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        RDF_CUDA(cudaFuncSetAttribute(rdf_group_hands_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * 3 * GR_MAX_PIXELS)));
+        smem_set = sizeof(int) * 3 * GR_MAX_PIXELS;
+    }
+    rdf_group_hands_kernel<<<1, GR_THREADS, smem, rdf_stream(stream)>>>(img_dev, dim_x, dim_y, pct_thresh, stencil_dev, g_info_dev);
+    RDF_LAUNCH_CHECK("rdf_group_hands_kernel");
+    return RDF_OK;
+}

@@ -122,6 +122,17 @@ RDF_API int rdf_mean_shift_workspace_bytes(int dim_x, int dim_y, int num_labels,
 RDF_API int rdf_mean_shift(const uint16_t* labels_dev, int dim_x, int dim_y, int num_labels, const float* variances_dev,
                    int rounds, double* means_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ---- hand grouping (the step before the forest in the live product) -------------------------------
+ * rdf_group_hands replaces the D2H copy + CppGrouping.make_groups (src/cpp_grouping/grouping.cpp:80-191, binding
+ * src/cpp_grouping/cpp_grouping.pyx:15-26, call site src/3d_bz.py:222-231) + H2D copy + write_pixel_groups_to_stencil_image
+ * (src/3d_bz.py:239-250) by one launch: 4-connected components of the non-zero pixels of img_dev uint16[dim_y,dim_x] (the
+ * 1/8-resolution depth image; at most 16384 pixels), components with size/(dim_x*dim_y) <= pct_thresh dropped, the largest
+ * component whose centroid x < dim_x/2 becomes group 1 ("right"), the largest other one group 2 ("left"), ties -> first in
+ * raster order.  stencil_dev uint16[dim_y,dim_x] receives 1 / 2 / 0; g_info_dev float32[2][3] = (size, centroid x,
+ * centroid y) per group (zeros for an empty group; the reference leaves the centroid unspecified there). */
+RDF_API int rdf_group_hands(const uint16_t* img_dev, int dim_x, int dim_y, float pct_thresh, uint16_t* stencil_dev,
+                    float* g_info_dev, void* stream);
+
 /* ---- synthetic inputs (bench / tests; bit-exact twins of rdf_b200/synth.py) -------------------------------
  * kind: 0 dense-smooth, 1 dense-noise, 2 live-mask.  Frames first_frame .. first_frame+N-1. */
 RDF_API int rdf_synth_depth(uint16_t* depth_dev, int kind, int num_images, int dim_x, int dim_y, uint32_t seed,
