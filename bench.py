@@ -14,6 +14,7 @@ A step = one pass of get_labels_forest over the rank's frames, inputs resident i
   latency      BASELINE.json configs[1]: one 848x480 frame -> 2-layer stacked forest + 6-round mean shift, p50/p95/p99
   ref_gpu      the reference's own kernels (compiled unchanged for sm_100a) on the same GPU, same inputs (sub-batch)
   cpu_baseline the C oracle on the host cores over a bounded sample (rank 0, N=1 only)
+  train_cfg4   BASELINE.json configs[3]: one level of the training split search (bucket + histogram + pick-best)
 """
 import argparse
 import json
@@ -261,6 +262,69 @@ def latency_cfg2(iters=1000, warm=100):
     }
 
 
+def train_cfg4(level=8, iters=2):
+    """BASELINE configs[3] on this rank's GPU: one level of the split search over 42 dense-smooth 848x480 frames (17.1 M labelled
+    pixels), 2000 features x 64 thresholds, C = 4, 2^level active nodes: bucket the pixels by node + histogram + pick-best.
+    A feature sub-block is checked against the C oracle on two frames."""
+    import ctypes
+    import torch
+    from rdf_b200 import _capi, synth
+    from oracle import c_oracle as co
+    lib = _capi.load()
+    N, H, W, C, F, NT, D = 42, 480, 848, 4, 2000, 64, 16
+    S = 1 << level
+    depth_np = synth.depth_frames('dense-smooth', N, H, W)
+    labels_np = synth.train_labels(N, H, W)
+    nodes_np = synth.random_node_assignment(labels_np, level)
+    off_np, th_np = synth.random_proposals(F, NT)
+    depth = torch.from_numpy(depth_np.view(np.int16)).cuda()
+    labels = torch.from_numpy(labels_np.view(np.int16)).cuda()
+    nodes = torch.from_numpy(nodes_np).cuda()
+    offsets, thresholds = torch.from_numpy(off_np).cuda(), torch.from_numpy(th_np).cuda()
+    slot = torch.arange(S, dtype=torch.int32, device='cuda')
+    parent = torch.zeros((1 << D, C), dtype=torch.int64, device='cuda')
+    parent.view(-1).index_add_(0, nodes.view(-1).long() * C + labels.view(-1).long(), torch.ones(N * H * W, dtype=torch.int64, device='cuda'))
+    next_counts = torch.zeros_like(parent)
+    best_gain = torch.full((1 << D,), -1.0, dtype=torch.float32, device='cuda')
+    tree = torch.zeros(((1 << D) - 1, 7 + 2 * C), dtype=torch.float32, device='cuda')
+    hist = torch.zeros((S, F, NT + 1, C), dtype=torch.int32, device='cuda')
+    need = ctypes.c_size_t()
+    _capi.check(lib.rdf_train_bucket_workspace_bytes(N * H * W, S, ctypes.byref(need)))
+    ws = torch.zeros(((need.value + 3) // 4,), dtype=torch.int32, device='cuda')
+    st = _capi.stream_ptr
+
+    def one_level():
+        _capi.check(lib.rdf_train_bucket(_capi.dptr(nodes), N * H * W, _capi.dptr(slot), S, _capi.dptr(ws), need.value, st()))
+        hist.zero_()
+        _capi.check(lib.rdf_train_hist_bucketed(_capi.dptr(depth), _capi.dptr(labels), N, W, H, _capi.dptr(ws), S, _capi.dptr(offsets),
+                                                _capi.dptr(thresholds), F, NT, C, _capi.dptr(hist), st()))
+        _capi.check(lib.rdf_train_pick_best(S, _capi.dptr(slot), _capi.dptr(slot), _capi.dptr(parent), _capi.dptr(hist), S,
+                                            _capi.dptr(offsets), _capi.dptr(thresholds), F, NT, C, level, D, _capi.dptr(tree),
+                                            _capi.dptr(next_counts), _capi.dptr(best_gain), st()))
+    one_level()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        one_level()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    nf = 6                                                       # parity: 6 features x 64 thresholds on 2 frames vs the C oracle
+    h2 = torch.zeros((S, nf, NT + 1, C), dtype=torch.int32, device='cuda')
+    nodes2 = nodes[:2].contiguous()
+    _capi.check(lib.rdf_train_bucket(_capi.dptr(nodes2), 2 * H * W, _capi.dptr(slot), S, _capi.dptr(ws), need.value, st()))
+    _capi.check(lib.rdf_train_hist_bucketed(_capi.dptr(depth[:2]), _capi.dptr(labels[:2]), 2, W, H, _capi.dptr(ws), S, _capi.dptr(offsets[:nf]),
+                                            _capi.dptr(thresholds[:nf]), nf, NT, C, _capi.dptr(h2), st()))
+    torch.cuda.synchronize()
+    exp = co.train_hist(depth_np[:2], labels_np[:2], nodes_np[:2], np.arange(S, dtype=np.int32), S, off_np[:nf], th_np[:nf], C)
+    px = N * H * W
+    return {'workload': f'cfg4: {px} labelled pixels (42 frames 848x480), {F} features x {NT} thresholds, C={C}, level {level} ({S} nodes)',
+            'ms_per_level': ms, 'g_feature_evals_per_s': px * F / ms / 1e6, 'algorithmic_GBps': (px * 8 + px * F * 8) / ms / 1e6,
+            'histogram_bit_exact_vs_c_oracle': bool(np.array_equal(h2.cpu().numpy().view(np.uint32), exp)),
+            'what': 'rdf_train_bucket + rdf_train_hist_bucketed + rdf_train_pick_best, inputs resident'}
+
+
 def ref_gpu_rate(forest_canon, depth_dev, frames, H, W, steps=2):
     """The reference's evaluate_image_using_forest (compiled unchanged, its own launch geometry) on a sub-batch."""
     import torch
@@ -473,6 +537,10 @@ def main():
             line['latency'] = latency_cfg2()
         except Exception as e:                                        # never lose the headline number to an extra
             line['latency'] = {'error': repr(e)}
+        try:
+            line['train_cfg4'] = train_cfg4()
+        except Exception as e:
+            line['train_cfg4'] = {'error': repr(e)}
     print(json.dumps(line), flush=True)
 
 
