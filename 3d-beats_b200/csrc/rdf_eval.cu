@@ -15,8 +15,11 @@ struct rdf_eval_params {
     int tiles_x;
     int filter_class;
     int image0;
+    int smem_levels;          // upper tree levels staged in shared memory (0 .. RDF_EVAL_SMEM_LEVELS)
     float scale;
 };
+
+#define RDF_EVAL_SMEM_LEVELS 6
 
 #ifndef RDF_EVAL_MIN_BLOCKS
 #define RDF_EVAL_MIN_BLOCKS 4      // CTAs per SM the register allocation aims for (experiments: -DRDF_EVAL_MIN_BLOCKS=5)
@@ -25,6 +28,13 @@ template <int T, int WARP_W, bool SCALE1, bool FORCE_EXACT>
 __global__ void __launch_bounds__(256, RDF_EVAL_MIN_BLOCKS) rdf_eval_packed_kernel(const rdf_eval_params p) {
     constexpr int WARP_H = 32 / WARP_W;
     constexpr int WARPS_X = 32 / WARP_W;
+    // levels 0 .. KS-1 of all T trees in shared memory (2 KB per tree at KS = 6), staged before any thread leaves
+    __shared__ __align__(32) rdf_node_hdr hdr_s[T * ((1 << RDF_EVAL_SMEM_LEVELS) - 1)];
+    const int KS = min(p.fv.D, p.smem_levels);
+    if (KS > 0) {
+        rdf_stage_upper_levels(p.fv, KS, hdr_s);
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile_y = blockIdx.x / p.tiles_x, tile_x = blockIdx.x - tile_y * p.tiles_x;
     const int x = tile_x * 32 + (warp % WARPS_X) * WARP_W + (lane % WARP_W);
@@ -39,7 +49,7 @@ __global__ void __launch_bounds__(256, RDF_EVAL_MIN_BLOCKS) rdf_eval_packed_kern
     const unsigned d = __ldg(img + (size_t)Y * p.W + X);
     if (d == 0u || d == RDF_NO_PIXEL) return;                                            // tree_eval.cu:88-89
     int state[T];
-    rdf_walk<T, SCALE1, FORCE_EXACT>(p.fv, img, p.W, p.H, X, Y, d, p.scale, state);
+    rdf_walk<T, SCALE1, FORCE_EXACT>(p.fv, img, p.W, p.H, X, Y, d, p.scale, state, hdr_s, KS);
     const int lab = rdf_vote<T>(p.fv, state, p.probs ? p.probs + li * p.fv.C : nullptr);
     p.labels[li] = (uint16_t)lab;
 }
@@ -185,6 +195,15 @@ extern "C" int rdf_eval_forest(const rdf_forest_t* forest, const uint16_t* depth
     const int tiles_y = (h + 7) / 8;
     p.filter_class = filter_class;
     p.scale = scale;
+    {
+        static int lv = -1;                                         // RDF_SMEM_LEVELS overrides (experiments)
+        if (lv < 0) {
+            const char* e = getenv("RDF_SMEM_LEVELS");
+            lv = e ? atoi(e) : RDF_EVAL_SMEM_LEVELS;
+            if (lv < 0 || lv > RDF_EVAL_SMEM_LEVELS) lv = RDF_EVAL_SMEM_LEVELS;
+        }
+        p.smem_levels = lv;
+    }
     for (int n0 = 0; n0 < num_images; n0 += 65535) {
         const int nb = num_images - n0 < 65535 ? num_images - n0 : 65535;
         p.image0 = n0;

@@ -48,19 +48,14 @@ __device__ __forceinline__ rdf_hdr_regs rdf_load_hdr(const rdf_node_hdr* __restr
     return h;
 }
 
-// Walk T trees from their roots.  On return state[t] < 0: ~leaf_id of the reached leaf, or RDF_NO_LEAF if the walk fell
-// off level D-1 with a "continue" flag (adds nothing, src/cuda/tree_eval.cu:95-128).
-// SCALE1: scale == 1.0f, so scale*u == u exactly and the multiplies are dropped.  FORCE_EXACT: always use __fdiv_rn
-// (scale outside the fast domain); otherwise nodes flagged RDF_FLAG_EXACT_DIV take the exact path per level.
-template <int T, bool SCALE1, bool FORCE_EXACT>
-__device__ __forceinline__ void rdf_walk(const rdf_forest_view& fv, const uint16_t* __restrict__ img, int W, int H, int X,
-                                         int Y, unsigned d, float scale, int (&state)[T]) {
-    const float df = (float)d;
-    const float rcp = __frcp_rn(df);                                 // RN(1/d), once per pixel
-    const float xm = (float)X + RDF_MAGIC_F, ym = (float)Y + RDF_MAGIC_F;   // exact: X, Y < 2^16
-#pragma unroll
-    for (int t = 0; t < T; t++) state[t] = t * fv.nodes_per_tree;
-    for (int j = 0; j < fv.D; j++) {
+// Levels [j0, j1) of T interleaved walks.  SMEM = true: headers come from a shared-memory copy of the upper levels (index =
+// t * stride + row, child ids already rewritten to that indexing, see rdf_stage_upper_levels); else from the packed forest.
+// state[t] >= 0: current node; < 0: ended (~leaf_id or RDF_NO_LEAF).
+template <int T, bool SCALE1, bool FORCE_EXACT, bool SMEM>
+__device__ __forceinline__ void rdf_walk_levels(const rdf_node_hdr* __restrict__ hdr, int tree_stride, int j0, int j1,
+                                                const uint16_t* __restrict__ img, int W, int H, int X, int Y, float df, float rcp,
+                                                float xm, float ym, float scale, int (&state)[T]) {
+    for (int j = j0; j < j1; j++) {
         int all = state[0];
 #pragma unroll
         for (int t = 1; t < T; t++) all &= state[t];
@@ -70,7 +65,14 @@ __device__ __forceinline__ void rdf_walk(const rdf_forest_view& fv, const uint16
 #pragma unroll
         for (int t = 0; t < T; t++) {
             // ended walks re-read their tree's root (cached): harmless, keeps the loop branch-free
-            h[t] = rdf_load_hdr(fv.hdr, max(state[t], t * fv.nodes_per_tree));
+            const int node = max(state[t], t * tree_stride);
+            if (SMEM) {
+                const float4* sp = reinterpret_cast<const float4*>(hdr + node);
+                h[t].a = sp[0];
+                h[t].b = *reinterpret_cast<const int4*>(sp + 1);
+            } else {
+                h[t] = rdf_load_hdr(hdr, node);
+            }
             any_flags |= h[t].b.w;
             if (!SCALE1) {
                 h[t].a.x = __fmul_rn(scale, h[t].a.x);
@@ -95,6 +97,53 @@ __device__ __forceinline__ void rdf_walk(const rdf_forest_view& fv, const uint16
             state[t] = state[t] < 0 ? state[t] : next;
         }
     }
+}
+
+// Upper levels of every tree in shared memory (north_star: "upper tree levels are packed into shared memory"): on those
+// levels most lanes of a warp sit on the same node, and a broadcast pair of 128-bit shared loads costs 2 L1 data-pipe
+// wavefronts where the 256-bit global load costs 8 whatever the addresses (profiles/r01_micro_l1.md).
+// Copies levels 0 .. KS-1 of the T trees to hdr_s[t * M + row], M = 2^KS - 1, rewriting child ids that stay inside the copy
+// (levels < KS-1) to the shared indexing; children of level KS-1 keep their global ids, leaves stay negative.
+// Must be called by all threads of the block, followed by __syncthreads().
+__device__ __forceinline__ void rdf_stage_upper_levels(const rdf_forest_view& fv, int KS, rdf_node_hdr* __restrict__ hdr_s) {
+    const int M = (1 << KS) - 1;
+    const int first_last = (1 << (KS - 1)) - 1;                      // rows >= this are on level KS-1
+    for (int i = threadIdx.x; i < fv.T * M; i += blockDim.x) {
+        const int t = i / M, row = i - t * M;
+        rdf_hdr_regs h = rdf_load_hdr(fv.hdr, t * fv.nodes_per_tree + row);
+        if (row < first_last) {
+            const int shift = t * M - t * fv.nodes_per_tree;
+            if (h.b.y >= 0) h.b.y += shift;
+            if (h.b.z >= 0) h.b.z += shift;
+        }
+        float4* sp = reinterpret_cast<float4*>(hdr_s + i);
+        sp[0] = h.a;
+        *reinterpret_cast<int4*>(sp + 1) = h.b;
+    }
+}
+
+// Walk T trees from their roots.  On return state[t] < 0: ~leaf_id of the reached leaf, or RDF_NO_LEAF if the walk fell
+// off level D-1 with a "continue" flag (adds nothing, src/cuda/tree_eval.cu:95-128).
+// SCALE1: scale == 1.0f, so scale*u == u exactly and the multiplies are dropped.  FORCE_EXACT: always use __fdiv_rn
+// (scale outside the fast domain); otherwise nodes flagged RDF_FLAG_EXACT_DIV take the exact path per level.
+// hdr_s / KS: optional shared-memory copy of levels 0 .. KS-1 (rdf_stage_upper_levels); KS = 0: everything from global memory.
+template <int T, bool SCALE1, bool FORCE_EXACT>
+__device__ __forceinline__ void rdf_walk(const rdf_forest_view& fv, const uint16_t* __restrict__ img, int W, int H, int X,
+                                         int Y, unsigned d, float scale, int (&state)[T], const rdf_node_hdr* hdr_s = nullptr,
+                                         int KS = 0) {
+    const float df = (float)d;
+    const float rcp = __frcp_rn(df);                                 // RN(1/d), once per pixel
+    const float xm = (float)X + RDF_MAGIC_F, ym = (float)Y + RDF_MAGIC_F;   // exact: X, Y < 2^16
+    if (KS > 0) {
+        const int M = (1 << KS) - 1;
+#pragma unroll
+        for (int t = 0; t < T; t++) state[t] = t * M;
+        rdf_walk_levels<T, SCALE1, FORCE_EXACT, true>(hdr_s, M, 0, KS, img, W, H, X, Y, df, rcp, xm, ym, scale, state);
+    } else {
+#pragma unroll
+        for (int t = 0; t < T; t++) state[t] = t * fv.nodes_per_tree;
+    }
+    rdf_walk_levels<T, SCALE1, FORCE_EXACT, false>(fv.hdr, fv.nodes_per_tree, KS, fv.D, img, W, H, X, Y, df, rcp, xm, ym, scale, state);
 #pragma unroll
     for (int t = 0; t < T; t++)
         if (state[t] >= 0) state[t] = RDF_NO_LEAF;                   // D levels done and still on a node (cannot happen
