@@ -239,3 +239,23 @@ def test_golden_fixtures_from_reference_kernels():
         dt.DecisionTreeEvaluator().get_labels(tree, to_dev(depth), out)
         torch.cuda.synchronize()
         assert np.array_equal(to_np(out), want), name
+
+
+@pytest.mark.parametrize('block', range(8))
+def test_fuzz_against_c_oracle(block):
+    """Random tiny forests with NaN / inf / huge / denormal-range offsets and thresholds, non-canonical child flags, zero nodes,
+    1..9 trees (9 = canonical-layout kernel), depth frames full of 0 / 65535, random labels_reduce / scale / filter."""
+    from fuzz_cases import make_case
+    from oracle import c_oracle as co
+    for seed in range(block * 40, block * 40 + 40):
+        c = make_case(seed)
+        N, h, w = c['shape']
+        if h == 0 or w == 0:
+            continue
+        exp = np.full((N, h, w), 4321, np.uint16)
+        exp_p = np.zeros((N, h, w, c['C']), np.float32)
+        co.eval_forest(c['forest'], c['depth'], exp, c['r'], c['filt'], c['fclass'], c['scale'], probs_out=exp_p)
+        got, probs = _run_ours(c['forest'], c['depth'], c['r'], c['filt'], c['fclass'], c['scale'], want_probs=True, prefill=4321)
+        assert np.array_equal(got, exp), f'seed {seed}: {(got != exp).sum()} label(s) differ'
+        written = exp != 4321
+        assert np.allclose(probs[written], exp_p[written], atol=1e-5, rtol=0, equal_nan=True), f'seed {seed}'

@@ -136,3 +136,35 @@ def test_multi_threshold_training_runs_and_is_consistent():
         return [np.concatenate([np.repeat(off, NT, axis=0), th.reshape(-1, 1)], axis=1).astype(np.float32)]
     exp = no.train_tree(depth, labels, C, D, flat)
     _assert_same_tree(ours, exp, 'numpy oracle (flattened proposals)')
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_hist_fuzz_special_values(seed):
+    """Random small cases: offsets with NaN / inf / huge / zero, duplicate and infinite thresholds, NT not a power of two,
+    depth with zeros and 65535, unlabelled pixels, nodes without a slot."""
+    from fuzz_cases import SPECIAL_OFFSETS
+    from rdf_b200 import synth
+    from oracle import c_oracle as co
+    rng = np.random.default_rng(1000 + seed)
+    N, H, W, C = int(rng.integers(1, 4)), int(rng.integers(5, 40)), int(rng.integers(5, 50)), int(rng.integers(2, 7))
+    F, NT, level = int(rng.integers(1, 9)), int(rng.choice([1, 2, 3, 7, 33, 64])), int(rng.integers(0, 4))
+    depth = rng.integers(0, 65536, size=(N, H, W)).astype(np.uint16) if seed % 2 else (1000 + rng.integers(0, 64, size=(N, H, W))).astype(np.uint16)
+    depth[rng.random((N, H, W)) < 0.05] = 0
+    depth[rng.random((N, H, W)) < 0.05] = 65535
+    labels = rng.integers(0, C, size=(N, H, W)).astype(np.uint16)
+    nodes = rng.integers(0, 1 << level, size=(N, H, W)).astype(np.int32)
+    nodes[labels == 0] = -1
+    offsets, thresholds = synth.random_proposals(F, NT, seed=seed)
+    k = rng.random(offsets.shape) < 0.15
+    offsets[k] = SPECIAL_OFFSETS[rng.integers(0, len(SPECIAL_OFFSETS), size=int(k.sum()))]
+    thresholds[rng.random(thresholds.shape) < 0.1] = 0.0                      # duplicates
+    thresholds[:, -1:][rng.random((F, 1)) < 0.3] = np.inf
+    thresholds = np.sort(thresholds, axis=1)
+    node_slot = np.arange(1 << level, dtype=np.int32)
+    if level > 0:
+        node_slot[rng.integers(0, 1 << level)] = -1
+        node_slot[node_slot >= 0] = np.arange((node_slot >= 0).sum(), dtype=np.int32)
+    S = int((node_slot >= 0).sum())
+    got = _hist_ours(depth, labels, nodes, node_slot, S, offsets, thresholds, C)
+    exp = co.train_hist(depth, labels, nodes, node_slot, S, offsets, thresholds, C)
+    assert np.array_equal(got, exp)
