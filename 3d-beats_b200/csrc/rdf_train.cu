@@ -1,6 +1,8 @@
 // Training split search: replaces evaluate_random_features, pick_best_features, get_active_nodes_next_level and
 // copy_pixel_groups (reference src/cuda/tree_train.cu:4-64, :66-236, :238-273, :275-324) plus the host-side root
 // statistics of DecisionTreeTrainer.train (src/decision_tree.py:452-467).
+#include <string.h>
+
 #include "rdf_common.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -315,6 +317,10 @@ struct rdf_histb_params {
     const float* thresholds;     // [F][NT]
     uint32_t* hist;              // [S][F][NB][C]
     int W, H, S, F, NT, NB, C, FC;
+    // feature-sharded reduction fused into the flush (multi-GPU): feature f belongs to rank f / Fo, whose buffer
+    // owner_hist[rank] is laid out [S][Fo][NB][C]; the pointers are peer-mapped (NVLink) device addresses
+    uint32_t* const* owner_hist; // [world] or NULL
+    int Fo;
 };
 
 // ceil(t) for "t <= f" against an integer-valued feature: t <= f  <=>  ceil(t) <= f.  NaN never counts (-> INT_MAX).
@@ -462,12 +468,29 @@ __global__ void __launch_bounds__(TB_THREADS, 1) rdf_train_hist_bucketed_kernel(
         }
         __syncthreads();
         // flush this node's counters and clear them for the next node
-        uint32_t* out = p.hist + ((size_t)slot * p.F + f0) * p.NB * p.C;
-        for (int i = threadIdx.x; i < per_chunk; i += TB_THREADS) {
-            const uint32_t v = hist_s[i];
-            if (v) {
-                atomicAdd(out + i, v);
-                hist_s[i] = 0u;
+        if (p.owner_hist == nullptr) {
+            uint32_t* out = p.hist + ((size_t)slot * p.F + f0) * p.NB * p.C;
+            for (int i = threadIdx.x; i < per_chunk; i += TB_THREADS) {
+                const uint32_t v = hist_s[i];
+                if (v) {
+                    atomicAdd(out + i, v);
+                    hist_s[i] = 0u;
+                }
+            }
+        } else {
+            // reduce-scatter fused into the flush: every counter goes straight to the rank that owns its feature, as a
+            // system-scope reduction over NVLink (no separate collective, and it overlaps the other CTAs' evaluation)
+            const int row = p.NB * p.C;
+            for (int i = threadIdx.x; i < per_chunk; i += TB_THREADS) {
+                const uint32_t v = hist_s[i];
+                if (v) {
+                    const int j = i / row;
+                    const int f = f0 + j;
+                    const int o = f / p.Fo;
+                    uint32_t* dst = p.owner_hist[o] + ((size_t)slot * p.Fo + (f - o * p.Fo)) * row + (i - j * row);
+                    atomicAdd_system(dst, v);
+                    hist_s[i] = 0u;
+                }
             }
         }
         __syncthreads();
@@ -475,11 +498,11 @@ __global__ void __launch_bounds__(TB_THREADS, 1) rdf_train_hist_bucketed_kernel(
     }
 }
 
-extern "C" int rdf_train_hist_bucketed(const uint16_t* depth_dev, const uint16_t* labels_dev, int num_images, int dim_x, int dim_y,
-                                       const void* bucket_workspace_dev, int num_slots, const float* offsets_dev,
-                                       const float* thresholds_dev, int num_features, int num_thresholds, int num_classes,
-                                       uint32_t* hist_dev, void* stream) {
-    RDF_REQUIRE(depth_dev && labels_dev && bucket_workspace_dev && offsets_dev && thresholds_dev && hist_dev,
+static int rdf_hist_bucketed_launch(const uint16_t* depth_dev, const uint16_t* labels_dev, int num_images, int dim_x, int dim_y,
+                                    const void* bucket_workspace_dev, int num_slots, const float* offsets_dev,
+                                    const float* thresholds_dev, int num_features, int num_thresholds, int num_classes,
+                                    uint32_t* hist_dev, uint32_t* const* owner_hist_dev, int world, void* stream) {
+    RDF_REQUIRE(depth_dev && labels_dev && bucket_workspace_dev && offsets_dev && thresholds_dev && (hist_dev || owner_hist_dev),
                 "rdf_train_hist_bucketed: NULL argument");
     RDF_REQUIRE(num_images >= 0 && dim_x > 0 && dim_y > 0 && num_slots >= 1 && num_features >= 1 && num_thresholds >= 1 &&
                     num_classes >= 1 && num_classes <= RDF_MAX_CLASSES,
@@ -497,6 +520,8 @@ extern "C" int rdf_train_hist_bucketed(const uint16_t* depth_dev, const uint16_t
     p.offsets = offsets_dev; p.thresholds = thresholds_dev; p.hist = hist_dev;
     p.W = dim_x; p.H = dim_y; p.S = num_slots; p.F = num_features; p.NT = num_thresholds; p.NB = num_thresholds + 1;
     p.C = num_classes;
+    p.owner_hist = owner_hist_dev;
+    p.Fo = owner_hist_dev ? (num_features + world - 1) / world : num_features;
     int log2ntp = 0;
     while ((1 << log2ntp) < p.NT) log2ntp++;
     RDF_REQUIRE(log2ntp <= 10, "rdf_train_hist_bucketed: at most 1024 thresholds per feature (got %d)", p.NT);
@@ -536,6 +561,24 @@ extern "C" int rdf_train_hist_bucketed(const uint16_t* depth_dev, const uint16_t
     return RDF_OK;
 }
 
+extern "C" int rdf_train_hist_bucketed(const uint16_t* depth_dev, const uint16_t* labels_dev, int num_images, int dim_x, int dim_y,
+                                       const void* bucket_workspace_dev, int num_slots, const float* offsets_dev,
+                                       const float* thresholds_dev, int num_features, int num_thresholds, int num_classes,
+                                       uint32_t* hist_dev, void* stream) {
+    RDF_REQUIRE(hist_dev != nullptr, "rdf_train_hist_bucketed: hist_dev is NULL");
+    return rdf_hist_bucketed_launch(depth_dev, labels_dev, num_images, dim_x, dim_y, bucket_workspace_dev, num_slots, offsets_dev,
+                                    thresholds_dev, num_features, num_thresholds, num_classes, hist_dev, nullptr, 1, stream);
+}
+
+extern "C" int rdf_train_hist_bucketed_p2p(const uint16_t* depth_dev, const uint16_t* labels_dev, int num_images, int dim_x, int dim_y,
+                                           const void* bucket_workspace_dev, int num_slots, const float* offsets_dev,
+                                           const float* thresholds_dev, int num_features, int num_thresholds, int num_classes,
+                                           uint32_t* const* owner_hist_dev, int world, void* stream) {
+    RDF_REQUIRE(owner_hist_dev != nullptr && world >= 1, "rdf_train_hist_bucketed_p2p: bad owner table");
+    return rdf_hist_bucketed_launch(depth_dev, labels_dev, num_images, dim_x, dim_y, bucket_workspace_dev, num_slots, offsets_dev,
+                                    thresholds_dev, num_features, num_thresholds, num_classes, nullptr, owner_hist_dev, world, stream);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // pick best split per active node
 // ---------------------------------------------------------------------------------------------------------------
@@ -566,7 +609,68 @@ struct rdf_pick_params {
     unsigned long long* next_counts;           // [2^D][C] by child node id
     float* best_gain;                          // [num_active]
     int num_active, S, F, NT, NB, C, level, D;
+    // candidates mode (feature-sharded split search): hist holds features f_offset .. f_offset + F - 1 of the global proposal
+    // block; the node's best local candidate is written here instead of being finalised
+    float* cand_gain;                          // [num_active] or NULL
+    int* cand_idx;                             // [num_active] global candidate index (f_offset + f) * NT + k
+    unsigned long long* cand_counts;           // [num_active][2][C] child counts of that candidate
+    int f_offset;
 };
+
+// Writes the node record for the winning candidate (tree_train.cu:170-235).  best_i indexes p.offsets / p.thresholds.
+__device__ __forceinline__ void pb_finalize(const rdf_pick_params& p, int a, int node, float best_g, int best_i,
+                                            const unsigned long long* left, const unsigned long long* right,
+                                            const unsigned long long* par) {
+    const int C = p.C;
+    if (!(best_g > -1.f)) return;                                  // the reference asserts best_g > -1 (tree_train.cu:170)
+    if (best_g <= p.best_gain[a]) return;                          // tree_train.cu:172
+    p.best_gain[a] = best_g;
+    unsigned long long ls = 0, rs = 0, ps = 0;
+    for (int c = 0; c < C; c++) {
+        ls += left[c];
+        rs += right[c];
+        ps += par[c];
+    }
+    const float p_sum_f = __ull2float_rn(ps);
+    const int bf = best_i / p.NT, bk = best_i - bf * p.NT;
+    const int E = 7 + 2 * C;
+    float* out = p.tree + ((((size_t)1 << p.level) - 1) + node) * E;
+    out[0] = p.offsets[4 * bf + 0];                                // tree_train.cu:183-186
+    out[1] = p.offsets[4 * bf + 1];
+    out[2] = p.offsets[4 * bf + 2];
+    out[3] = p.offsets[4 * bf + 3];
+    out[4] = p.thresholds[(size_t)bf * p.NT + bk];
+    if (best_g <= 0.f) {                                           // tree_train.cu:190-198
+        out[5] = 0.f;
+        out[6] = 0.f;
+        for (int c = 0; c < C; c++) {
+            const float v = __fdiv_rn(__ull2float_rn(par[c]), p_sum_f);
+            out[7 + c] = v;
+            out[7 + C + c] = v;
+        }
+        return;
+    }
+    for (int side = 0; side < 2; side++) {                         // tree_train.cu:201-235
+        const unsigned long long* cnt = side ? right : left;
+        const unsigned long long sum = side ? rs : ls;
+        const float sum_f = __ull2float_rn(sum);
+        float* pdf = out + 7 + side * C;
+        int cut = -1;
+        for (int c = 0; c < C; c++)
+            if (__fdiv_rn(__ull2float_rn(cnt[c]), sum_f) >= 0.999f) { cut = c; break; }      // count_above_cutoff (:92-97)
+        if (cut > -1) {
+            out[5 + side] = 0.f;
+            pdf[cut] = 1.f;                                        // other entries keep whatever they held (:204-206)
+        } else if (p.level == p.D - 1) {
+            out[5 + side] = 0.f;
+            for (int c = 0; c < C; c++) pdf[c] = __fdiv_rn(__ull2float_rn(cnt[c]), sum_f);
+        } else {
+            out[5 + side] = -1.f;
+            unsigned long long* nc = p.next_counts + ((size_t)2 * node + side) * C;
+            for (int c = 0; c < C; c++) nc[c] = cnt[c];
+        }
+    }
+}
 
 __device__ __forceinline__ unsigned pb_warp_incl_scan(unsigned v, int lane) {
 #pragma unroll
@@ -697,62 +801,64 @@ __global__ void __launch_bounds__(PB_THREADS) rdf_train_pick_best_kernel(const r
     }
     best_g = red_g[0];
     best_i = red_i[0];
-    if (!(best_g > -1.f)) return;                                  // the reference asserts best_g > -1 (tree_train.cu:170)
-    if (best_g <= p.best_gain[a]) return;                          // tree_train.cu:172
-    p.best_gain[a] = best_g;
-
-    const int bf = best_i / p.NT, bk = best_i - bf * p.NT;
-    const uint32_t* h = p.hist + ((size_t)slot * p.F + bf) * p.NB * C;
-    unsigned long long ls = 0, rs = 0;
-    for (int c = 0; c < C; c++) {
-        unsigned long long l = 0, tot = 0;
-        for (int b = 0; b < p.NB; b++) {
-            const unsigned long long v = h[b * C + c];
-            tot += v;
-            if (b <= bk) l += v;
-        }
-        left[c] = l;
-        right[c] = tot - l;
-        ls += l;
-        rs += tot - l;
-    }
-    const int E = 7 + 2 * C;
-    float* out = p.tree + ((((size_t)1 << p.level) - 1) + node) * E;
-    out[0] = p.offsets[4 * bf + 0];                                // tree_train.cu:183-186
-    out[1] = p.offsets[4 * bf + 1];
-    out[2] = p.offsets[4 * bf + 2];
-    out[3] = p.offsets[4 * bf + 3];
-    out[4] = p.thresholds[(size_t)bf * p.NT + bk];
-    if (best_g <= 0.f) {                                           // tree_train.cu:190-198
-        out[5] = 0.f;
-        out[6] = 0.f;
+    // child counts of the winner, from its histogram row
+    if (best_i != 0x7fffffff) {
+        const int bf = best_i / p.NT, bk = best_i - bf * p.NT;
+        const uint32_t* h = p.hist + ((size_t)slot * p.F + bf) * p.NB * C;
         for (int c = 0; c < C; c++) {
-            const float v = __fdiv_rn(__ull2float_rn(par[c]), p_sum_f);
-            out[7 + c] = v;
-            out[7 + C + c] = v;
+            unsigned long long l = 0, tot = 0;
+            for (int b = 0; b < p.NB; b++) {
+                const unsigned long long v = h[b * C + c];
+                tot += v;
+                if (b <= bk) l += v;
+            }
+            left[c] = l;
+            right[c] = tot - l;
+        }
+    }
+    if (p.cand_gain) {                                             // feature-sharded search: hand the local winner over
+        p.cand_gain[a] = best_g;
+        p.cand_idx[a] = best_i == 0x7fffffff ? best_i : best_i + p.f_offset * p.NT;
+        unsigned long long* cc = p.cand_counts + (size_t)a * 2 * C;
+        for (int c = 0; c < C; c++) {
+            cc[c] = best_i == 0x7fffffff ? 0ull : left[c];
+            cc[C + c] = best_i == 0x7fffffff ? 0ull : right[c];
         }
         return;
     }
-    for (int side = 0; side < 2; side++) {                         // tree_train.cu:201-235
-        const unsigned long long* cnt = side ? right : left;
-        const unsigned long long sum = side ? rs : ls;
-        const float sum_f = __ull2float_rn(sum);
-        float* pdf = out + 7 + side * C;
-        int cut = -1;
-        for (int c = 0; c < C; c++)
-            if (__fdiv_rn(__ull2float_rn(cnt[c]), sum_f) >= 0.999f) { cut = c; break; }      // count_above_cutoff (:92-97)
-        if (cut > -1) {
-            out[5 + side] = 0.f;
-            pdf[cut] = 1.f;                                        // other entries keep whatever they held (:204-206)
-        } else if (p.level == p.D - 1) {
-            out[5 + side] = 0.f;
-            for (int c = 0; c < C; c++) pdf[c] = __fdiv_rn(__ull2float_rn(cnt[c]), sum_f);
-        } else {
-            out[5 + side] = -1.f;
-            unsigned long long* nc = p.next_counts + ((size_t)2 * node + side) * C;
-            for (int c = 0; c < C; c++) nc[c] = cnt[c];
+    pb_finalize(p, a, node, best_g, best_i, left, right, par);
+}
+
+// Feature-sharded split search, second step: every rank holds the gathered local winners of all ranks
+// (gain / idx [world][num_active], counts [world][num_active][2][C]); greatest gain wins, ties -> smallest candidate index,
+// i.e. exactly the candidate a single GPU scanning all features in order would have kept.  One thread per active node.
+struct rdf_pick_final_params {
+    rdf_pick_params base;
+    const float* all_gain;
+    const int* all_idx;
+    const unsigned long long* all_counts;
+    int world;
+};
+
+__global__ void __launch_bounds__(128) rdf_train_pick_finalize_kernel(const rdf_pick_final_params q) {
+    const rdf_pick_params& p = q.base;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= p.num_active) return;
+    const int node = p.active_nodes[a];
+    if (p.node_slot[node] < 0) return;
+    float best_g = -1.f;
+    int best_i = 0x7fffffff, best_r = 0;
+    for (int r = 0; r < q.world; r++) {
+        const float g = q.all_gain[(size_t)r * p.num_active + a];
+        const int i = q.all_idx[(size_t)r * p.num_active + a];
+        if (g > best_g || (g == best_g && i < best_i)) {
+            best_g = g;
+            best_i = i;
+            best_r = r;
         }
     }
+    const unsigned long long* cc = q.all_counts + ((size_t)best_r * p.num_active + a) * 2 * p.C;
+    pb_finalize(p, a, node, best_g, best_i, cc, cc + p.C, p.parent_counts + (size_t)node * p.C);
 }
 
 extern "C" int rdf_train_pick_best(int num_active, const int32_t* active_nodes_dev, const int32_t* node_slot_dev,
@@ -775,6 +881,7 @@ extern "C" int rdf_train_pick_best(int num_active, const int32_t* active_nodes_d
     p.best_gain = best_gain_dev;
     p.num_active = num_active; p.S = num_slots; p.F = num_features; p.NT = num_thresholds; p.NB = num_thresholds + 1;
     p.C = num_classes; p.level = level; p.D = max_depth;
+    p.cand_gain = nullptr; p.cand_idx = nullptr; p.cand_counts = nullptr; p.f_offset = 0;
     const size_t smem = sizeof(unsigned long long) * 3 * (size_t)num_classes + sizeof(unsigned) * (size_t)PB_WARPS * 2 * num_classes;
     static size_t smem_set = 0;
     if (smem > 48 * 1024 && smem > smem_set) {
@@ -784,6 +891,61 @@ extern "C" int rdf_train_pick_best(int num_active, const int32_t* active_nodes_d
     RDF_REQUIRE(smem <= 220 * 1024, "rdf_train_pick_best: %d classes exceed the shared-memory scratch", num_classes);
     rdf_train_pick_best_kernel<<<num_active, PB_THREADS, smem, rdf_stream(stream)>>>(p);
     RDF_LAUNCH_CHECK("rdf_train_pick_best_kernel");
+    return RDF_OK;
+}
+
+extern "C" int rdf_train_pick_candidates(int num_active, const int32_t* active_nodes_dev, const int32_t* node_slot_dev,
+                                         const uint64_t* parent_counts_dev, const uint32_t* hist_local_dev, int num_slots,
+                                         int num_local_features, int feature_offset, int num_thresholds, int num_classes,
+                                         float* cand_gain_dev, int32_t* cand_idx_dev, uint64_t* cand_counts_dev, void* stream) {
+    RDF_REQUIRE(active_nodes_dev && node_slot_dev && parent_counts_dev && hist_local_dev && cand_gain_dev && cand_idx_dev && cand_counts_dev,
+                "rdf_train_pick_candidates: NULL argument");
+    RDF_REQUIRE(num_active >= 0 && num_slots >= 1 && num_local_features >= 0 && feature_offset >= 0 && num_thresholds >= 1 &&
+                    num_classes >= 1 && num_classes <= RDF_MAX_CLASSES,
+                "rdf_train_pick_candidates: bad argument");
+    if (num_active == 0) return RDF_OK;
+    rdf_pick_params p;
+    memset(&p, 0, sizeof(p));
+    p.active_nodes = active_nodes_dev; p.node_slot = node_slot_dev;
+    p.parent_counts = reinterpret_cast<const unsigned long long*>(parent_counts_dev);
+    p.hist = hist_local_dev;
+    p.num_active = num_active; p.S = num_slots; p.F = num_local_features; p.NT = num_thresholds; p.NB = num_thresholds + 1;
+    p.C = num_classes;
+    p.cand_gain = cand_gain_dev; p.cand_idx = cand_idx_dev;
+    p.cand_counts = reinterpret_cast<unsigned long long*>(cand_counts_dev);
+    p.f_offset = feature_offset;
+    const size_t smem = sizeof(unsigned long long) * 3 * (size_t)num_classes + sizeof(unsigned) * (size_t)PB_WARPS * 2 * num_classes;
+    rdf_train_pick_best_kernel<<<num_active, PB_THREADS, smem, rdf_stream(stream)>>>(p);
+    RDF_LAUNCH_CHECK("rdf_train_pick_best_kernel (candidates)");
+    return RDF_OK;
+}
+
+extern "C" int rdf_train_pick_finalize(int num_active, const int32_t* active_nodes_dev, const int32_t* node_slot_dev,
+                                       const uint64_t* parent_counts_dev, int world, const float* all_gain_dev,
+                                       const int32_t* all_idx_dev, const uint64_t* all_counts_dev, const float* offsets_dev,
+                                       const float* thresholds_dev, int num_thresholds, int num_classes, int level, int max_depth,
+                                       float* tree_dev, uint64_t* next_counts_dev, float* best_gain_dev, void* stream) {
+    RDF_REQUIRE(active_nodes_dev && node_slot_dev && parent_counts_dev && all_gain_dev && all_idx_dev && all_counts_dev && offsets_dev &&
+                    thresholds_dev && tree_dev && next_counts_dev && best_gain_dev,
+                "rdf_train_pick_finalize: NULL argument");
+    RDF_REQUIRE(num_active >= 0 && world >= 1 && num_thresholds >= 1 && num_classes >= 1 && num_classes <= RDF_MAX_CLASSES &&
+                    level >= 0 && level < max_depth && max_depth <= RDF_MAX_DEPTH,
+                "rdf_train_pick_finalize: bad argument");
+    if (num_active == 0) return RDF_OK;
+    rdf_pick_final_params q;
+    memset(&q, 0, sizeof(q));
+    q.base.active_nodes = active_nodes_dev; q.base.node_slot = node_slot_dev;
+    q.base.parent_counts = reinterpret_cast<const unsigned long long*>(parent_counts_dev);
+    q.base.offsets = offsets_dev; q.base.thresholds = thresholds_dev; q.base.tree = tree_dev;
+    q.base.next_counts = reinterpret_cast<unsigned long long*>(next_counts_dev);
+    q.base.best_gain = best_gain_dev;
+    q.base.num_active = num_active; q.base.NT = num_thresholds; q.base.NB = num_thresholds + 1; q.base.C = num_classes;
+    q.base.level = level; q.base.D = max_depth;
+    q.all_gain = all_gain_dev; q.all_idx = all_idx_dev;
+    q.all_counts = reinterpret_cast<const unsigned long long*>(all_counts_dev);
+    q.world = world;
+    rdf_train_pick_finalize_kernel<<<(num_active + 127) / 128, 128, 0, rdf_stream(stream)>>>(q);
+    RDF_LAUNCH_CHECK("rdf_train_pick_finalize_kernel");
     return RDF_OK;
 }
 

@@ -47,6 +47,12 @@ SIGNATURES = {
     'rdf_train_bucket': [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_size_t, c_void_p],
     'rdf_train_hist_bucketed': [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                 c_void_p, c_void_p],
+    'rdf_train_hist_bucketed_p2p': [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                                    c_void_p, c_int, c_void_p],
+    'rdf_train_pick_candidates': [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_void_p],
+    'rdf_train_pick_finalize': [c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     'rdf_train_pick_best': [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                             c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     'rdf_train_next_active': [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p],

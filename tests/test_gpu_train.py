@@ -168,3 +168,75 @@ def test_hist_fuzz_special_values(seed):
     got = _hist_ours(depth, labels, nodes, node_slot, S, offsets, thresholds, C)
     exp = co.train_hist(depth, labels, nodes, node_slot, S, offsets, thresholds, C)
     assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize('world,F,level', [(2, 24, 3), (3, 20, 0), (4, 37, 5)])
+def test_feature_sharded_search_equals_single_gpu(world, F, level):
+    """The multi-GPU scheme on ONE GPU: `world` owner buffers stand in for the ranks' peer-mapped buffers.  The fused
+    reduce-scatter flush must leave in owner r's buffer exactly the feature slice r of the plain histogram, and
+    pick-candidates per slice + pick-finalize must write the same node records as the single pick-best."""
+    import torch
+    from rdf_b200 import _capi, synth
+    lib = _capi.load()
+    N, H, W, C, NT, D = 3, 96, 128, 4, 16, 8
+    depth = synth.depth_frames('dense-smooth', N, H, W, seed=2)
+    labels = synth.train_labels(N, H, W)
+    labels[1, 40:50, :] = 0
+    nodes = synth.random_node_assignment(labels, level, seed=5)
+    S = 1 << level
+    offsets, thresholds = synth.random_proposals(F, NT, seed=9)
+    d, l, nd = to_dev(depth), to_dev(labels), to_dev(nodes)
+    slot = torch.arange(S, dtype=torch.int32, device='cuda')
+    od, td = to_dev(offsets), to_dev(thresholds)
+    need = ctypes.c_size_t()
+    _capi.check(lib.rdf_train_bucket_workspace_bytes(N * H * W, S, ctypes.byref(need)))
+    ws = torch.zeros(((need.value + 3) // 4,), dtype=torch.int32, device='cuda')
+    st = _capi.stream_ptr
+    _capi.check(lib.rdf_train_bucket(_capi.dptr(nd), N * H * W, _capi.dptr(slot), S, _capi.dptr(ws), need.value, st()))
+    full = torch.zeros((S, F, NT + 1, C), dtype=torch.int32, device='cuda')
+    _capi.check(lib.rdf_train_hist_bucketed(_capi.dptr(d), _capi.dptr(l), N, W, H, _capi.dptr(ws), S, _capi.dptr(od), _capi.dptr(td),
+                                            F, NT, C, _capi.dptr(full), st()))
+    Fo = (F + world - 1) // world
+    owners = [torch.zeros((S, Fo, NT + 1, C), dtype=torch.int32, device='cuda') for _ in range(world)]
+    table = torch.tensor([o.data_ptr() for o in owners], dtype=torch.int64, device='cuda')
+    _capi.check(lib.rdf_train_hist_bucketed_p2p(_capi.dptr(d), _capi.dptr(l), N, W, H, _capi.dptr(ws), S, _capi.dptr(od), _capi.dptr(td),
+                                                F, NT, C, _capi.dptr(table), world, st()))
+    torch.cuda.synchronize()
+    for r, o in enumerate(owners):
+        f0, f1 = r * Fo, min(F, (r + 1) * Fo)
+        assert torch.equal(o[:, :f1 - f0], full[:, f0:f1]), f'owner {r}'
+        assert int(o[:, f1 - f0:].abs().sum()) == 0
+
+    # split selection: single kernel vs candidates per slice + finalize
+    active = torch.arange(S, dtype=torch.int32, device='cuda')
+    parent = torch.zeros((1 << D, C), dtype=torch.int64, device='cuda')
+    parent.view(-1).index_add_(0, (nd.view(-1).long() * C + l.view(torch.int16).view(-1).long())[nd.view(-1) >= 0],
+                               torch.ones(int((nd.view(-1) >= 0).sum()), dtype=torch.int64, device='cuda'))
+    E = 7 + 2 * C
+
+    def fresh():
+        return (torch.zeros(((1 << D) - 1, E), dtype=torch.float32, device='cuda'), torch.zeros_like(parent),
+                torch.full((1 << D,), -1.0, dtype=torch.float32, device='cuda'))
+    tree1, next1, gain1 = fresh()
+    _capi.check(lib.rdf_train_pick_best(S, _capi.dptr(active), _capi.dptr(slot), _capi.dptr(parent), _capi.dptr(full), S, _capi.dptr(od),
+                                        _capi.dptr(td), F, NT, C, level, D, _capi.dptr(tree1), _capi.dptr(next1), _capi.dptr(gain1), st()))
+    tree2, next2, gain2 = fresh()
+    all_gain = torch.zeros((world, S), dtype=torch.float32, device='cuda')
+    all_idx = torch.zeros((world, S), dtype=torch.int32, device='cuda')
+    all_cnt = torch.zeros((world, S, 2, C), dtype=torch.int64, device='cuda')
+    for r, o in enumerate(owners):
+        nloc = max(0, min(F, (r + 1) * Fo) - r * Fo)
+        _capi.check(lib.rdf_train_pick_candidates(S, _capi.dptr(active), _capi.dptr(slot), _capi.dptr(parent), _capi.dptr(o), S, nloc,
+                                                  r * Fo, NT, C, _capi.dptr(all_gain[r]), _capi.dptr(all_idx[r]), _capi.dptr(all_cnt[r]), st())
+                    if nloc == Fo else
+                    lib.rdf_train_pick_candidates(S, _capi.dptr(active), _capi.dptr(slot), _capi.dptr(parent),
+                                                  _capi.dptr(o[:, :nloc].contiguous()), S, nloc, r * Fo, NT, C, _capi.dptr(all_gain[r]),
+                                                  _capi.dptr(all_idx[r]), _capi.dptr(all_cnt[r]), st()))
+    _capi.check(lib.rdf_train_pick_finalize(S, _capi.dptr(active), _capi.dptr(slot), _capi.dptr(parent), world, _capi.dptr(all_gain),
+                                            _capi.dptr(all_idx), _capi.dptr(all_cnt), _capi.dptr(od), _capi.dptr(td), NT, C, level, D,
+                                            _capi.dptr(tree2), _capi.dptr(next2), _capi.dptr(gain2), st()))
+    torch.cuda.synchronize()
+    # bitwise (nodes without pixels get NaN pdfs from 0/0 in both paths, as in the reference)
+    assert torch.equal(tree1.view(torch.int32), tree2.view(torch.int32)) and torch.equal(next1, next2)
+    assert torch.equal(gain1.view(torch.int32), gain2.view(torch.int32))
+    assert bool((tree1[:, 5:7] == -1).any())
