@@ -615,6 +615,7 @@ struct rdf_pick_params {
     int* cand_idx;                             // [num_active] global candidate index (f_offset + f) * NT + k
     unsigned long long* cand_counts;           // [num_active][2][C] child counts of that candidate
     int f_offset;
+    int f_stride;                              // features per slot in hist's layout (>= F)
 };
 
 // Writes the node record for the winning candidate (tree_train.cu:170-235).  best_i indexes p.offsets / p.thresholds.
@@ -724,7 +725,7 @@ __global__ void __launch_bounds__(PB_THREADS) rdf_train_pick_best_kernel(const r
     float best_g = -1.f;
     int best_i = 0x7fffffff;
     for (int f = warp; f < p.F; f += PB_WARPS) {
-        const uint32_t* h = p.hist + ((size_t)slot * p.F + f) * p.NB * C;
+        const uint32_t* h = p.hist + ((size_t)slot * p.f_stride + f) * p.NB * C;
         // class totals over all NT + 1 bins
         unsigned T = 0;
         for (int c = 0; c < C; c++) {
@@ -804,7 +805,7 @@ __global__ void __launch_bounds__(PB_THREADS) rdf_train_pick_best_kernel(const r
     // child counts of the winner, from its histogram row
     if (best_i != 0x7fffffff) {
         const int bf = best_i / p.NT, bk = best_i - bf * p.NT;
-        const uint32_t* h = p.hist + ((size_t)slot * p.F + bf) * p.NB * C;
+        const uint32_t* h = p.hist + ((size_t)slot * p.f_stride + bf) * p.NB * C;
         for (int c = 0; c < C; c++) {
             unsigned long long l = 0, tot = 0;
             for (int b = 0; b < p.NB; b++) {
@@ -881,7 +882,7 @@ extern "C" int rdf_train_pick_best(int num_active, const int32_t* active_nodes_d
     p.best_gain = best_gain_dev;
     p.num_active = num_active; p.S = num_slots; p.F = num_features; p.NT = num_thresholds; p.NB = num_thresholds + 1;
     p.C = num_classes; p.level = level; p.D = max_depth;
-    p.cand_gain = nullptr; p.cand_idx = nullptr; p.cand_counts = nullptr; p.f_offset = 0;
+    p.cand_gain = nullptr; p.cand_idx = nullptr; p.cand_counts = nullptr; p.f_offset = 0; p.f_stride = num_features;
     const size_t smem = sizeof(unsigned long long) * 3 * (size_t)num_classes + sizeof(unsigned) * (size_t)PB_WARPS * 2 * num_classes;
     static size_t smem_set = 0;
     if (smem > 48 * 1024 && smem > smem_set) {
@@ -896,12 +897,13 @@ extern "C" int rdf_train_pick_best(int num_active, const int32_t* active_nodes_d
 
 extern "C" int rdf_train_pick_candidates(int num_active, const int32_t* active_nodes_dev, const int32_t* node_slot_dev,
                                          const uint64_t* parent_counts_dev, const uint32_t* hist_local_dev, int num_slots,
-                                         int num_local_features, int feature_offset, int num_thresholds, int num_classes,
-                                         float* cand_gain_dev, int32_t* cand_idx_dev, uint64_t* cand_counts_dev, void* stream) {
+                                         int num_local_features, int feature_stride, int feature_offset, int num_thresholds,
+                                         int num_classes, float* cand_gain_dev, int32_t* cand_idx_dev, uint64_t* cand_counts_dev,
+                                         void* stream) {
     RDF_REQUIRE(active_nodes_dev && node_slot_dev && parent_counts_dev && hist_local_dev && cand_gain_dev && cand_idx_dev && cand_counts_dev,
                 "rdf_train_pick_candidates: NULL argument");
-    RDF_REQUIRE(num_active >= 0 && num_slots >= 1 && num_local_features >= 0 && feature_offset >= 0 && num_thresholds >= 1 &&
-                    num_classes >= 1 && num_classes <= RDF_MAX_CLASSES,
+    RDF_REQUIRE(num_active >= 0 && num_slots >= 1 && num_local_features >= 0 && feature_stride >= num_local_features &&
+                    feature_offset >= 0 && num_thresholds >= 1 && num_classes >= 1 && num_classes <= RDF_MAX_CLASSES,
                 "rdf_train_pick_candidates: bad argument");
     if (num_active == 0) return RDF_OK;
     rdf_pick_params p;
@@ -914,6 +916,7 @@ extern "C" int rdf_train_pick_candidates(int num_active, const int32_t* active_n
     p.cand_gain = cand_gain_dev; p.cand_idx = cand_idx_dev;
     p.cand_counts = reinterpret_cast<unsigned long long*>(cand_counts_dev);
     p.f_offset = feature_offset;
+    p.f_stride = feature_stride;
     const size_t smem = sizeof(unsigned long long) * 3 * (size_t)num_classes + sizeof(unsigned) * (size_t)PB_WARPS * 2 * num_classes;
     rdf_train_pick_best_kernel<<<num_active, PB_THREADS, smem, rdf_stream(stream)>>>(p);
     RDF_LAUNCH_CHECK("rdf_train_pick_best_kernel (candidates)");

@@ -49,8 +49,8 @@ SIGNATURES = {
                                 c_void_p, c_void_p],
     'rdf_train_hist_bucketed_p2p': [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                     c_void_p, c_int, c_void_p],
-    'rdf_train_pick_candidates': [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
-                                  c_void_p, c_void_p],
+    'rdf_train_pick_candidates': [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                  c_void_p, c_void_p, c_void_p],
     'rdf_train_pick_finalize': [c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                 c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     'rdf_train_pick_best': [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,

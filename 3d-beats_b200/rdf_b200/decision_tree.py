@@ -431,7 +431,12 @@ class DecisionTreeTrainer():
     """
 
     def __init__(self, NUM_IMAGES_PER_IMAGE_BLOCK, NUM_PROPOSALS_PER_PROPOSAL_BLOCK, thresholds_per_feature=1,
-                 proposal_fn=None, process_group=None, hist_budget_bytes=8 << 30):
+                 proposal_fn=None, process_group=None, hist_budget_bytes=8 << 30, exchange=None):
+        """exchange (multi-GPU only): 'p2p' = the reduction is fused into the histogram kernel (every counter is flushed over
+        NVLink into the peer-mapped buffer of the rank owning its feature, then each rank scores its feature slice and the
+        small per-node winners are all-gathered); 'allreduce' = NCCL sum-allreduce of the whole histogram, then every rank
+        scores everything.  Default: 'p2p' when torch symmetric memory can be set up, else 'allreduce' (env RDF_TRAIN_EXCHANGE)."""
+        self.exchange = exchange or os.environ.get('RDF_TRAIN_EXCHANGE')
         self._lib = _capi.load()
         self.NUM_IMAGES_PER_IMAGE_BLOCK = NUM_IMAGES_PER_IMAGE_BLOCK
         self.NUM_PROPOSALS_PER_PROPOSAL_BLOCK = NUM_PROPOSALS_PER_PROPOSAL_BLOCK
@@ -474,6 +479,35 @@ class DecisionTreeTrainer():
         _capi.check(self._lib.rdf_train_bucket_workspace_bytes(int(np.prod(dataset.images_shape())), self.MAX_SLOTS_PER_BLOCK,
                                                                ctypes.byref(need)))
         self.bucket_ws = GPUArray(((need.value + 3) // 4,), dtype=np.int32)
+        self._p2p = None
+        dist = self._dist()
+        if dist is not None and self.exchange != 'allreduce':
+            try:
+                self._setup_p2p(dist, P, NT, C)
+            except Exception as e:                               # no symmetric memory on this system: NCCL allreduce instead
+                if self.exchange == 'p2p':
+                    raise
+                self._p2p = None
+                self._p2p_error = repr(e)
+
+    def _setup_p2p(self, dist, P, NT, C):
+        """Peer-mapped histogram buffers through torch symmetric memory (PyTorch is only the plumbing: allocation, handle
+        exchange and the device-side barrier; the reduction itself is rdf_train_hist_bucketed_p2p)."""
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self.process_group if self.process_group is not None else dist.group.WORLD
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        Fo = (P + world - 1) // world
+        n = self.MAX_SLOTS_PER_BLOCK * Fo * (NT + 1) * C
+        buf = symm_mem.empty(n, dtype=torch.int32, device=torch.device('cuda', torch.cuda.current_device()))
+        hdl = symm_mem.rendezvous(buf, group)
+        ptrs = torch.tensor([int(x) for x in hdl.buffer_ptrs], dtype=torch.int64, device=buf.device)
+        L = self.MAX_LEAF_NODES
+        self._p2p = {
+            'group': group, 'world': world, 'rank': rank, 'Fo': Fo, 'buf': buf, 'hdl': hdl, 'ptrs': ptrs,
+            'cand_gain': torch.zeros((L,), dtype=torch.float32, device=buf.device),
+            'cand_idx': torch.zeros((L,), dtype=torch.int32, device=buf.device),
+            'cand_cnt': torch.zeros((L, 2, C), dtype=torch.int64, device=buf.device),
+        }
 
     # -- proposal stream -------------------------------------------------------------------------------------
     def _next_proposals(self, level, block):
@@ -502,6 +536,35 @@ class DecisionTreeTrainer():
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1:
             return dist
         return None
+
+    def _level_block_p2p(self, lib, st, depth, labels, N, W, H, S, P, NT, C, num_active, level, D, tree):
+        """One (proposal block, node block) with the feature-sharded exchange (include/rdf_b200.h)."""
+        import torch.distributed as dist
+        q = self._p2p
+        world, rank, Fo = q['world'], q['rank'], q['Fo']
+        local = q['buf'][:S * Fo * (NT + 1) * C]
+        local.zero_()
+        q['hdl'].barrier(channel=0)                                   # every owner buffer is zero before anyone pushes
+        _capi.check(lib.rdf_train_hist_bucketed_p2p(_capi.dptr(depth), _capi.dptr(labels), N, W, H, _capi.dptr(self.bucket_ws), S,
+                                                    _capi.dptr(self.current_offsets), _capi.dptr(self.current_thresholds), P, NT, C,
+                                                    _capi.dptr(q['ptrs']), world, st()))
+        q['hdl'].barrier(channel=0)                                   # all ranks' reductions have landed in my slice
+        nloc = max(0, min(P, (rank + 1) * Fo) - rank * Fo)
+        cg, ci, cc = q['cand_gain'][:num_active], q['cand_idx'][:num_active], q['cand_cnt'][:num_active]
+        _capi.check(lib.rdf_train_pick_candidates(num_active, _capi.dptr(self.active_nodes_cu), _capi.dptr(self.node_slot_cu),
+                                                  _capi.dptr(self.node_counts_cu), _capi.dptr(local), S, nloc, Fo, rank * Fo, NT, C,
+                                                  _capi.dptr(cg), _capi.dptr(ci), _capi.dptr(cc), st()))
+        ag = torch.empty((world, num_active), dtype=torch.float32, device=cg.device)
+        ai = torch.empty((world, num_active), dtype=torch.int32, device=cg.device)
+        ac = torch.empty((world, num_active, 2, C), dtype=torch.int64, device=cg.device)
+        dist.all_gather_into_tensor(ag, cg, group=q['group'])
+        dist.all_gather_into_tensor(ai, ci, group=q['group'])
+        dist.all_gather_into_tensor(ac, cc, group=q['group'])
+        _capi.check(lib.rdf_train_pick_finalize(num_active, _capi.dptr(self.active_nodes_cu), _capi.dptr(self.node_slot_cu),
+                                                _capi.dptr(self.node_counts_cu), world, _capi.dptr(ag), _capi.dptr(ai), _capi.dptr(ac),
+                                                _capi.dptr(self.current_offsets), _capi.dptr(self.current_thresholds), NT, C, level, D,
+                                                _capi.dptr(tree.tree_out_cu), _capi.dptr(self.next_node_counts_cu),
+                                                _capi.dptr(self.best_gain_seen_per_node), st()))
 
     def train(self, dataset, tree):
         lib, st = self._lib, _capi.stream_ptr
@@ -549,6 +612,9 @@ class DecisionTreeTrainer():
                         self.node_slot_cu[:num_nodes_level].set(slot_host)
                         _capi.check(lib.rdf_train_bucket(_capi.dptr(self.nodes_by_pixel), N * H * W, _capi.dptr(self.node_slot_cu), S,
                                                          _capi.dptr(self.bucket_ws), self.bucket_ws.nbytes, st()))
+                    if self._p2p is not None:
+                        self._level_block_p2p(lib, st, depth, labels, N, W, H, S, P, NT, C, num_active_nodes, current_level, D, tree)
+                        continue
                     hist = self.hist_cu[:S]
                     hist.fill(0)
                     _capi.check(lib.rdf_train_hist_bucketed(_capi.dptr(depth), _capi.dptr(labels), N, W, H, _capi.dptr(self.bucket_ws), S,

@@ -182,7 +182,8 @@ RDF_API int rdf_train_hist_bucketed(const uint16_t* depth_dev, const uint16_t* l
  * its owner, all ranks synchronised before and after the launch).  Every rank runs rdf_train_hist_bucketed_p2p on its own
  * pixels; counters are flushed as system-scope reductions straight into the owner's buffer, so after a barrier rank r holds
  * the FULL histogram of its feature slice - a reduce-scatter without a separate collective.  rdf_train_pick_candidates then
- * scores the local slice (feature_offset = r * Fo) and writes, per active node, the best local (gain, global candidate
+ * scores the local slice (hist_local_dev laid out [num_slots][feature_stride][NT+1][C], the first num_local_features of each
+ * slot valid, feature_offset = r * Fo) and writes, per active node, the best local (gain, global candidate
  * index, child counts); after an all-gather of those small records rdf_train_pick_finalize picks the global winner
  * (greatest gain, ties -> smallest index: what one GPU scanning all features in order keeps) and writes the node record. */
 RDF_API int rdf_train_hist_bucketed_p2p(const uint16_t* depth_dev, const uint16_t* labels_dev, int num_images, int dim_x, int dim_y,
@@ -191,8 +192,9 @@ RDF_API int rdf_train_hist_bucketed_p2p(const uint16_t* depth_dev, const uint16_
                                 uint32_t* const* owner_hist_dev, int world, void* stream);
 RDF_API int rdf_train_pick_candidates(int num_active, const int32_t* active_nodes_dev, const int32_t* node_slot_dev,
                               const uint64_t* parent_counts_dev, const uint32_t* hist_local_dev, int num_slots,
-                              int num_local_features, int feature_offset, int num_thresholds, int num_classes,
-                              float* cand_gain_dev, int32_t* cand_idx_dev, uint64_t* cand_counts_dev, void* stream);
+                              int num_local_features, int feature_stride, int feature_offset, int num_thresholds,
+                              int num_classes, float* cand_gain_dev, int32_t* cand_idx_dev, uint64_t* cand_counts_dev,
+                              void* stream);
 RDF_API int rdf_train_pick_finalize(int num_active, const int32_t* active_nodes_dev, const int32_t* node_slot_dev,
                             const uint64_t* parent_counts_dev, int world, const float* all_gain_dev,
                             const int32_t* all_idx_dev, const uint64_t* all_counts_dev, const float* offsets_dev,

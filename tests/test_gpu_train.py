@@ -226,12 +226,8 @@ def test_feature_sharded_search_equals_single_gpu(world, F, level):
     all_cnt = torch.zeros((world, S, 2, C), dtype=torch.int64, device='cuda')
     for r, o in enumerate(owners):
         nloc = max(0, min(F, (r + 1) * Fo) - r * Fo)
-        _capi.check(lib.rdf_train_pick_candidates(S, _capi.dptr(active), _capi.dptr(slot), _capi.dptr(parent), _capi.dptr(o), S, nloc,
-                                                  r * Fo, NT, C, _capi.dptr(all_gain[r]), _capi.dptr(all_idx[r]), _capi.dptr(all_cnt[r]), st())
-                    if nloc == Fo else
-                    lib.rdf_train_pick_candidates(S, _capi.dptr(active), _capi.dptr(slot), _capi.dptr(parent),
-                                                  _capi.dptr(o[:, :nloc].contiguous()), S, nloc, r * Fo, NT, C, _capi.dptr(all_gain[r]),
-                                                  _capi.dptr(all_idx[r]), _capi.dptr(all_cnt[r]), st()))
+        _capi.check(lib.rdf_train_pick_candidates(S, _capi.dptr(active), _capi.dptr(slot), _capi.dptr(parent), _capi.dptr(o), S, nloc, Fo,
+                                                  r * Fo, NT, C, _capi.dptr(all_gain[r]), _capi.dptr(all_idx[r]), _capi.dptr(all_cnt[r]), st()))
     _capi.check(lib.rdf_train_pick_finalize(S, _capi.dptr(active), _capi.dptr(slot), _capi.dptr(parent), world, _capi.dptr(all_gain),
                                             _capi.dptr(all_idx), _capi.dptr(all_cnt), _capi.dptr(od), _capi.dptr(td), NT, C, level, D,
                                             _capi.dptr(tree2), _capi.dptr(next2), _capi.dptr(gain2), st()))

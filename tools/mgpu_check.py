@@ -2,8 +2,9 @@
 """Multi-GPU parity check, run under torchrun (one rank per GPU, NCCL):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/mgpu_check.py
   1. frame-sharded forest eval: every rank evaluates its shard; the gathered label maps equal rank 0's single-GPU result;
-  2. image-sharded training with NCCL sum-allreduce of the split histograms: every rank ends with the tree a single GPU
-     trains on the whole dataset (bit-identical canonical array).
+  2. image-sharded training, both exchange modes (reduction fused into the histogram kernel over peer-mapped buffers, and
+     NCCL sum-allreduce of the split histograms): every rank ends with the tree a single GPU trains on the whole dataset
+     (bit-identical canonical array).
 Prints one JSON line on rank 0."""
 import json
 import os
@@ -56,31 +57,39 @@ def main():
     Nt, Ht, Wt, Dt, F, NT = 4 * world, 64, 96, 6, 32, 8
     props = {lvl: synth.random_proposals(F, NT, seed=100 + lvl) for lvl in range(Dt)}
 
-    def train(n0, n1, group_world):
+    modes = {}
+
+    def train(n0, n1, group_world, exchange=None):
         d = synth.depth_frames('dense-smooth', n1 - n0, Ht, Wt, seed=9, first_frame=n0)
         l = synth.train_labels(n1 - n0, Ht, Wt, first_frame=n0)
         ds = dt.DecisionTreeDatasetConfig.from_arrays(d, l, C)
         tr = dt.DecisionTreeTrainer(n1 - n0, F, thresholds_per_feature=NT, proposal_fn=lambda lvl, b: props[lvl],
-                                    process_group=None if group_world > 1 else False)
+                                    process_group=None if group_world > 1 else False, exchange=exchange)
         tr.allocate(ds, F, Dt)
+        if group_world > 1:
+            modes[str(exchange)] = 'p2p (reduction fused into the histogram kernel)' if tr._p2p is not None else 'nccl allreduce ' + getattr(tr, '_p2p_error', '')
         tree = dt.DecisionTree(Dt, C)
         tr.train(ds, tree)
         torch.cuda.synchronize()
         return tree.tree_out_cu.get()
 
     i0, i1 = rdist.shard_range(Nt, rank, world)
-    sharded = train(i0, i1, world)
+    results = {}
+    for exchange in ((None, 'allreduce') if world > 1 else (None,)):
+        sharded = train(i0, i1, world, exchange)
+        trees = [None] * world
+        if world > 1:
+            dist.all_gather_object(trees, sharded.tobytes())
+        else:
+            trees = [sharded.tobytes()]
+        results[exchange] = trees
     train_ok = True
-    trees = [None] * world
-    if world > 1:
-        dist.all_gather_object(trees, sharded.tobytes())
-    else:
-        trees = [sharded.tobytes()]
     if rank == 0:
         single = train(0, Nt, 1)
-        train_ok = all(t == single.tobytes() for t in trees) and bool((single[:, 5:7] == -1).any())
+        train_ok = all(t == single.tobytes() for trees in results.values() for t in trees) and bool((single[:, 5:7] == -1).any())
         print(json.dumps({'world': world, 'eval_shards_match_single_gpu': eval_ok, 'sharded_training_matches_single_gpu': train_ok,
-                          'frames': N, 'train_images': Nt}), flush=True)
+                          'exchange_modes_tested': modes, 'frames': N,
+                          'train_images': Nt}), flush=True)
     rdist.barrier()
     if world > 1:
         dist.destroy_process_group()
