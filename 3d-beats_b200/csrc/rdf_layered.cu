@@ -137,6 +137,9 @@ __global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_co
     // let a dependent grid (the mean shift that follows in the live pipeline) be scheduled now; it waits for this grid's
     // completion itself (griddepcontrol.wait) before reading the label images
     asm volatile("griddepcontrol.launch_dependents;");
+    // ... and this grid may itself have been scheduled early behind the kernel that produces the depth frame
+    // (rdf_upload_frame in the live pipeline): nothing of the frame is read before that kernel has completed
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     __shared__ int leaf_s[RL2_MAX_WALKS][32];
     __shared__ unsigned short lab_s[RDF_MAX_LAYERS][32];
     const int lane = threadIdx.x, walk = threadIdx.y;
@@ -304,13 +307,22 @@ extern "C" int rdf_layered_run(const rdf_forest_t* const* forests, int num_layer
         }
         const int nb = q.base.tiles_x * ((p.h + 3) / 4);
         dim3 block(32, num_walks, 1);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(nb, 1, 1);
+        cfg.blockDim = block;
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = rdf_stream(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see griddepcontrol.wait in the kernel
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = getenv("RDF_NO_PDL") ? 0 : 1;
         if (!fast)
-            rdf_layered_walks_kernel<false, true><<<nb, block, 0, rdf_stream(stream)>>>(q);
+            RDF_CUDA(cudaLaunchKernelEx(&cfg, rdf_layered_walks_kernel<false, true>, q));
         else if (scale == 1.f)
-            rdf_layered_walks_kernel<true, false><<<nb, block, 0, rdf_stream(stream)>>>(q);
+            RDF_CUDA(cudaLaunchKernelEx(&cfg, rdf_layered_walks_kernel<true, false>, q));
         else
-            rdf_layered_walks_kernel<false, false><<<nb, block, 0, rdf_stream(stream)>>>(q);
-        RDF_LAUNCH_CHECK("rdf_layered_walks_kernel");
+            RDF_CUDA(cudaLaunchKernelEx(&cfg, rdf_layered_walks_kernel<false, false>, q));
         return RDF_OK;
     }
     const int nblk = p.tiles_x * tiles_y;
@@ -321,5 +333,35 @@ extern "C" int rdf_layered_run(const rdf_forest_t* const* forests, int num_layer
     else
         rdf_layered_kernel<8, false, false><<<nblk, 256, 0, rdf_stream(stream)>>>(p);
     RDF_LAUNCH_CHECK("rdf_layered_kernel");
+    return RDF_OK;
+}
+
+// ---- frame upload as a kernel ------------------------------------------------------------------------------------------
+// Replaces the host-to-device copy of the live frame (depth_image.cu().set(np), src/3d_bz.py:156-157, src/run_live.py:80) inside
+// a per-frame CUDA graph: the SMs read the frame from pinned host memory (zero-copy over PCIe, one 16-byte load per thread,
+// everything in flight at once) and write it to HBM.  As a kernel it can be chained to the layered forest with programmatic
+// dependent launch, which a copy-engine node cannot (the copy -> kernel edge of the graph cost ~4 us).
+__global__ void __launch_bounds__(256) rdf_upload_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n16,
+                                                         const unsigned char* __restrict__ src_tail, unsigned char* __restrict__ dst_tail,
+                                                         int tail) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = src[i];
+    if (blockIdx.x == 0 && (int)threadIdx.x < tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
+}
+
+extern "C" int rdf_upload_frame(const void* host_pinned, void* dev, size_t bytes, void* stream) {
+    RDF_REQUIRE(host_pinned && dev, "rdf_upload_frame: NULL argument");
+    RDF_REQUIRE(((uintptr_t)host_pinned & 15u) == 0 && ((uintptr_t)dev & 15u) == 0, "rdf_upload_frame: buffers must be 16-byte aligned");
+    if (bytes == 0) return RDF_OK;
+    const size_t n16 = bytes / 16;
+    const int tail = (int)(bytes - n16 * 16);
+    size_t blocks = (n16 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    rdf_upload_kernel<<<(unsigned)blocks, 256, 0, rdf_stream(stream)>>>(
+        reinterpret_cast<const uint4*>(host_pinned), reinterpret_cast<uint4*>(dev), n16,
+        reinterpret_cast<const unsigned char*>(host_pinned) + n16 * 16, reinterpret_cast<unsigned char*>(dev) + n16 * 16, tail);
+    RDF_LAUNCH_CHECK("rdf_upload_kernel");
     return RDF_OK;
 }

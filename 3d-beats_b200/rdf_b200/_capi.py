@@ -34,6 +34,7 @@ SIGNATURES = {
     'rdf_composite': [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     'rdf_layered_run': [ctypes.POINTER(c_void_p), c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_void_p, c_int, c_int,
                         ctypes.POINTER(c_void_p), c_void_p, c_int, c_void_p, c_int, c_float, c_void_p],
+    'rdf_upload_frame': [c_void_p, c_void_p, c_size_t, c_void_p],
     'rdf_mean_shift_workspace_bytes': [c_int, c_int, c_int, ctypes.POINTER(c_size_t)],
     'rdf_mean_shift': [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p],
     'rdf_group_hands': [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p],

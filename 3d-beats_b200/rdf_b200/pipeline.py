@@ -77,7 +77,8 @@ class LiveFramePipeline:
     """One frame in, fingertip centroids out.  All device work of a frame is one CUDA-graph replay."""
 
     def __init__(self, layered_forest, num_rounds, variances, scale_factor=1., use_graph=True, upload=True, zero_copy_out=True):
-        """upload=False: the frame is already in `depth_dev` (device-resident producer, e.g. a pre-processing kernel);
+        """upload: True = upload kernel reading the pinned frame (default), 'copy' = copy-engine H2D node, False = the frame is
+        already in `depth_dev` (device-resident producer, e.g. a pre-processing kernel);
         zero_copy_out: the mean-shift kernel writes the K x 2 centroids straight into pinned host memory."""
         self.upload = upload
         self.zero_copy_out = zero_copy_out
@@ -109,8 +110,13 @@ class LiveFramePipeline:
                 self._enqueue()
 
     def _enqueue(self):
-        if self.upload:
+        if self.upload == 'copy':
             self.depth_dev.cu().tensor.view(torch.int16).copy_(self.depth_host.view(torch.int16), non_blocking=True)
+        elif self.upload:
+            # upload kernel (zero-copy read of the pinned frame): chains to the layered kernel by programmatic dependent launch
+            import ctypes
+            _capi.check(_capi.load().rdf_upload_frame(ctypes.c_void_p(self.depth_host.data_ptr()), _capi.dptr(self.depth_dev.cu()),
+                                                      self.depth_host.numel() * 2, _capi.stream_ptr()))
         self.ldf.run(self.depth_dev, self.labels_dev, self.scale)
         if self.zero_copy_out:
             self.ms.run_async(self.rounds, self.labels_dev.cu(), self.K, self.variances, means_out=self.means_host)

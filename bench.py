@@ -166,8 +166,10 @@ def latency_cfg2(iters=1000, warm=100):
     """BASELINE configs[1]: one 848x480 live-mask frame through the 2-layer stacked forest (hand/background -> 10 finger
     parts, labels_reduce 2) + 6-round mean shift.  Two variants, each ONE CUDA-graph replay per frame, timed as host wall
     time (perf_counter around replay + stream sync) and as device time (CUDA events on the pipeline's stream):
-      e2e       frame in pinned host memory -> H2D copy -> layered kernel -> mean-shift kernel writing the centroids straight
-                into pinned host memory (the call a user of run_live_layered.py / 3d_bz.py makes per frame)
+      e2e       frame in pinned host memory -> upload kernel (zero-copy read over PCIe) -> layered kernel -> mean-shift kernel
+                writing the centroids straight into pinned host memory, the three kernels chained by programmatic dependent
+                launch (the call a user of run_live_layered.py / 3d_bz.py makes per frame); also measured with a copy-engine
+                H2D node instead of the upload kernel
       resident  frame already in HBM (what the product has after its own pre-processing kernels, src/3d_bz.py:394-420):
                 layered kernel -> mean-shift kernel -> centroids in pinned host memory."""
     import torch
@@ -217,8 +219,10 @@ def latency_cfg2(iters=1000, warm=100):
                        'p50_us_with_event_records': pc(wall, 50), 'device_p50_us': pc(devt, 50), 'device_p99_us': pc(devt, 99),
                        'h2d_bytes': pipe.h2d_bytes, 'd2h_bytes': pipe.d2h_bytes}
 
-    pipe = LiveFramePipeline(ldf, 6, variances, scale_factor=1.0)
+    pipe = LiveFramePipeline(ldf, 6, variances, scale_factor=1.0)              # upload kernel -> layered -> mean shift (PDL chain)
     means, e2e = measure(pipe)
+    pipe_copy = LiveFramePipeline(ldf, 6, variances, scale_factor=1.0, upload='copy')   # copy-engine H2D node instead
+    means_copy, e2e_copy = measure(pipe_copy)
     pipe_res = LiveFramePipeline(ldf, 6, variances, scale_factor=1.0, upload=False)
     means_res, resident = measure(pipe_res)
     # parity of exactly what was timed: centroids vs the NumPy oracle on the oracle's own composite map
@@ -226,7 +230,14 @@ def latency_cfg2(iters=1000, warm=100):
     exp_means = no.mean_shift(exp_comp, ldf.num_layered_classes, variances, 6)
     comp_ok = bool(np.array_equal(pipe.labels_dev.cu().get()[0], exp_comp))
     means_ok = bool(np.array_equal(np.isnan(means), np.isnan(exp_means)) and np.nanmax(np.abs(means - exp_means)) <= 1e-5 and
-                    np.array_equal(np.nan_to_num(means), np.nan_to_num(means_res)))
+                    np.array_equal(np.nan_to_num(means), np.nan_to_num(means_res)) and
+                    np.array_equal(np.nan_to_num(means), np.nan_to_num(means_copy)))
+
+    def _upload(pp):
+        import ctypes
+        from rdf_b200 import _capi
+        _capi.check(_capi.load().rdf_upload_frame(ctypes.c_void_p(pp.depth_host.data_ptr()), _capi.dptr(pp.depth_dev.cu()),
+                                                  pp.depth_host.numel() * 2, _capi.stream_ptr()))
 
     # per-stage device time: each stage captured alone as its own CUDA graph and replayed back to back
     def stage(fn, n=300):
@@ -247,7 +258,8 @@ def latency_cfg2(iters=1000, warm=100):
         pipe.stream.synchronize()
         return a.elapsed_time(b) * 1e3 / n
     stages = {
-        'h2d_frame_us': stage(lambda: pipe.depth_dev.cu().tensor.view(torch.int16).copy_(pipe.depth_host.view(torch.int16), non_blocking=True)),
+        'h2d_copy_engine_us': stage(lambda: pipe.depth_dev.cu().tensor.view(torch.int16).copy_(pipe.depth_host.view(torch.int16), non_blocking=True)),
+        'h2d_upload_kernel_us': stage(lambda: _upload(pipe)),
         'layered_kernel_us': stage(lambda: pipe.ldf.run(pipe.depth_dev, pipe.labels_dev, pipe.scale)),
         'mean_shift_kernel_us': stage(lambda: pipe.ms.run_async(pipe.rounds, pipe.labels_dev.cu(), pipe.K, pipe.variances, means_out=pipe.means_host)),
         'note': 'each stage replayed alone as a 1-node CUDA graph, back to back; includes per-graph launch latency',
@@ -256,7 +268,8 @@ def latency_cfg2(iters=1000, warm=100):
         'workload': 'cfg2: one 848x480 live-mask frame, L1 (T3 D16 C3) -> L2 (T3 D16 C11, gated by L1==1), labels_reduce 2, '
                     'mean shift 6 rounds over 11 classes; one CUDA-graph replay per frame',
         'p50_us': e2e['p50_us'], 'p95_us': e2e['p95_us'], 'p99_us': e2e['p99_us'], 'device_p50_us': e2e['device_p50_us'],
-        'e2e_host_frame': e2e, 'resident_frame': resident, 'iters': iters, 'evaluated_pixels': valid_px,
+        'e2e_host_frame': e2e, 'e2e_host_frame_copy_engine': e2e_copy, 'resident_frame': resident, 'iters': iters,
+        'evaluated_pixels': valid_px,
         'labelled_classes': int(np.isfinite(means[:, 0]).sum()), 'kernels_per_frame': 2,
         'parity': {'composite_bit_exact_vs_oracle': comp_ok, 'centroids_within_1e-5': means_ok}, 'stages': stages,
     }

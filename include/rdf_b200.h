@@ -112,6 +112,11 @@ RDF_API int rdf_layered_run(const rdf_forest_t* const* forests, int num_layers, 
                     uint16_t* const* labels_per_layer, const int32_t* conditions_dev, int n_cond,
                     uint16_t* composite_dev, int labels_reduce, float scale, void* stream);
 
+/* rdf_upload_frame: the live frame's host-to-device copy (depth_image.cu().set(np), src/3d_bz.py:156-157) as a kernel that
+ * reads PINNED, device-mapped host memory and writes device memory; both 16-byte aligned.  In a per-frame CUDA graph it chains
+ * to rdf_layered_run by programmatic dependent launch. */
+RDF_API int rdf_upload_frame(const void* host_pinned, void* dev, size_t bytes, void* stream);
+
 /* ---- mean shift -----------------------------------------------------------------------------------------
  * rdf_mean_shift replaces MeanShift.run (src/cuda/mean_shift.py:19-59): per round 1 fill + kernel `run`
  * (src/cuda/mean_shift.cu:3-48) + 2 blocking D2H + host divide + H2D, all `rounds` rounds in ONE launch with no
