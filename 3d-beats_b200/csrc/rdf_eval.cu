@@ -16,6 +16,7 @@ struct rdf_eval_params {
     int filter_class;
     int image0;
     int smem_levels;          // upper tree levels staged in shared memory (0 .. RDF_EVAL_SMEM_LEVELS)
+    int tree_mode;            // evaluate_image_using_tree semantics: no write when the walk reaches no leaf (tree_eval.cu:174-210)
     float scale;
 };
 
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(256, RDF_EVAL_MIN_BLOCKS) rdf_eval_packed_kern
     if (d == 0u || d == RDF_NO_PIXEL) return;                                            // tree_eval.cu:88-89
     int state[T];
     rdf_walk<T, SCALE1, FORCE_EXACT>(p.fv, img, p.W, p.H, X, Y, d, p.scale, state, hdr_s, KS);
+    if (T == 1 && p.tree_mode && state[0] == RDF_NO_LEAF) return;
     const int lab = rdf_vote<T>(p.fv, state, p.probs ? p.probs + li * p.fv.C : nullptr);
     p.labels[li] = (uint16_t)lab;
 }
@@ -168,9 +170,9 @@ static void rdf_launch_packed_t(const rdf_eval_params& p, dim3 grid, cudaStream_
     }
 }
 
-extern "C" int rdf_eval_forest(const rdf_forest_t* forest, const uint16_t* depth_dev, int num_images, int dim_x, int dim_y,
-                               const uint16_t* filter_dev, int filter_class, uint16_t* labels_dev, float* probs_dev,
-                               int labels_reduce, float scale, void* stream) {
+static int rdf_eval_packed(const rdf_forest_t* forest, const uint16_t* depth_dev, int num_images, int dim_x, int dim_y,
+                           const uint16_t* filter_dev, int filter_class, uint16_t* labels_dev, float* probs_dev,
+                           int labels_reduce, float scale, int tree_mode, void* stream) {
     RDF_REQUIRE(forest && depth_dev && labels_dev, "rdf_eval_forest: NULL argument");
     RDF_REQUIRE(num_images >= 0 && dim_x > 0 && dim_y > 0 && labels_reduce >= 1, "rdf_eval_forest: bad shape N=%d W=%d H=%d r=%d",
                 num_images, dim_x, dim_y, labels_reduce);
@@ -195,6 +197,7 @@ extern "C" int rdf_eval_forest(const rdf_forest_t* forest, const uint16_t* depth
     const int tiles_y = (h + 7) / 8;
     p.filter_class = filter_class;
     p.scale = scale;
+    p.tree_mode = tree_mode;
     {
         static int lv = -1;                                         // RDF_SMEM_LEVELS overrides (experiments)
         if (lv < 0) {
@@ -221,6 +224,20 @@ extern "C" int rdf_eval_forest(const rdf_forest_t* forest, const uint16_t* depth
         RDF_LAUNCH_CHECK("rdf_eval_packed_kernel");
     }
     return RDF_OK;
+}
+
+extern "C" int rdf_eval_forest(const rdf_forest_t* forest, const uint16_t* depth_dev, int num_images, int dim_x, int dim_y,
+                               const uint16_t* filter_dev, int filter_class, uint16_t* labels_dev, float* probs_dev,
+                               int labels_reduce, float scale, void* stream) {
+    return rdf_eval_packed(forest, depth_dev, num_images, dim_x, dim_y, filter_dev, filter_class, labels_dev, probs_dev, labels_reduce,
+                           scale, 0, stream);
+}
+
+// evaluate_image_using_tree over a packed one-tree handle (the fast path; rdf_eval_tree reads the canonical array)
+extern "C" int rdf_eval_tree_packed(const rdf_forest_t* tree, const uint16_t* depth_dev, int num_images, int dim_x, int dim_y,
+                                    uint16_t* labels_dev, void* stream) {
+    RDF_REQUIRE(tree != nullptr && tree->T == 1, "rdf_eval_tree_packed: the handle must hold exactly one tree");
+    return rdf_eval_packed(tree, depth_dev, num_images, dim_x, dim_y, nullptr, -1, labels_dev, nullptr, 1, 1.f, 1, stream);
 }
 
 // Same contract as rdf_eval_forest but reads the canonical array directly (no handle, any tree count).

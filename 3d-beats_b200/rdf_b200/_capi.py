@@ -31,6 +31,7 @@ SIGNATURES = {
     'rdf_eval_forest_canonical': [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                                   c_void_p, c_int, c_float, c_void_p],
     'rdf_eval_tree': [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    'rdf_eval_tree_packed': [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     'rdf_composite': [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     'rdf_layered_run': [ctypes.POINTER(c_void_p), c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_void_p, c_int, c_int,
                         ctypes.POINTER(c_void_p), c_void_p, c_int, c_void_p, c_int, c_float, c_void_p],

@@ -52,6 +52,35 @@ class DecisionTree():
         self.TOTAL_TREE_NODES, self.MAX_LEAF_NODES, self.TREE_NODE_ELS = DecisionTree.get_config(max_depth, num_classes)
         self.tree_out_cu = GPUArray((self.TOTAL_TREE_NODES, self.TREE_NODE_ELS), dtype=np.float32)
         self.tree_out_cu.fill(np.float32(0.))
+        self._handle = None
+        self._packed_version = None
+
+    def handle(self):
+        """Packed one-tree shadow of tree_out_cu (re-packed when tree_out_cu was written), for the fast evaluation path."""
+        lib = _capi.load()
+        ver = _version_of(self.tree_out_cu)
+        if self._handle is None:
+            h = ctypes.c_void_p()
+            _capi.check(lib.rdf_forest_create(_capi.dptr(self.tree_out_cu), 1, self.max_depth, self.num_classes, _capi.stream_ptr(),
+                                              ctypes.byref(h)))
+            self._handle = h
+        elif ver != self._packed_version:
+            _capi.check(lib.rdf_forest_update(self._handle, _capi.dptr(self.tree_out_cu), _capi.stream_ptr()))
+        self._packed_version = ver
+        return self._handle
+
+    def invalidate(self):
+        """Force a re-pack on next use: needed when tree_out_cu was written by something torch does not see (the training
+        kernels of librdf_b200 write it through raw pointers)."""
+        self._packed_version = None
+
+    def __del__(self):
+        if getattr(self, '_handle', None) is not None:
+            try:
+                _capi.load().rdf_forest_destroy(self._handle)
+            except Exception:
+                pass
+            self._handle = None
 
     @staticmethod
     def get_config(max_depth, num_classes):
@@ -129,9 +158,14 @@ class DecisionTreeEvaluator():
         num_images, dim_y, dim_x = depth_images_in.shape
         assert labels_out.shape == (num_images, dim_y, dim_x)
         assert depth_images_in.dtype == np.uint16 and labels_out.dtype == np.uint16
-        _capi.check(self._lib.rdf_eval_tree(_capi.dptr(tree.tree_out_cu), tree.max_depth, tree.num_classes,
-                                            _capi.dptr(depth_images_in), num_images, dim_x, dim_y, _capi.dptr(labels_out),
-                                            _capi.stream_ptr()))
+        if hasattr(tree, 'handle'):
+            tree.invalidate()           # the trainer writes tree_out_cu through raw pointers: always re-pack (60 -> 64 B per node)
+            _capi.check(self._lib.rdf_eval_tree_packed(tree.handle(), _capi.dptr(depth_images_in), num_images, dim_x, dim_y,
+                                                       _capi.dptr(labels_out), _capi.stream_ptr()))
+        else:
+            _capi.check(self._lib.rdf_eval_tree(_capi.dptr(tree.tree_out_cu), tree.max_depth, tree.num_classes,
+                                                _capi.dptr(depth_images_in), num_images, dim_x, dim_y, _capi.dptr(labels_out),
+                                                _capi.stream_ptr()))
 
     def get_labels_forest(self, forest, depth_images_in, labels_out, labels_reduce=1, filter_images=None,
                           filter_images_class=None, scale_factor=1., probs_out=None):

@@ -94,6 +94,11 @@ RDF_API int rdf_eval_forest_canonical(const float* forest_dev, int num_trees, in
 RDF_API int rdf_eval_tree(const float* tree_dev, int max_depth, int num_classes, const uint16_t* depth_dev, int num_images,
                   int dim_x, int dim_y, uint16_t* labels_dev, void* stream);
 
+/* Same result as rdf_eval_tree through a packed one-tree handle (rdf_forest_create(tree_dev, 1, D, C, ...)): the fast path
+ * DecisionTreeEvaluator.get_labels uses for the per-tree evaluation of train_model.py (src/train_model.py:104-105). */
+RDF_API int rdf_eval_tree_packed(const rdf_forest_t* tree, const uint16_t* depth_dev, int num_images, int dim_x, int dim_y,
+                         uint16_t* labels_dev, void* stream);
+
 /* rdf_composite replaces kernel `make_composite_labels_image` (src/cuda/tree_eval.cu:214-248) and its wrapper
  * (src/decision_tree.py:333-347).  label_images_dev: DEVICE array of L device pointers (the reference's int64
  * pointer table, src/decision_tree.py:203-207); conditions_dev int32[n_cond,2]; composite_dev uint16[dim_y,dim_x]. */

@@ -259,3 +259,30 @@ def test_fuzz_against_c_oracle(block):
         assert np.array_equal(got, exp), f'seed {seed}: {(got != exp).sum()} label(s) differ'
         written = exp != 4321
         assert np.allclose(probs[written], exp_p[written], atol=1e-5, rtol=0, equal_nan=True), f'seed {seed}'
+
+
+def test_single_tree_packed_and_canonical_paths_agree():
+    """get_labels runs the packed one-tree path (rdf_eval_tree_packed); rdf_eval_tree (canonical array) must agree, including
+    'no write when no leaf is reached', and so must both with the C oracle."""
+    import torch
+    from rdf_b200 import _capi, synth
+    from rdf_b200 import decision_tree as dt
+    from oracle import c_oracle as co
+    for ragged, kill_leaves in ((True, False), (False, True)):
+        depth = synth.depth_frames('dense-noise', 2, 60, 80, seed=3)
+        tree_np = synth.random_forest(1, 8, 5, seed=11, ragged=ragged)[0]
+        if kill_leaves:
+            tree_np[191:, 5:7] = -1.0                                  # half of the last level (rows 127..254) never reaches a leaf
+        tree = dt.DecisionTree(8, 5)
+        tree.tree_out_cu.set(tree_np)
+        a = filled_u16((2, 60, 80), 4242)
+        dt.DecisionTreeEvaluator().get_labels(tree, to_dev(depth), a)
+        b = filled_u16((2, 60, 80), 4242)
+        _capi.check(_capi.load().rdf_eval_tree(_capi.dptr(tree.tree_out_cu), 8, 5, _capi.dptr(to_dev(depth)), 2, 80, 60, _capi.dptr(b),
+                                               _capi.stream_ptr()))
+        torch.cuda.synchronize()
+        exp = np.full((2, 60, 80), 4242, np.uint16)
+        co.eval_tree(tree_np, depth, exp)
+        assert np.array_equal(to_np(a), exp) and np.array_equal(to_np(b), exp)
+        if kill_leaves:
+            assert (exp == 4242).any() and (exp != 4242).any()
