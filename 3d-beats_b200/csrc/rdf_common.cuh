@@ -236,3 +236,21 @@ static inline bool rdf_scale_fastfloor_ok(float s) {
 }
 
 static inline cudaStream_t rdf_stream(void* s) { return (cudaStream_t)s; }
+
+// Opt-in dynamic shared memory above 48 KB is a PER-DEVICE function attribute: remember what was set on each device so that a
+// process driving several GPUs (or switching devices) gets it on all of them.
+#define RDF_MAX_DEVICES 64
+static inline int rdf_current_device() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= RDF_MAX_DEVICES) d = 0;
+    return d;
+}
+#define RDF_ENSURE_DYN_SMEM(func, bytes)                                                                              \
+    do {                                                                                                              \
+        static size_t set__[RDF_MAX_DEVICES];                                                                         \
+        const int d__ = rdf_current_device();                                                                         \
+        if ((size_t)(bytes) > set__[d__]) {                                                                           \
+            RDF_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));          \
+            set__[d__] = (size_t)(bytes);                                                                             \
+        }                                                                                                             \
+    } while (0)

@@ -125,12 +125,7 @@ __global__ void __launch_bounds__(128) rdf_eval_canon_kernel(const rdf_eval_cano
 static int rdf_launch_canon(const rdf_eval_canon_params& p, cudaStream_t stream) {
     const int threads = 128;
     const size_t smem = (size_t)p.C * threads * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        RDF_CUDA(cudaFuncSetAttribute(rdf_eval_canon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      RDF_MAX_CLASSES * threads * (int)sizeof(float)));
-        attr_set = true;
-    }
+    RDF_ENSURE_DYN_SMEM(rdf_eval_canon_kernel, RDF_MAX_CLASSES * threads * sizeof(float));
     const int64_t blocks = (p.num_pixels + threads - 1) / threads;
     RDF_REQUIRE(blocks <= 0x7fffffffLL, "too many pixels for one launch: %lld", (long long)p.num_pixels);
     rdf_eval_canon_kernel<<<(unsigned)blocks, threads, smem, stream>>>(p);
@@ -174,6 +169,8 @@ static int rdf_eval_packed(const rdf_forest_t* forest, const uint16_t* depth_dev
                            const uint16_t* filter_dev, int filter_class, uint16_t* labels_dev, float* probs_dev,
                            int labels_reduce, float scale, int tree_mode, void* stream) {
     RDF_REQUIRE(forest && depth_dev && labels_dev, "rdf_eval_forest: NULL argument");
+    RDF_REQUIRE(forest->device == rdf_current_device(), "rdf_eval_forest: the forest was packed on device %d, current device is %d",
+                forest->device, rdf_current_device());
     RDF_REQUIRE(num_images >= 0 && dim_x > 0 && dim_y > 0 && labels_reduce >= 1, "rdf_eval_forest: bad shape N=%d W=%d H=%d r=%d",
                 num_images, dim_x, dim_y, labels_reduce);
     RDF_REQUIRE((int64_t)dim_x * dim_y < ((int64_t)1 << 31), "rdf_eval_forest: image of %dx%d pixels is too large", dim_x, dim_y);

@@ -162,11 +162,7 @@ extern "C" int rdf_group_hands(const uint16_t* img_dev, int dim_x, int dim_y, fl
         return RDF_ERR_UNSUPPORTED;
     }
     const size_t smem = sizeof(int) * 3 * (size_t)n;
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        RDF_CUDA(cudaFuncSetAttribute(rdf_group_hands_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * 3 * GR_MAX_PIXELS)));
-        smem_set = sizeof(int) * 3 * GR_MAX_PIXELS;
-    }
+    if (smem > 48 * 1024) RDF_ENSURE_DYN_SMEM(rdf_group_hands_kernel, sizeof(int) * 3 * GR_MAX_PIXELS);
     rdf_group_hands_kernel<<<1, GR_THREADS, smem, rdf_stream(stream)>>>(img_dev, dim_x, dim_y, pct_thresh, stencil_dev, g_info_dev);
     RDF_LAUNCH_CHECK("rdf_group_hands_kernel");
     return RDF_OK;

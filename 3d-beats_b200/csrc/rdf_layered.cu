@@ -266,6 +266,8 @@ extern "C" int rdf_layered_run(const rdf_forest_t* const* forests, int num_layer
     memset(&p, 0, sizeof(p));
     for (int i = 0; i < num_layers; i++) {
         RDF_REQUIRE(forests[i] != nullptr && labels_per_layer[i] != nullptr, "rdf_layered_run: layer %d is NULL", i);
+        RDF_REQUIRE(forests[i]->device == rdf_current_device(), "rdf_layered_run: layer %d was packed on device %d, current device is %d",
+                    i, forests[i]->device, rdf_current_device());
         if (forests[i]->T > RDF_FAST_MAX_TREES) {
             rdf_set_error("rdf_layered_run: layer %d has %d trees (max %d in the fused path)", i, forests[i]->T, RDF_FAST_MAX_TREES);
             return RDF_ERR_UNSUPPORTED;

@@ -553,7 +553,8 @@ extern "C" int rdf_mean_shift(const uint16_t* labels_dev, int dim_x, int dim_y, 
         !getenv("RDF_MS_V1")) {
         // cluster size: 16 CTAs (non-portable size, opt-in) when the device can co-schedule such a cluster with the kernel's
         // full shared-memory footprint, else the portable 8.  RDF_MS_CLUSTER overrides (experiments).
-        static int nc_cap = 0;
+        static int nc_cap_dev[RDF_MAX_DEVICES];                       // per device: function attributes are per device
+        int& nc_cap = nc_cap_dev[rdf_current_device()];
         if (!nc_cap) {
             const char* e = getenv("RDF_MS_CLUSTER");
             int want = e ? atoi(e) : MS2_MAX_CLUSTER;
@@ -586,11 +587,7 @@ extern "C" int rdf_mean_shift(const uint16_t* labels_dev, int dim_x, int dim_y, 
         q.chunk = ((ngroups + NC - 1) / NC) * 8;                  // entries a CTA may hold (its share of 8-pixel groups)
         q.trace = getenv("RDF_MS_TRACE") ? reinterpret_cast<unsigned long long*>(workspace_dev) : nullptr;
         const size_t smem2 = ms2_smem_bytes(num_labels, NC, q.chunk);
-        static size_t smem2_set = 0;
-        if (smem2 > smem2_set) {
-            RDF_CUDA(cudaFuncSetAttribute(rdf_mean_shift_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            smem2_set = smem2;
-        }
+        RDF_ENSURE_DYN_SMEM(rdf_mean_shift_v2_kernel, smem2);
         cudaLaunchConfig_t cfg2 = {};
         cfg2.gridDim = dim3(NC, 1, 1);
         cfg2.blockDim = dim3(MS2_THREADS, 1, 1);
@@ -625,11 +622,7 @@ extern "C" int rdf_mean_shift(const uint16_t* labels_dev, int dim_x, int dim_y, 
     p.item = item;
 
     const size_t smem = ms_smem_bytes(num_labels, NC);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        RDF_CUDA(cudaFuncSetAttribute(rdf_mean_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
+    RDF_ENSURE_DYN_SMEM(rdf_mean_shift_kernel, smem);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(NC, 1, 1);
     cfg.blockDim = dim3(MS_THREADS, 1, 1);

@@ -168,11 +168,7 @@ extern "C" int rdf_train_hist(const uint16_t* depth_dev, const uint16_t* labels_
     }
     p.FC = fc;
     const size_t smem = per_feature_static * fc + (p.privatise ? per_feature_hist * fc : 0);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        RDF_CUDA(cudaFuncSetAttribute(rdf_train_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget + 1024));
-        smem_set = smem_budget + 1024;
-    }
+    RDF_ENSURE_DYN_SMEM(rdf_train_hist_kernel, smem_budget + 1024);
     const int64_t tiles = (p.num_pixels + TH_PIX - 1) / TH_PIX;
     const int chunks = (p.F + fc - 1) / fc;
     RDF_REQUIRE(tiles <= 0x7fffffffLL && chunks <= 65535, "rdf_train_hist: grid too large (%lld tiles, %d feature chunks)",
@@ -543,14 +539,9 @@ static int rdf_hist_bucketed_launch(const uint16_t* depth_dev, const uint16_t* l
     const int chunks2 = (p.F + fc - 1) / fc;
     RDF_REQUIRE(chunks2 <= 65535, "rdf_train_hist_bucketed: too many feature chunks (%d)", chunks2);
     const dim3 grid((unsigned)tiles, (unsigned)chunks2);
-    static bool attr_set[11] = {false};
 #define TB_CASE(L)                                                                                                      \
     case L:                                                                                                             \
-        if (!attr_set[L]) {                                                                                             \
-            RDF_CUDA(cudaFuncSetAttribute(rdf_train_hist_bucketed_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          (int)smem_budget + 4096));                                                   \
-            attr_set[L] = true;                                                                                         \
-        }                                                                                                               \
+        RDF_ENSURE_DYN_SMEM(rdf_train_hist_bucketed_kernel<L>, smem_budget + 4096);                                    \
         rdf_train_hist_bucketed_kernel<L><<<grid, TB_THREADS, smem, rdf_stream(stream)>>>(p);                           \
         break;
     switch (log2ntp) {
@@ -884,11 +875,7 @@ extern "C" int rdf_train_pick_best(int num_active, const int32_t* active_nodes_d
     p.C = num_classes; p.level = level; p.D = max_depth;
     p.cand_gain = nullptr; p.cand_idx = nullptr; p.cand_counts = nullptr; p.f_offset = 0; p.f_stride = num_features;
     const size_t smem = sizeof(unsigned long long) * 3 * (size_t)num_classes + sizeof(unsigned) * (size_t)PB_WARPS * 2 * num_classes;
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        RDF_CUDA(cudaFuncSetAttribute(rdf_train_pick_best_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
+    if (smem > 48 * 1024) RDF_ENSURE_DYN_SMEM(rdf_train_pick_best_kernel, smem);
     RDF_REQUIRE(smem <= 220 * 1024, "rdf_train_pick_best: %d classes exceed the shared-memory scratch", num_classes);
     rdf_train_pick_best_kernel<<<num_active, PB_THREADS, smem, rdf_stream(stream)>>>(p);
     RDF_LAUNCH_CHECK("rdf_train_pick_best_kernel");
