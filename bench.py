@@ -101,22 +101,30 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def host_cores():
+    """Host threads this process may use (torchrun exports OMP_NUM_THREADS=1, so OpenMP's default is not it)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_oracle_rate(T, D, C, W, H, kind, budget_s=12.0, max_frames=64, seed=1234):
     """C oracle (oracle/rdf_oracle.c) on all host threads over a bounded sample of the workload's frames."""
     from rdf_b200 import synth
     from oracle import c_oracle as co
     forest = synth.hash_forest(T, D, C, seed=seed)
-    cores = co.num_threads()
+    cores = host_cores()
     depth1 = synth.depth_frames(kind, 1, H, W, seed=seed)
     lab1 = np.full((1, H, W), 65535, np.uint16)
     t0 = time.perf_counter()
-    co.eval_forest(forest, depth1, lab1)
+    co.eval_forest(forest, depth1, lab1, nthreads=cores)
     t1 = time.perf_counter() - t0
     frames = int(max(1, min(max_frames, budget_s / max(t1, 1e-6))))
     depth = synth.depth_frames(kind, frames, H, W, seed=seed)
     labels = np.full((frames, H, W), 65535, np.uint16)
     t0 = time.perf_counter()
-    co.eval_forest(forest, depth, labels)
+    co.eval_forest(forest, depth, labels, nthreads=cores)
     dt = time.perf_counter() - t0
     return {'value': frames * H * W / dt / 1e6, 'unit': 'Mpixels/s', 'cores': cores, 'kind': 'port',
             'sample': f'{frames} of the workload\'s {W}x{H} frames, same forest, C oracle with OpenMP on {cores} threads, {dt:.1f} s'}, forest
@@ -133,15 +141,15 @@ def run_reference_arm(args):
     from oracle import c_oracle as co
     frames, W, H, T, D, C, kind = WORKLOADS[args.workload]
     forest = synth.hash_forest(T, D, C, seed=args.seed)
-    cores = co.num_threads()
+    cores = host_cores()
     sample = max(1, min(frames, args.ref_frames))
     depth = synth.depth_frames(kind, sample, H, W, seed=args.seed)
     labels = np.full((sample, H, W), 65535, np.uint16)
     for _ in range(args.warmup):
-        co.eval_forest(forest, depth[:1], labels[:1])
+        co.eval_forest(forest, depth[:1], labels[:1], nthreads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        co.eval_forest(forest, depth, labels)
+        co.eval_forest(forest, depth, labels, nthreads=cores)
     dt = time.perf_counter() - t0
     value = sample * H * W * args.steps / dt / 1e6
     line = {
