@@ -19,7 +19,7 @@ extern "C" const char* rdf_last_error(void) { return g_err; }
 // canonical node = (ux,uy,vx,vy,thresh,l_next,r_next,l_pdf[C],r_pdf[C]) (src/cuda/tree_eval.cu:47).
 // "child continues" is floor(flag) == -1 exactly as the kernels test it (__float2int_rd, tree_eval.cu:101-102).
 __global__ void rdf_pack_kernel(const float* __restrict__ canon, rdf_node_hdr* __restrict__ hdr, float* __restrict__ pdf,
-                                int64_t total_nodes, int64_t nodes_per_tree, int D, int C, int CP) {
+                                int64_t total_nodes, int64_t nodes_per_tree, int D, int C, int CP, int* __restrict__ exact_flag) {
     const int E = 7 + 2 * C;
     const int64_t first_last_level = ((int64_t)1 << (D - 1)) - 1;      // rows >= this are at level D-1: no children
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_nodes; i += (int64_t)gridDim.x * blockDim.x) {
@@ -36,6 +36,7 @@ __global__ void rdf_pack_kernel(const float* __restrict__ canon, rdf_node_hdr* _
         h.flags = (rdf_fastfloor_domain(nd[0]) && rdf_fastfloor_domain(nd[1]) && rdf_fastfloor_domain(nd[2]) &&
                    rdf_fastfloor_domain(nd[3])) ? 0 : RDF_FLAG_EXACT_DIV;
         hdr[i] = h;
+        if (h.flags & RDF_FLAG_EXACT_DIV) *exact_flag = 1;            // benign race: everybody writes 1
         float* p = pdf + i * 2 * CP;
         for (int c = 0; c < CP; c++) {
             p[c] = c < C ? nd[7 + c] : 0.f;
@@ -48,8 +49,12 @@ static int rdf_pack(rdf_forest* f, const float* canon_dev, cudaStream_t stream) 
     const int64_t total = f->nodes_per_tree * f->T;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 32) blocks = 148 * 32;
-    rdf_pack_kernel<<<blocks, 256, 0, stream>>>(canon_dev, f->hdr, f->pdf, total, f->nodes_per_tree, f->D, f->C, f->CP);
+    RDF_CUDA(cudaMemsetAsync(f->exact_flag_dev, 0, sizeof(int), stream));
+    rdf_pack_kernel<<<blocks, 256, 0, stream>>>(canon_dev, f->hdr, f->pdf, total, f->nodes_per_tree, f->D, f->C, f->CP, f->exact_flag_dev);
     RDF_LAUNCH_CHECK("rdf_pack_kernel");
+    // the flag is needed on the host to choose kernels: packing is handle creation / update, not the per-frame path
+    RDF_CUDA(cudaMemcpyAsync(&f->has_exact_nodes, f->exact_flag_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    RDF_CUDA(cudaStreamSynchronize(stream));
     return RDF_OK;
 }
 
@@ -79,9 +84,13 @@ extern "C" int rdf_forest_create(const float* canon_dev, int num_trees, int max_
     cudaError_t e = cudaGetDevice(&f->device);
     if (e == cudaSuccess) e = cudaMalloc(&f->hdr, hdr_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&f->pdf, pdf_bytes);
+    f->exact_flag_dev = nullptr;
+    f->has_exact_nodes = 0;
+    if (e == cudaSuccess) e = cudaMalloc(&f->exact_flag_dev, sizeof(int));
     if (e != cudaSuccess) {
         rdf_set_error("rdf_forest_create: allocating %zu packed bytes failed: %s", f->packed_bytes, cudaGetErrorString(e));
         if (f->hdr) cudaFree(f->hdr);
+        if (f->pdf) cudaFree(f->pdf);
         delete f;
         return RDF_ERR_CUDA;
     }
@@ -103,6 +112,7 @@ extern "C" int rdf_forest_destroy(rdf_forest_t* forest) {
     if (!forest) return RDF_OK;
     if (forest->hdr) cudaFree(forest->hdr);
     if (forest->pdf) cudaFree(forest->pdf);
+    if (forest->exact_flag_dev) cudaFree(forest->exact_flag_dev);
     delete forest;
     return RDF_OK;
 }

@@ -67,6 +67,8 @@ struct rdf_forest {
     float* pdf;                   // [T * nodes_per_tree * 2][CP]
     size_t packed_bytes;
     int device;
+    int has_exact_nodes;          // some node carries RDF_FLAG_EXACT_DIV (set by the last pack; read back at create / update)
+    int* exact_flag_dev;          // device word the pack kernel ORs into
 };
 
 // ---- reference arithmetic --------------------------------------------------------------------------------
@@ -236,6 +238,9 @@ static inline bool rdf_scale_fastfloor_ok(float s) {
 }
 
 static inline cudaStream_t rdf_stream(void* s) { return (cudaStream_t)s; }
+
+// CTAs per SM the register allocation of the per-pixel forest kernels aims for, by number of interleaved trees (see rdf_eval.cu)
+#define RDF_EVAL_MIN_BLOCKS_T(T) ((T) <= 5 ? 4 : (T) == 6 ? 3 : 2)
 
 // Opt-in dynamic shared memory above 48 KB is a PER-DEVICE function attribute: remember what was set on each device so that a
 // process driving several GPUs (or switching devices) gets it on all of them.

@@ -25,7 +25,7 @@ struct rdf_eval_params {
 // CTAs per SM the register allocation aims for: 4 (<= 64 registers) up to 5 interleaved trees; the state of 6..8 trees does not
 // fit 64 registers (it spilled 64-128 B of stack and cfg5 lost a third of its speed), so those get 3 / 2 CTAs per SM.
 // Measured on cfg3 (T=4): 5 or 6 CTAs per SM with 48 / 40 registers spill and are 18 % / 30 % slower.
-#define RDF_EVAL_MIN_BLOCKS(T) ((T) <= 5 ? 4 : (T) == 6 ? 3 : 2)
+#define RDF_EVAL_MIN_BLOCKS(T) RDF_EVAL_MIN_BLOCKS_T(T)
 template <int T, int WARP_W, bool SCALE1, bool FORCE_EXACT>
 __global__ void __launch_bounds__(256, RDF_EVAL_MIN_BLOCKS(T)) rdf_eval_packed_kernel(const rdf_eval_params p) {
     constexpr int WARP_H = 32 / WARP_W;

@@ -28,6 +28,10 @@ SIGNATURES = {
     'rdf_forest_destroy': [c_void_p],
     'rdf_forest_info': [c_void_p, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_size_t)],
     'rdf_eval_forest': [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p],
+    'rdf_depth_tex_create': [c_int, c_int, c_int, ctypes.POINTER(c_void_p)],
+    'rdf_depth_tex_destroy': [c_void_p],
+    'rdf_depth_tex_upload': [c_void_p, c_void_p, c_int, c_void_p],
+    'rdf_eval_forest_tex': [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p],
     'rdf_eval_forest_canonical': [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                                   c_void_p, c_int, c_float, c_void_p],
     'rdf_eval_tree': [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],

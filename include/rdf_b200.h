@@ -58,7 +58,9 @@ RDF_API const char* rdf_last_error(void);
  * canon_dev: float32[T, 2^D-1, 7+2C] canonical layout (node = ux,uy,vx,vy,thresh,l_next,r_next,l_pdf[C],r_pdf[C];
  * src/cuda/tree_eval.cu:47, node addressing src/cuda/cu_utils.hpp:32-39).  The handle owns a packed shadow
  * (32-byte node headers + 16-byte aligned leaf pdf rows); the caller keeps ownership of canon_dev.
- * rdf_forest_update re-packs after the caller mutated canon_dev (e.g. forest_cu.set(...), src/train_model.py:126). */
+ * rdf_forest_update re-packs after the caller mutated canon_dev (e.g. forest_cu.set(...), src/train_model.py:126).
+ * Create and update synchronise `stream` once (the pack reports back whether any node needs the exact-divide path); they are
+ * set-up calls, not part of the per-frame path. */
 RDF_API int rdf_forest_create(const float* canon_dev, int num_trees, int max_depth, int num_classes, void* stream,
                       rdf_forest_t** out);
 RDF_API int rdf_forest_update(rdf_forest_t* forest, const float* canon_dev, void* stream);
@@ -80,6 +82,18 @@ RDF_API int rdf_forest_info(const rdf_forest_t* forest, int* num_trees, int* max
 RDF_API int rdf_eval_forest(const rdf_forest_t* forest, const uint16_t* depth_dev, int num_images, int dim_x, int dim_y,
                     const uint16_t* filter_dev, int filter_class, uint16_t* labels_dev, float* probs_dev,
                     int labels_reduce, float scale, void* stream);
+
+/* Texture-unit variant of rdf_eval_forest for batches (scale 1, no probability output, forests whose offsets are all inside
+ * the fast-divide domain - otherwise RDF_ERR_UNSUPPORTED): the frames are first copied into a layered 2-D array holding
+ * 65535 - d (rdf_depth_tex_upload, at most 2048 frames per array), then every depth probe is one integer-coordinate texel fetch
+ * with border addressing (outside the image -> 65535, src/cuda/cu_utils.hpp:58-62,79-86).  depth_dev = the same frames in linear
+ * memory (centre depth).  Handle creation / destruction allocate; upload and eval are asynchronous on `stream`. */
+typedef struct rdf_depth_tex rdf_depth_tex_t;
+RDF_API int rdf_depth_tex_create(int max_images, int dim_x, int dim_y, rdf_depth_tex_t** out);
+RDF_API int rdf_depth_tex_destroy(rdf_depth_tex_t* tex);
+RDF_API int rdf_depth_tex_upload(rdf_depth_tex_t* tex, const uint16_t* depth_dev, int num_images, void* stream);
+RDF_API int rdf_eval_forest_tex(const rdf_forest_t* forest, const rdf_depth_tex_t* tex, const uint16_t* depth_dev, int num_images,
+                        const uint16_t* filter_dev, int filter_class, uint16_t* labels_dev, int labels_reduce, void* stream);
 
 /* Same contract as rdf_eval_forest, reading the canonical array float32[T,2^D-1,7+2C] directly (no handle, any
  * number of trees): the path for forests with more than 8 trees, which the packed fast path does not cover. */

@@ -286,3 +286,38 @@ def test_single_tree_packed_and_canonical_paths_agree():
         assert np.array_equal(to_np(a), exp) and np.array_equal(to_np(b), exp)
         if kill_leaves:
             assert (exp == 4242).any() and (exp != 4242).any()
+
+
+@pytest.mark.parametrize('kind,T,D,C,r', [('dense-smooth', 3, 8, 4, 1), ('dense-noise', 4, 7, 11, 1), ('live-mask', 2, 9, 3, 2), ('dense-noise', 8, 5, 4, 3)])
+def test_texture_probe_variant_matches_oracle(kind, T, D, C, r):
+    """rdf_eval_forest_tex (probes through the texture units, border addressing = the 65535 default) against the C oracle, with a
+    filter image; forests with out-of-domain offsets are refused."""
+    import ctypes
+    import torch
+    from rdf_b200 import _capi, synth
+    from rdf_b200 import decision_tree as dt
+    from oracle import c_oracle as co
+    lib = _capi.load()
+    N, H, W = 3, 61, 83
+    depth_np = synth.depth_frames(kind, N, H, W, seed=T)
+    depth_np[0, 3:6, 4:9] = 0
+    forest_np = synth.random_forest(T, D, C, seed=D, ragged=True)
+    filt_np = (np.arange(N * (H // r) * (W // r)).reshape(N, H // r, W // r) % 3).astype(np.uint16)
+    f = dt.DecisionForest(T, D, C)
+    f.forest_cu.set(forest_np)
+    d, filt = to_dev(depth_np), to_dev(filt_np)
+    lab = filled_u16((N, H // r, W // r), 777)
+    h = ctypes.c_void_p()
+    _capi.check(lib.rdf_depth_tex_create(N, W, H, ctypes.byref(h)))
+    try:
+        _capi.check(lib.rdf_depth_tex_upload(h, _capi.dptr(d), N, _capi.stream_ptr()))
+        _capi.check(lib.rdf_eval_forest_tex(f.handle(), h, _capi.dptr(d), N, _capi.dptr(filt), 1, _capi.dptr(lab), r, _capi.stream_ptr()))
+        torch.cuda.synchronize()
+        exp = np.full((N, H // r, W // r), 777, np.uint16)
+        co.eval_forest(forest_np, depth_np, exp, r, filt_np, 1)
+        assert np.array_equal(to_np(lab), exp)
+        forest_np[0, 0, 0] = np.inf                                 # exact-divide node: the texture variant must refuse
+        f.forest_cu.set(forest_np)
+        assert lib.rdf_eval_forest_tex(f.handle(), h, _capi.dptr(d), N, None, -1, _capi.dptr(lab), r, _capi.stream_ptr()) == -3
+    finally:
+        lib.rdf_depth_tex_destroy(h)
