@@ -523,16 +523,18 @@ static int rdf_hist_bucketed_launch(const uint16_t* depth_dev, const uint16_t* l
     RDF_REQUIRE(log2ntp <= 10, "rdf_train_hist_bucketed: at most 1024 thresholds per feature (got %d)", p.NT);
     const size_t smem_budget = 220 * 1024;
     const size_t per_feature = sizeof(float4) + sizeof(int) * ((size_t)1 << log2ntp) + sizeof(uint32_t) * (size_t)p.NB * p.C + 1;
-    int fc = (int)((smem_budget - 64) / per_feature);
-    if (fc > TB_MAX_FC) fc = TB_MAX_FC;
-    if (fc > p.F) fc = p.F;
-    if (fc < 1) {
-        rdf_set_error("rdf_train_hist_bucketed: %d thresholds x %d classes per feature do not fit shared memory", p.NT, p.C);
+    // features per CTA: a multiple of TB_U (the loop evaluates TB_U at a time, the chunk is padded to it) that fits shared memory
+    int fc_max = (int)((smem_budget - 64) / per_feature);
+    if (fc_max > TB_MAX_FC) fc_max = TB_MAX_FC;
+    fc_max &= ~(TB_U - 1);
+    if (fc_max < TB_U) {
+        rdf_set_error("rdf_train_hist_bucketed: %d thresholds x %d classes per feature do not fit shared memory (use rdf_train_hist)",
+                      p.NT, p.C);
         return RDF_ERR_UNSUPPORTED;
     }
-    const int chunks = (p.F + fc - 1) / fc;
-    fc = (p.F + chunks - 1) / chunks;                                            // equal chunks
-    fc = (fc + 3) & ~3;                                                          // keeps the arrays behind off_s 16-byte aligned
+    const int chunks = (p.F + fc_max - 1) / fc_max;
+    int fc = (p.F + chunks - 1) / chunks;                                        // equal chunks
+    fc = (fc + TB_U - 1) & ~(TB_U - 1);                                          // <= fc_max (a multiple of TB_U itself)
     p.FC = fc;
     const size_t smem = per_feature * fc + 64;
     const int64_t tiles = (num_pixels + TB_TILE - 1) / TB_TILE;

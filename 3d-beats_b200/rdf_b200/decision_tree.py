@@ -651,9 +651,14 @@ class DecisionTreeTrainer():
                         continue
                     hist = self.hist_cu[:S]
                     hist.fill(0)
-                    _capi.check(lib.rdf_train_hist_bucketed(_capi.dptr(depth), _capi.dptr(labels), N, W, H, _capi.dptr(self.bucket_ws), S,
-                                                            _capi.dptr(self.current_offsets), _capi.dptr(self.current_thresholds),
-                                                            P, NT, C, _capi.dptr(hist), st()))
+                    rc = lib.rdf_train_hist_bucketed(_capi.dptr(depth), _capi.dptr(labels), N, W, H, _capi.dptr(self.bucket_ws), S,
+                                                     _capi.dptr(self.current_offsets), _capi.dptr(self.current_thresholds),
+                                                     P, NT, C, _capi.dptr(hist), st())
+                    if rc == -3:        # RDF_ERR_UNSUPPORTED: a feature's [NT+1][C] histogram exceeds shared memory -> raster kernel
+                        rc = lib.rdf_train_hist(_capi.dptr(depth), _capi.dptr(labels), _capi.dptr(self.nodes_by_pixel), N, W, H,
+                                                _capi.dptr(self.node_slot_cu), S, _capi.dptr(self.current_offsets),
+                                                _capi.dptr(self.current_thresholds), P, NT, C, _capi.dptr(hist), st())
+                    _capi.check(rc)
                     if dist is not None:                                       # the path's only exchange step
                         dist.all_reduce(hist.tensor.view(torch.int32), group=self.process_group)
                     _capi.check(lib.rdf_train_pick_best(num_active_nodes, _capi.dptr(self.active_nodes_cu),

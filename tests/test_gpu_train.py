@@ -236,3 +236,37 @@ def test_feature_sharded_search_equals_single_gpu(world, F, level):
     assert torch.equal(tree1.view(torch.int32), tree2.view(torch.int32)) and torch.equal(next1, next2)
     assert torch.equal(gain1.view(torch.int32), gain2.view(torch.int32))
     assert bool((tree1[:, 5:7] == -1).any())
+
+
+def test_many_classes_fall_back_to_the_raster_kernel():
+    """C = 240 classes x 64 thresholds: one feature's histogram (62 KB) x 4 features exceeds shared memory, so the bucketed kernel
+    refuses and the trainer uses the raster kernel; the trained tree still matches the NumPy oracle."""
+    import torch
+    from rdf_b200 import _capi, synth
+    from rdf_b200 import decision_tree as dt
+    from oracle import numpy_oracle as no
+    lib = _capi.load()
+    N, H, W, C, D, F, NT = 1, 40, 48, 240, 3, 8, 64
+    rng = np.random.default_rng(3)
+    depth = synth.depth_frames('dense-smooth', N, H, W, seed=4)
+    labels = rng.integers(1, C, size=(N, H, W)).astype(np.uint16)
+    props = {lvl: synth.random_proposals(F, NT, seed=50 + lvl) for lvl in range(D)}
+    ds = dt.DecisionTreeDatasetConfig.from_arrays(depth, labels, C)
+    trainer = dt.DecisionTreeTrainer(N, F, thresholds_per_feature=NT, proposal_fn=lambda lvl, b: props[lvl])
+    trainer.allocate(ds, F, D)
+    # the bucketed entry point itself reports RDF_ERR_UNSUPPORTED for this shape
+    S = 1
+    hist = torch.zeros((S, F, NT + 1, C), dtype=torch.int32, device='cuda')
+    rc = lib.rdf_train_hist_bucketed(_capi.dptr(to_dev(depth)), _capi.dptr(to_dev(labels)), N, W, H, _capi.dptr(trainer.bucket_ws), S,
+                                     _capi.dptr(to_dev(props[0][0])), _capi.dptr(to_dev(props[0][1])), F, NT, C, _capi.dptr(hist),
+                                     _capi.stream_ptr())
+    assert rc == -3
+    tree = dt.DecisionTree(D, C)
+    trainer.train(ds, tree)
+    torch.cuda.synchronize()
+
+    def flat(lvl):
+        off, th = props[lvl]
+        return [np.concatenate([np.repeat(off, NT, axis=0), th.reshape(-1, 1)], axis=1).astype(np.float32)]
+    exp = no.train_tree(depth, labels, C, D, flat)
+    _assert_same_tree(tree.tree_out_cu.get(), exp, 'numpy oracle (240 classes)')
