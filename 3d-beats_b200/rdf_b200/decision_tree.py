@@ -515,7 +515,11 @@ class DecisionTreeTrainer():
         self.bucket_ws = GPUArray(((need.value + 3) // 4,), dtype=np.int32)
         self._p2p = None
         dist = self._dist()
-        if dist is not None and self.exchange != 'allreduce':
+        ntp = 1
+        while ntp < NT:
+            ntp *= 2
+        bucketed_fits = 4 * (16 + 4 * ntp + 4 * (NT + 1) * C + 1) + 64 <= 220 * 1024      # rdf_train_hist_bucketed's shared-memory need
+        if dist is not None and self.exchange != 'allreduce' and bucketed_fits:
             try:
                 self._setup_p2p(dist, P, NT, C)
             except Exception as e:                               # no symmetric memory on this system: NCCL allreduce instead
