@@ -507,6 +507,212 @@ __global__ void __launch_bounds__(MS2_THREADS, 1) rdf_mean_shift_v2_kernel(const
     if (p.trace && rank == 0 && tid == 0) p.trace[17] = (unsigned long long)clock64();
 }
 
+// =================================================================================================================
+// v3: class-parallel latency path.  The classes never interact (each has its own mean), so instead of spreading the PIXELS
+// over a cluster and meeting at a cluster barrier every round (v2: ~2.4 us per round, mostly synchronisation), every CLASS
+// gets its own small cluster of R CTAs (R = 1 for images up to 50 880 pixels, 2 for the product's 424 x 240 label image,
+// 8 for 848 x 480).  Each CTA filters its share of the label image for its class (128-bit loads, the image is read once per
+// class out of L2), compacts the coordinates into shared memory (one 32-bit block scan), and then iterates: every thread owns
+// fixed entries, the CTA reduces with shuffles, and only when R > 1 the R partial sums cross distributed shared memory.
+// Results are bitwise reproducible (fixed entry -> thread mapping, fixed reduction trees).
+// =================================================================================================================
+#define MS3_THREADS 1024
+#define MS3_WARPS 32
+#define MS3_GROUPS 7                      // 8-pixel groups per thread: up to 57 344 pixels per CTA
+#define MS3_CAP 50944                     // pixels per CTA (= entries it may have to hold): 8 CTAs cover 848 x 480
+#define MS3_MAX_R 8
+
+struct rdf_ms3_params {
+    const uint16_t* labels;
+    const float* variances;
+    double* means_out;
+    int w, h, K, rounds, R;
+    unsigned long long* trace;   // optional: %globaltimer stamps of class 0 / rank 0 (workspace head), phase by phase
+};
+#define MS3_TRACE(slot)                                                              \
+    do {                                                                             \
+        if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[slot] = ms_now();        \
+    } while (0)
+
+__global__ void __launch_bounds__(MS3_THREADS, 1) rdf_mean_shift_v3_kernel(const rdf_ms3_params p) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int R = p.R;
+    const int rank = R > 1 ? (int)cluster.block_rank() : 0;
+    const int k = blockIdx.x / R;                                            // class of this cluster (label k + 1)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    extern __shared__ __align__(16) unsigned char ms_smem[];
+    double* xpart = reinterpret_cast<double*>(ms_smem);                       // [2][MS3_MAX_R][3] partial sums of the cluster's CTAs
+    double* wpart = xpart + 2 * MS3_MAX_R * 3;                                // [2][MS3_WARPS][3] warp partial sums, by round parity
+    int* wtot = reinterpret_cast<int*>(wpart + 2 * MS3_WARPS * 3);            // [MS3_WARPS]
+    uint32_t* entries = reinterpret_cast<uint32_t*>(wtot + MS3_WARPS);        // [<= MS3_CAP]
+
+    asm volatile("griddepcontrol.wait;" ::: "memory");                        // programmatic dependent launch (see v2)
+    const int npx = p.w * p.h;
+    const unsigned want = (unsigned)k + 1u;
+    MS3_TRACE(0);
+
+    // ---- my 8-pixel groups (dealt round-robin to the R CTAs), all loads issued first ----
+    uint4 px[MS3_GROUPS];
+#pragma unroll
+    for (int g = 0; g < MS3_GROUPS; g++) {
+        const int q = ((g * MS3_THREADS + tid) * R + rank) * 8;
+        px[g] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        if (q + 8 <= npx) {
+            px[g] = __ldg(reinterpret_cast<const uint4*>(p.labels + q));
+        } else if (q < npx) {
+            unsigned short tmp[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) tmp[j] = q + j < npx ? __ldg(p.labels + q + j) : (unsigned short)0xffff;
+            px[g] = make_uint4(tmp[0] | (tmp[1] << 16), tmp[2] | (tmp[3] << 16), tmp[4] | (tmp[5] << 16), tmp[6] | (tmp[7] << 16));
+        }
+    }
+    // match mask of my pixels: bit (8 g + j) set when pixel j of group g carries this class' label (two labels per SIMD compare)
+    const unsigned want2 = want | (want << 16);
+    unsigned long long mask = 0ull;
+#pragma unroll
+    for (int g = 0; g < MS3_GROUPS; g++) {
+        const unsigned w0 = __vcmpeq2(px[g].x, want2), w1 = __vcmpeq2(px[g].y, want2), w2 = __vcmpeq2(px[g].z, want2),
+                       w3 = __vcmpeq2(px[g].w, want2);                   // 0xffff per matching half-word
+        const unsigned m8 = (w0 & 1u) | ((w0 >> 15) & 2u) | ((w1 & 1u) << 2) | ((w1 >> 13) & 8u) | ((w2 & 1u) << 4) | ((w2 >> 11) & 32u) |
+                            ((w3 & 1u) << 6) | ((w3 >> 9) & 128u);
+        mask |= (unsigned long long)m8 << (8 * g);
+    }
+    const int cnt = __popcll(mask);
+    MS3_TRACE(1);
+    // ---- block exclusive scan -> positions (thread-major, then pixel order: deterministic) ----
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int t = wtot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, t, o);
+            if (lane >= o) t += u;
+        }
+        wtot[lane] = t;
+    }
+    __syncthreads();
+    const int n = wtot[MS3_WARPS - 1];                                        // entries of this CTA
+    MS3_TRACE(2);
+    {
+        int pos = (warp ? wtot[warp - 1] : 0) + incl - cnt;
+        unsigned long long m = mask;
+        while (m) {                                                          // only the matching pixels are visited
+            const int b = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            const int q = (((b >> 3) * MS3_THREADS + tid) * R + rank) * 8 + (b & 7);
+            const int y = q / p.w, x = q - y * p.w;
+            entries[pos++] = (uint32_t)x | ((uint32_t)y << 16);
+        }
+    }
+    const float var = p.variances[k];
+    const double nis = -1.0 / (2.0 * (double)__fmul_rn(var, var));            // sigma^2 = fp32 product, widened (mean_shift.cu:41)
+    __syncthreads();
+
+    MS3_TRACE(3);
+    // ---- rounds ----
+    // Barriers per round: one block barrier (warp partials visible) and, for R > 1, the cluster barrier.  The new mean is then
+    // computed redundantly by every thread that owns entries (nobody else needs it), from buffers that alternate by round
+    // parity, so no broadcast barrier is needed.
+    const int nw = (min(n, MS3_THREADS) + 31) >> 5;                           // warps that own entries
+    const bool owner = tid < nw * 32;
+    double mx = 0.0, my = 0.0;
+    for (int it = 0; it < p.rounds; it++) {
+        if (it < 10) MS3_TRACE(4 + it);
+        double* wp = wpart + (size_t)(it & 1) * MS3_WARPS * 3;
+        if (owner) {
+            double sx = 0.0, sy = 0.0, sp = 0.0;
+            for (int e = tid; e < n; e += 2 * MS3_THREADS) {                  // two entries per trip: independent exp chains
+                const int e2 = e + MS3_THREADS;
+                const bool v2 = e2 < n;
+                const uint32_t ca = entries[e], cb = v2 ? entries[e2] : 0u;
+                const double cxa = (double)(ca & 0xffffu), cya = (double)(ca >> 16);
+                const double cxb = (double)(cb & 0xffffu), cyb = (double)(cb >> 16);
+                if (it == 0) {                                               // mean_shift.cu:31-34
+                    const double wb = v2 ? 1.0 : 0.0;
+                    sx += cxa + cxb * wb;
+                    sy += cya + cyb * wb;
+                    sp += 1.0 + wb;
+                } else {                                                     // mean_shift.cu:36-46
+                    const double dxa = cxa - mx, dya = cya - my, dxb = cxb - mx, dyb = cyb - my;
+                    const double pa = ms_exp_nonpos((dxa * dxa + dya * dya) * nis);
+                    double pb = ms_exp_nonpos((dxb * dxb + dyb * dyb) * nis);
+                    pb = v2 ? pb : 0.0;
+                    sx += dxa * pa + dxb * pb;
+                    sy += dya * pa + dyb * pb;
+                    sp += pa + pb;
+                }
+            }
+            if (it == 1) MS3_TRACE(20);
+            sx = ms_warp_sum(sx);
+            sy = ms_warp_sum(sy);
+            sp = ms_warp_sum(sp);
+            if (it == 1) MS3_TRACE(21);
+            if (lane == 0) {
+                wp[warp * 3 + 0] = sx;
+                wp[warp * 3 + 1] = sy;
+                wp[warp * 3 + 2] = sp;
+            }
+        }
+        __syncthreads();
+        double a = 0.0, b = 0.0, c = 0.0;
+        if (R > 1) {
+            double* buf = xpart + (size_t)(it & 1) * MS3_MAX_R * 3;
+            if (tid < 3) {                                                   // CTA total of one component, warps in order
+                double t = 0.0;
+                for (int wv = 0; wv < nw; wv++) t += wp[wv * 3 + tid];
+                for (int r = 0; r < R; r++) cluster.map_shared_rank(buf, r)[rank * 3 + tid] = t;
+            }
+            if (it == 1) MS3_TRACE(22);
+            cluster.sync();
+            if (it == 1) MS3_TRACE(23);
+            if (owner) {
+                for (int r = 0; r < R; r++) {
+                    a += buf[r * 3 + 0];
+                    b += buf[r * 3 + 1];
+                    c += buf[r * 3 + 2];
+                }
+            }
+        } else if (owner) {
+            for (int wv = 0; wv < nw; wv++) {
+                a += wp[wv * 3 + 0];
+                b += wp[wv * 3 + 1];
+                c += wp[wv * 3 + 2];
+            }
+        }
+        if (owner || tid == 0) {
+            if (R > 1 && !owner) {                                           // tid 0 of a CTA without entries still reports the mean
+                const double* buf = xpart + (size_t)(it & 1) * MS3_MAX_R * 3;
+                for (int r = 0; r < R; r++) {
+                    a += buf[r * 3 + 0];
+                    b += buf[r * 3 + 1];
+                    c += buf[r * 3 + 2];
+                }
+            }
+            mx += a / c;                                                     // mean_shift.py:53-55 (0/0 -> NaN)
+            my += b / c;
+        }
+        if (it == 1) MS3_TRACE(24);
+    }
+    MS3_TRACE(14);
+    if (rank == 0 && tid == 0) {
+        p.means_out[2 * k] = mx;
+        p.means_out[2 * k + 1] = my;
+    }
+    if (R > 1) cluster.sync();   // no CTA may exit while peers can still address its shared memory
+}
+
+static size_t ms3_smem_bytes(int chunk) {
+    return sizeof(double) * (2 * MS3_MAX_R * 3 + 2 * MS3_WARPS * 3) + sizeof(int) * MS3_WARPS + sizeof(uint32_t) * (size_t)chunk;
+}
+
 static size_t ms2_smem_bytes(int K, int NC, int chunk) {
     size_t b = 0;
     b += sizeof(double) * 2 * (size_t)NC * K * 3;
@@ -548,7 +754,52 @@ extern "C" int rdf_mean_shift(const uint16_t* labels_dev, int dim_x, int dim_y, 
     RDF_REQUIRE((int64_t)dim_x * dim_y < (1LL << 30), "rdf_mean_shift: image too large");
 
     const int npx = dim_x * dim_y;
-    // latency path: everything in shared memory (see v2 above)
+    // class-parallel latency path (v3 above): one small cluster per class
+    if (npx <= MS3_MAX_R * MS3_CAP && (reinterpret_cast<uintptr_t>(labels_dev) & 15u) == 0 && !getenv("RDF_MS_V1") && !getenv("RDF_MS_V2")) {
+        // CTAs per class: enough that a CTA scans at most ~12 800 pixels (52 KB of shared memory: such CTAs can be scheduled
+        // beside the still-running layered kernel under programmatic dependent launch, and the scan of the label image is
+        // spread over more SMs).  Measured on cfg2 (424 x 240 labels): R = 2 / 4 / 8 -> 28.7 / 26.6 / 22.6-24.6 us per launch,
+        // e2e frame latency 74.7 / 72.7 / 68.2-69.5 us.  RDF_MS3_R overrides the minimum (experiments).
+        int R = (npx + MS3_CAP - 1) / MS3_CAP;
+        {
+            static int r_min = -1;
+            if (r_min < 0) {
+                const char* e = getenv("RDF_MS3_R");
+                r_min = e ? atoi(e) : 0;
+                if (r_min < 0 || r_min > MS3_MAX_R) r_min = 0;
+            }
+            int want = r_min ? r_min : (npx + 12799) / 12800;
+            if (want > MS3_MAX_R) want = MS3_MAX_R;
+            if (R < want) R = want;
+        }
+        if (R == 3) R = 4;                                            // cluster sizes: 1, 2, 4, 8
+        if (R > 4 && R < 8) R = 8;
+        rdf_ms3_params q;
+        q.labels = labels_dev; q.variances = variances_dev; q.means_out = means_dev;
+        q.w = dim_x; q.h = dim_y; q.K = num_labels; q.rounds = rounds; q.R = R;
+        q.trace = getenv("RDF_MS_TRACE") ? reinterpret_cast<unsigned long long*>(workspace_dev) : nullptr;
+        const int ngroups = (npx + 7) / 8;
+        const int chunk = ((ngroups + R - 1) / R) * 8;                // pixels (= upper bound of entries) per CTA
+        const size_t smem3 = ms3_smem_bytes(chunk);
+        RDF_ENSURE_DYN_SMEM(rdf_mean_shift_v3_kernel, smem3);
+        cudaLaunchConfig_t cfg3 = {};
+        cfg3.gridDim = dim3(num_labels * R, 1, 1);
+        cfg3.blockDim = dim3(MS3_THREADS, 1, 1);
+        cfg3.dynamicSmemBytes = smem3;
+        cfg3.stream = rdf_stream(stream);
+        cudaLaunchAttribute attr3[2];
+        attr3[0].id = cudaLaunchAttributeClusterDimension;
+        attr3[0].val.clusterDim.x = R;
+        attr3[0].val.clusterDim.y = 1;
+        attr3[0].val.clusterDim.z = 1;
+        attr3[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr3[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg3.attrs = attr3;
+        cfg3.numAttrs = getenv("RDF_NO_PDL") ? 1 : 2;
+        RDF_CUDA(cudaLaunchKernelEx(&cfg3, rdf_mean_shift_v3_kernel, q));
+        return RDF_OK;
+    }
+    // pixel-parallel latency path: everything in shared memory (see v2 above)
     if (num_labels <= MS2_MAX_K && npx <= MS_MAX_CLUSTER * MS2_CAP &&   /* capacity at the portable cluster size */ (reinterpret_cast<uintptr_t>(labels_dev) & 15u) == 0 &&
         !getenv("RDF_MS_V1")) {
         // cluster size: 16 CTAs (non-portable size, opt-in) when the device can co-schedule such a cluster with the kernel's

@@ -32,6 +32,10 @@ t = ms._workspace.get()[:64].view(np.uint64).astype(np.int64)
 print('labelled px', int(m.sum()))
 print('setup (ns): load+count', int(t[1] - t[0]), 'scan', int(t[2] - t[1]), 'scatter', int(t[3] - t[2]))
 print('rounds (ns):', [int(t[5 + i] - t[4 + i]) for i in range(5)], 'last:', int(t[14] - t[9]), 'tail:', int(t[15] - t[14]), 'total:', int(t[15] - t[0]))
-print('round 1 detail (ns): items..lastwarp', int(t[22] - t[5]), 'class sums + DSMEM', int(t[23] - t[22]), 'cluster.sync', int(t[24] - t[23]),
-      'means', int(t[25] - t[24]), 'to next round', int(t[6] - t[25]))
+if os.environ.get('RDF_MS_V2'):
+    print('round 1 detail (ns): items..lastwarp', int(t[22] - t[5]), 'class sums + DSMEM', int(t[23] - t[22]), 'cluster.sync', int(t[24] - t[23]),
+          'means', int(t[25] - t[24]), 'to next round', int(t[6] - t[25]))
+else:   # v3 (class-parallel): stamps of class 0, rank 0
+    print('round 1 detail (ns): entries+exp', int(t[20] - t[5]), 'warp sums', int(t[21] - t[20]), 'CTA sum (+DSMEM)', int(t[22] - t[21]),
+          'cluster.sync', int(t[23] - t[22]), 'mean + block sync', int(t[24] - t[23]), 'to next round', int(t[6] - t[24]))
 print('max |ours - oracle|', float(np.nanmax(np.abs(out - no.mean_shift(lab, 11, var, 6)))))
