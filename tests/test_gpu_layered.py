@@ -76,7 +76,7 @@ def test_layered_matches_reference_kernels(tmp_path):
     assert np.nanmax(np.abs(ms - ref_ms)) <= 1e-5
 
 
-@pytest.mark.parametrize('h,w,K', [(240, 424, 11), (33, 57, 3), (480, 848, 11), (720, 1280, 20), (7, 5, 2)])
+@pytest.mark.parametrize('h,w,K', [(240, 424, 11), (33, 57, 3), (480, 848, 11), (720, 1280, 20), (7, 5, 2), (120, 160, 5), (200, 212, 30)])
 def test_mean_shift_matches_oracle(h, w, K):
     from rdf_b200.mean_shift import MeanShift
     from oracle import numpy_oracle as no
