@@ -53,6 +53,7 @@ struct rdf_layered_params {
     int W, H, w, h, r;
     int tiles_x;
     float scale;
+    int flip_out;              // composite written mirrored in x (the left hand of the live product, src/3d_bz.py:439-446)
 };
 
 template <int WARP_W, bool SCALE1, bool FORCE_EXACT>
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(256) rdf_layered_kernel(const __grid_constant_
         }
         off = tv.y;
     }
-    p.composite[li] = (uint16_t)comp;
+    p.composite[p.flip_out ? (size_t)y * p.w + (p.w - 1 - x) : li] = (uint16_t)comp;
 }
 
 // ---- latency path: one thread per (pixel, tree walk) ---------------------------------------------------------------
@@ -151,10 +152,11 @@ __global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_co
     if (inside) d = __ldg(p.depth + (size_t)Y * p.W + X);
     const bool valid = inside && d != 0u && d != RDF_NO_PIXEL;
     const size_t li = (size_t)y * p.w + x;
+    const size_t lo = p.flip_out ? (size_t)y * p.w + (p.w - 1 - x) : li;   // where the composite label of this pixel goes
     if (__syncthreads_or(valid) == 0) {                                   // nothing to evaluate in this tile: pre-fill only
         if (walk == 0 && inside) {
             for (int i = 0; i < p.L; i++) p.layer_labels[i][li] = (uint16_t)RDF_NO_PIXEL;
-            p.composite[li] = (uint16_t)RDF_NO_PIXEL;
+            p.composite[lo] = (uint16_t)RDF_NO_PIXEL;
         }
         return;
     }
@@ -250,13 +252,13 @@ __global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_co
         }
         off = tv.y;
     }
-    p.composite[li] = (uint16_t)comp;
+    p.composite[lo] = (uint16_t)comp;
 }
 
-extern "C" int rdf_layered_run(const rdf_forest_t* const* forests, int num_layers, const int* filter_model,
+static int rdf_layered_run_impl(const rdf_forest_t* const* forests, int num_layers, const int* filter_model,
                                const int* filter_class, const uint16_t* depth_dev, int dim_x, int dim_y,
                                uint16_t* const* labels_per_layer, const int32_t* conditions_dev, int n_cond,
-                               uint16_t* composite_dev, int labels_reduce, float scale, void* stream) {
+                               uint16_t* composite_dev, int labels_reduce, float scale, int composite_flip_x, void* stream) {
     RDF_REQUIRE(forests && filter_model && filter_class && depth_dev && labels_per_layer && conditions_dev && composite_dev,
                 "rdf_layered_run: NULL argument");
     RDF_REQUIRE(num_layers >= 1 && num_layers <= RDF_MAX_LAYERS, "rdf_layered_run: num_layers=%d outside 1..%d", num_layers,
@@ -288,6 +290,7 @@ extern "C" int rdf_layered_run(const rdf_forest_t* const* forests, int num_layer
     if (p.w == 0 || p.h == 0) return RDF_OK;
     p.tiles_x = (p.w + 31) / 32;
     p.scale = scale;
+    p.flip_out = composite_flip_x ? 1 : 0;
     const int tiles_y = (p.h + 7) / 8;
     RDF_REQUIRE((int64_t)dim_x * dim_y < ((int64_t)1 << 31), "rdf_layered_run: image of %dx%d pixels is too large", dim_x, dim_y);
     const bool fast = rdf_scale_fastfloor_ok(scale) && dim_x <= 65535 && dim_y <= 65535;   // see rdf_common.cuh
@@ -336,6 +339,22 @@ extern "C" int rdf_layered_run(const rdf_forest_t* const* forests, int num_layer
         rdf_layered_kernel<8, false, false><<<nblk, 256, 0, rdf_stream(stream)>>>(p);
     RDF_LAUNCH_CHECK("rdf_layered_kernel");
     return RDF_OK;
+}
+
+extern "C" int rdf_layered_run(const rdf_forest_t* const* forests, int num_layers, const int* filter_model,
+                               const int* filter_class, const uint16_t* depth_dev, int dim_x, int dim_y,
+                               uint16_t* const* labels_per_layer, const int32_t* conditions_dev, int n_cond,
+                               uint16_t* composite_dev, int labels_reduce, float scale, void* stream) {
+    return rdf_layered_run_impl(forests, num_layers, filter_model, filter_class, depth_dev, dim_x, dim_y, labels_per_layer,
+                                conditions_dev, n_cond, composite_dev, labels_reduce, scale, 0, stream);
+}
+
+extern "C" int rdf_layered_run_hand(const rdf_forest_t* const* forests, int num_layers, const int* filter_model,
+                                    const int* filter_class, const uint16_t* depth_dev, int dim_x, int dim_y,
+                                    uint16_t* const* labels_per_layer, const int32_t* conditions_dev, int n_cond,
+                                    uint16_t* composite_dev, int labels_reduce, float scale, int composite_flip_x, void* stream) {
+    return rdf_layered_run_impl(forests, num_layers, filter_model, filter_class, depth_dev, dim_x, dim_y, labels_per_layer,
+                                conditions_dev, n_cond, composite_dev, labels_reduce, scale, composite_flip_x, stream);
 }
 
 // ---- frame upload as a kernel ------------------------------------------------------------------------------------------

@@ -253,7 +253,11 @@ class LayeredDecisionForest():
         self._c_label_ptrs = (ctypes.c_void_p * L)(*[i.cu().ptr for i in self.label_images])
         self._n_cond = int(labels_conditions.shape[0])
 
-    def run(self, depth_image, labels_image, scale_factor=1.):
+    def run(self, depth_image, labels_image, scale_factor=1., composite_flip_x=False, label_images=None):
+        """src/decision_tree.py:233-264 in one launch.  Two keyword extensions for the live product's per-hand loop
+        (src/3d_bz.py:387-446): composite_flip_x writes the composite label image mirrored in x (the reference's
+        labels_image_2.set + flip_x after the left hand's run); label_images = another set of per-layer label buffers than
+        self.label_images, so that two hands can be evaluated concurrently on two streams."""
         depth = as_gpuarray(depth_image)
         labels = as_gpuarray(labels_image)
         assert depth.dtype == np.uint16 and labels.dtype == np.uint16
@@ -261,10 +265,14 @@ class LayeredDecisionForest():
         assert labels.size == self.labels_dims[0] * self.labels_dims[1], 'labels image dims'
         L = self.num_models
         handles = (ctypes.c_void_p * L)(*[m.handle().value for m, _, _ in self.m])
-        _capi.check(self.eval._lib.rdf_layered_run(
+        label_ptrs = self._c_label_ptrs
+        if label_images is not None:
+            assert len(label_images) == L
+            label_ptrs = (ctypes.c_void_p * L)(*[as_gpuarray(i).ptr for i in label_images])
+        _capi.check(self.eval._lib.rdf_layered_run_hand(
             handles, L, self._c_filter_model, self._c_filter_class, _capi.dptr(depth), self.depth_dims[1], self.depth_dims[0],
-            self._c_label_ptrs, _capi.dptr(self.labels_conditions_cu.cu()), self._n_cond, _capi.dptr(labels),
-            int(self.labels_reduce), float(scale_factor), _capi.stream_ptr()))
+            label_ptrs, _capi.dptr(self.labels_conditions_cu.cu()), self._n_cond, _capi.dptr(labels),
+            int(self.labels_reduce), float(scale_factor), int(bool(composite_flip_x)), _capi.stream_ptr()))
 
     def run_unfused(self, depth_image, labels_image, scale_factor=1.):
         """The reference's launch sequence verbatim (fills, one forest eval per layer, composite): kept for parity tests

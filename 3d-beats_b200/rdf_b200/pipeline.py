@@ -5,6 +5,9 @@ HostBatchEvaluator  offline batches (test_on_saved_model.py shape, src/test_on_s
                     (H2D | eval | D2H) so copies overlap compute.
 LiveFramePipeline   the per-frame product path (src/3d_bz.py:437-465): H2D of one frame -> fused layered forest ->
                     cluster mean shift -> D2H of the K x 2 centroids, captured once as a CUDA graph and replayed.
+HandsFramePipeline  the whole compute of one product frame (App_3d_bz.tick + run_per_hand_pipeline x 2, src/3d_bz.py:129-300,
+                    387-522): raw camera frame in pinned host memory -> conditioning -> hand grouping -> per hand: stencil,
+                    layered forest, mean shift, fingertip depths -> centroids + fingertip z of both hands in pinned host memory.
 """
 import numpy as np
 import torch
@@ -12,6 +15,8 @@ import torch
 from . import _capi
 from .buffers import GPUArray, GpuBuffer
 from .mean_shift import MeanShift
+from .grouping import CppGrouping
+from .points_ops import PointsOps
 
 
 def pinned_like(shape, np_dtype):
@@ -142,3 +147,125 @@ class LiveFramePipeline:
         self.submit()
         self.stream.synchronize()
         return self.means_host.numpy().copy()
+
+
+class HandsFramePipeline:
+    """One raw camera frame in, both hands' fingertip centroids and plane-space depths out: the device work that
+    `App_3d_bz.tick` (src/3d_bz.py:129-300) and its two `run_per_hand_pipeline` calls (:387-522) issue as ~45 launches, 8 frame-sized
+    copies, one D2H + C++ flood fill + H2D round trip and 28 blocking mean-shift transfers is 10 launches here (upload,
+    conditioning, grouping, stencil, then per hand layered forest -> mean shift -> read-out on two concurrent branches), captured
+    once as a CUDA graph.  Defaults are the product's settings (src/3d_bz.py:49-113)."""
+
+    def __init__(self, layered_forest, variances, pp, focal, plane, fx=None, fy=None, num_rounds=6, plane_z_threshold=40.,
+                 gauss_sigma=2.0, k_size=5, mm_level=3, group_min_size=0.06, fingertip_idxes=(2, 3, 4, 5, 6), scale_factor=1.,
+                 use_graph=True, concurrent_hands=True, upload='kernel'):
+        """upload: 'kernel' = upload kernel into depth_raw, then conditioning; 'fused' = the conditioning kernel (and the read-out)
+        read the pinned host frame themselves (zero-copy over PCIe), no device copy of the raw frame exists."""
+        self.upload = upload
+        self.ldf = layered_forest
+        H, W = layered_forest.depth_dims
+        h, w = layered_forest.labels_dims
+        self.H, self.W, self.h, self.w = H, W, h, w
+        self.K = layered_forest.num_layered_classes
+        self.rounds = int(num_rounds)
+        self.pp = (float(pp[0]), float(pp[1]))
+        self.focal = float(focal)
+        self.fx = float(focal if fx is None else fx)
+        self.fy = float(focal if fy is None else fy)
+        self.thresh = float(plane_z_threshold)
+        self.sigma, self.k_size, self.mm_level = float(gauss_sigma), int(k_size), int(mm_level)
+        self.group_min_size = float(group_min_size)
+        self.fingertips = tuple(int(i) for i in fingertip_idxes)
+        self.scale = float(scale_factor)
+        self.hands = ((1, False), (2, True))                      # (group id, flip_x): right hand, left hand (src/3d_bz.py:281-285)
+        nh, nf = len(self.hands), len(self.fingertips)
+        mh, mw = H >> self.mm_level, W >> self.mm_level
+        self.ops = PointsOps()
+        self.grouping = CppGrouping()
+        # host side of the frame (pinned): what the camera thread writes and the consumer reads
+        self.depth_host = pinned_like((H, W), np.uint16)
+        self.means_host = torch.empty((nh, self.K, 2), dtype=torch.float64, pin_memory=True)
+        self.z_host = torch.empty((nh, nf), dtype=torch.float64, pin_memory=True)
+        # device buffers (names follow src/3d_bz.py:80-100)
+        self.depth_raw = GpuBuffer((H, W), np.uint16)             # depth_image_cpu's device twin: the read-out looks z up here
+        self.depth_image = GpuBuffer((H, W), np.uint16)
+        self.depth_image_mm = GpuBuffer((mh, mw), np.uint16)
+        self.depth_image_mm_groups_2 = GpuBuffer((mh, mw), np.uint16)   # stencil before grow_groups
+        self.g_info = GpuBuffer((2, 3), np.float32)
+        self.depth_image_hands = GpuBuffer((nh, H, W), np.uint16)       # depth_image_2 of each hand
+        self.labels_image = [GpuBuffer((1, h, w), np.uint16) for _ in range(nh)]
+        self.label_images = [[GpuBuffer((h, w), np.uint16) for _ in range(layered_forest.num_models)] for _ in range(nh)]
+        self.mean_shift = [MeanShift() for _ in range(nh)]
+        self.plane = GPUArray((4, 4), dtype=np.float32)
+        self.set_plane(plane)
+        self.variances = GPUArray((len(variances),), dtype=np.float32)
+        self.variances.set(np.ascontiguousarray(variances, dtype=np.float32))
+        self.stream = torch.cuda.Stream()
+        self.side = [torch.cuda.Stream() for _ in range(nh - 1)] if concurrent_hands else []
+        self.graph = None
+        self.h2d_bytes = H * W * 2
+        self.d2h_bytes = nh * (self.K * 2 + nf) * 8
+        with torch.cuda.stream(self.stream):
+            self._enqueue()                                       # eager pass: function attributes, mean-shift scratch
+        self.stream.synchronize()
+        if use_graph:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                self._enqueue()
+
+    def set_plane(self, plane):
+        """CalibratedPlane.get_mat() (src/calibrated_plane.py:33-35); lives in device memory, so a re-calibration does not
+        invalidate the captured graph."""
+        self.plane.set(np.ascontiguousarray(plane, dtype=np.float32).reshape(4, 4))
+
+    def _hand(self, i):
+        g_id, flip = self.hands[i]
+        depth_i = self.depth_image_hands.cu()[i]
+        self.ldf.run(depth_i, self.labels_image[i], self.scale, composite_flip_x=flip, label_images=self.label_images[i])
+        means = self.mean_shift[i].run_async(self.rounds, self.labels_image[i].cu(), self.K, self.variances)
+        raw = self.depth_host if self.upload == 'fused' else self.depth_raw
+        self.ops.fingertip_z(means, self.fingertips, self.ldf.labels_reduce, raw, self.pp, self.fx, self.fy, self.plane,
+                             self.z_host[i], means_copy=self.means_host[i])
+
+    def _enqueue(self):
+        import ctypes
+        if self.upload != 'fused':
+            _capi.check(_capi.load().rdf_upload_frame(ctypes.c_void_p(self.depth_host.data_ptr()), _capi.dptr(self.depth_raw.cu()),
+                                                      self.depth_host.numel() * 2, _capi.stream_ptr()))
+        self.ops.condition_depth(self.depth_host if self.upload == 'fused' else self.depth_raw, self.depth_image, self.depth_image_mm, self.pp, self.focal, self.plane, self.thresh,
+                                 self.sigma, self.k_size, self.mm_level)
+        self.grouping.make_groups_cu(self.depth_image_mm, self.depth_image_mm_groups_2, self.g_info, self.group_min_size)
+        self.ops.stencil_hands(self.depth_image, self.depth_image_mm_groups_2, self.mm_level, self.hands, self.depth_image_hands,
+                               grow=True)
+        main = torch.cuda.current_stream()
+        if self.side:
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for i, s in enumerate(self.side, start=1):
+                s.wait_event(fork)
+                with torch.cuda.stream(s):
+                    self._hand(i)
+            self._hand(0)
+            for s in self.side:
+                join = torch.cuda.Event()
+                join.record(s)
+                main.wait_event(join)
+        else:
+            for i in range(len(self.hands)):
+                self._hand(i)
+
+    def submit(self):
+        with torch.cuda.stream(self.stream):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._enqueue()
+
+    def run(self, depth_frame=None):
+        """depth_frame: np.uint16[H,W] raw camera frame (None = already written into self.depth_host).
+        Returns (means float64[2,K,2], z float64[2,num_fingertips]); NaN z = the reference's reset_positions()."""
+        if depth_frame is not None:
+            self.depth_host.view(torch.int16).numpy()[...] = np.asarray(depth_frame, dtype=np.uint16).reshape(self.H, self.W).view(np.int16)
+        self.submit()
+        self.stream.synchronize()
+        return self.means_host.numpy().copy(), self.z_host.numpy().copy()

@@ -231,3 +231,47 @@ def random_node_assignment(labels, level, seed=1234):
         nodes = np.repeat(np.repeat(tile, 32, axis=1), 32, axis=2)[:, :H, :W].copy()
     nodes[labels == 0] = -1
     return nodes
+
+
+def live_scene(H=480, W=848, seed=1234, num_hands=2):
+    """A raw camera frame of the live product (src/3d_bz.py): a tilted table seen from above, hand-sized blobs 0-5 cm above it
+    (their rims sink into the plane-clip threshold), a small distractor blob below the grouping size threshold, missing samples
+    (zeros) sprinkled everywhere and a band without data.  Units are the camera's 0.1 mm (src/rs_util.py:28).
+
+    Returns a dict: depth_raw uint16[H,W], pp float32[2], focal / fx / fy, plane float32[4,4] (camera -> plane space, row-major as
+    CalibratedPlane.get_mat() returns it; plane-space z is 0 on the table and negative above it), plane_z_threshold (product
+    default, src/3d_bz.py:54)."""
+    focal = 425.5 * W / 848.0
+    pp = np.array([W / 2.0 - 3.25, H / 2.0 + 1.75], dtype=np.float32)
+    n = np.array([0.08, -0.35, 0.93])
+    n /= np.linalg.norm(n)
+    p0 = np.array([0.0, 0.0, 4200.0])
+    xa = np.cross([0.0, 1.0, 0.0], n)
+    xa /= np.linalg.norm(xa)
+    ya = np.cross(n, xa)
+    R = np.stack([xa, ya, n])
+    plane = np.eye(4)
+    plane[:3, :3] = R
+    plane[:3, 3] = -R @ p0
+    plane = plane.astype(np.float32)
+
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    dirx, diry = (xx - float(pp[0])) / focal, (yy - float(pp[1])) / focal
+    t_table = float(n @ p0) / (n[0] * dirx + n[1] * diry + n[2])
+    h = _hash_nyx(seed & 0xFFFF, 1, H, W, seed)[0]
+    depth = t_table + ((h & np.uint32(15)).astype(np.float64) - 8.0)
+    blobs = [(0.29 * W, 0.56 * H, 0.135 * W, 0.19 * H, 520.0), (0.72 * W, 0.48 * H, 0.125 * W, 0.20 * H, 460.0),
+             (0.50 * W, 0.12 * H, 0.035 * W, 0.06 * H, 300.0)]
+    if num_hands < 2:
+        blobs = blobs[:num_hands] + blobs[2:]
+    for cx, cy, rx, ry, top in blobs:
+        r2 = ((xx - cx) / rx) ** 2 + ((yy - cy) / ry) ** 2
+        height = top * np.sqrt(np.clip(1.0 - r2, 0.0, None)) + 3.0 * np.sin(xx / 7.0) * np.cos(yy / 5.0)
+        inside = r2 < 1.0
+        depth = np.where(inside, t_table - height + ((h >> np.uint32(4)) & np.uint32(7)).astype(np.float64) - 3.0, depth)
+    depth = np.clip(np.rint(depth), 1, 65534).astype(np.uint16)
+    depth[(h % np.uint32(53)) == 0] = 0                       # missing samples
+    depth[H - max(1, H // 24):, :] = 0                        # band without data
+    depth[:, : max(1, W // 100)] = 0
+    return dict(depth_raw=depth, pp=pp, focal=np.float32(focal), fx=np.float32(focal), fy=np.float32(focal * 1.0015),
+                plane=plane, plane_z_threshold=np.float32(40.0))

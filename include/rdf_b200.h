@@ -131,6 +131,15 @@ RDF_API int rdf_layered_run(const rdf_forest_t* const* forests, int num_layers, 
                     uint16_t* const* labels_per_layer, const int32_t* conditions_dev, int n_cond,
                     uint16_t* composite_dev, int labels_reduce, float scale, void* stream);
 
+/* rdf_layered_run_hand: rdf_layered_run with one more switch for the live product's left hand, which is evaluated on an x-mirrored
+ * depth image and whose composite label image is mirrored back before mean shift (labels_image_2.set + flip_x,
+ * src/3d_bz.py:439-446): composite_flip_x != 0 writes the composite label of pixel (y,x) at (y, w-1-x).  Per-layer label images
+ * stay unmirrored, as in the reference. */
+RDF_API int rdf_layered_run_hand(const rdf_forest_t* const* forests, int num_layers, const int* filter_model,
+                         const int* filter_class, const uint16_t* depth_dev, int dim_x, int dim_y,
+                         uint16_t* const* labels_per_layer, const int32_t* conditions_dev, int n_cond,
+                         uint16_t* composite_dev, int labels_reduce, float scale, int composite_flip_x, void* stream);
+
 /* rdf_upload_frame: the live frame's host-to-device copy (depth_image.cu().set(np), src/3d_bz.py:156-157) as a kernel that
  * reads PINNED, device-mapped host memory and writes device memory; both 16-byte aligned.  In a per-frame CUDA graph it chains
  * to rdf_layered_run by programmatic dependent launch. */
@@ -156,6 +165,55 @@ RDF_API int rdf_mean_shift(const uint16_t* labels_dev, int dim_x, int dim_y, int
  * centroid y) per group (zeros for an empty group; the reference leaves the centroid unspecified there). */
 RDF_API int rdf_group_hands(const uint16_t* img_dev, int dim_x, int dim_y, float pct_thresh, uint16_t* stencil_dev,
                     float* g_info_dev, void* stream);
+
+/* ---- live-frame conditioning before the forest and fingertip read-out after it --------------
+ * rdf_condition_depth replaces, in ONE launch, deproject_points + transform_points + filter_points_by_plane +
+ * remove_missing_3d_points_from_depth_image + depth_image_2.set + gaussian_depth_filter + shrink_image
+ * (src/3d_bz.py:159-220; src/cuda/points_ops.cu:5-36,66-75,131-146,327-373,375-404; src/cuda/calibrated_plane.cu:30-45):
+ * a depth sample d > 0 at (x,y) is deprojected with (ppx, ppy, focal), moved into plane space by plane_dev (float32[4][4],
+ * row-major as the numpy matrix CalibratedPlane.get_mat() returns) and zeroed when its plane-space z > -plane_z_threshold; the
+ * k_size x k_size weights gauss_dev (float32, device; NULL = no filter, the reference's gauss_sigma <= 0.1) then smooth the
+ * result with the reference's zero-aware rule (0 when the zero samples outweigh the others, else floor of the weighted mean of
+ * the non-zero samples); depth_out_dev uint16[dim_y,dim_x] receives it and depth_mm_dev (nullable)
+ * uint16[dim_y >> mipmap_level, dim_x >> mipmap_level] its point-sampled reduction.  fp32 operation order = the reference's
+ * compiled kernels, results bit-identical.  depth_out_dev must not alias depth_in_dev (the raw frame stays intact for
+ * rdf_fingertip_z). */
+RDF_API int rdf_condition_depth(const uint16_t* depth_in_dev, int dim_x, int dim_y, float ppx, float ppy, float focal,
+                        const float* plane_dev, float plane_z_threshold, const float* gauss_dev, int k_size, int mipmap_level,
+                        uint16_t* depth_out_dev, uint16_t* depth_mm_dev, void* stream);
+
+/* rdf_grow_groups: grow_groups (src/cuda/points_ops.cu:407-438, call site src/3d_bz.py:252-259): a zero pixel takes the first
+ * non-zero value among its left, right, upper, lower neighbour. */
+RDF_API int rdf_grow_groups(const uint16_t* groups_in_dev, int dim_x, int dim_y, uint16_t* groups_out_dev, void* stream);
+
+/* rdf_stencil_hands replaces, for all hands in ONE launch, run_per_hand_pipeline's pre-processing (src/3d_bz.py:390-420):
+ * depth_image_group.fill(0) + stencil_depth_image_by_group + flip_x (or copy) + convert_0s_to_maxuint
+ * (src/cuda/points_ops.cu:118-129,441-483).  groups_dev uint16[dim_y >> level, dim_x >> level] is the group image
+ * (rdf_group_hands' stencil with grow != 0 - grow_groups is then applied on the fly - or an already grown image with grow = 0).
+ * out_dev uint16[num_hands, dim_y, dim_x]: hand i keeps the samples of depth_dev whose group is group_ids[i], mirrored in x
+ * when flip_x[i] != 0, everything else (and every 0) = 65535.  group_ids / flip_x are host arrays read at call time. */
+RDF_API int rdf_stencil_hands(const uint16_t* depth_dev, int dim_x, int dim_y, const uint16_t* groups_dev, int mipmap_level, int grow,
+                      int num_hands, const int* group_ids, const int* flip_x, uint16_t* out_dev, void* stream);
+
+/* rdf_flip_x: flip_x (src/cuda/points_ops.cu:466-483). */
+RDF_API int rdf_flip_x(const uint16_t* in_dev, int dim_x, int dim_y, uint16_t* out_dev, void* stream);
+
+/* rdf_labels_to_rgba: make_rgba_from_labels (src/cuda/points_ops.cu:258-281, call site src/3d_bz.py:448-456); colors_dev
+ * uint8[num_colors,4], rgba_dev uint8[dim_y,dim_x,4]; pixels labelled 0 / 65535 are left untouched.
+ * rdf_depth_to_rgba: make_depth_rgba (src/cuda/points_ops.cu:283-325, call site src/3d_bz.py:266-274). */
+RDF_API int rdf_labels_to_rgba(const uint16_t* labels_dev, int dim_x, int dim_y, const uint8_t* colors_dev, int num_colors,
+                       uint8_t* rgba_dev, void* stream);
+RDF_API int rdf_depth_to_rgba(const uint16_t* depth_dev, int dim_x, int dim_y, int d_min, int d_max, uint8_t* rgba_dev, void* stream);
+
+/* rdf_fingertip_z replaces the per-fingertip host loop after mean shift (src/3d_bz.py:503-522): for fingertip i with class
+ * f = fingertip_labels[i] (host array, 1-based label ids): (px,py) = int32(means[f-1]) * labels_reduce; outside the frame (or a
+ * NaN centroid) -> z_out[i] = NaN (the reference's reset_positions()); else z = raw_depth[py,px], deprojected with
+ * (ppx,ppy,fx,fy) in fp32 like rs2_deproject_pixel_to_point without distortion, z_out[i] = -(plane[2,:] . (pt,1)) in fp64.
+ * z_out float64[num_fingertips] and means_copy_out (nullable, float64[num_labels,2], receives a copy of means_dev) may be
+ * device memory or pinned host memory, so that this launch is the frame's only writer to the host. */
+RDF_API int rdf_fingertip_z(const double* means_dev, int num_labels, const int* fingertip_labels, int num_fingertips, int labels_reduce,
+                    const uint16_t* raw_depth_dev, int dim_x, int dim_y, float ppx, float ppy, float fx, float fy,
+                    const float* plane_dev, double* z_out, double* means_copy_out, void* stream);
 
 /* ---- synthetic inputs (bench / tests; bit-exact twins of rdf_b200/synth.py) -------------------------------
  * kind: 0 dense-smooth, 1 dense-noise, 2 live-mask.  Frames first_frame .. first_frame+N-1. */
