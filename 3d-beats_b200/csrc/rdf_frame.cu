@@ -325,16 +325,17 @@ __device__ __forceinline__ long long rf_astype_int32(double v) {
 __global__ void __launch_bounds__(RF_MAX_FINGERTIPS) rdf_fingertip_z_kernel(const __grid_constant__ rf_fingertip_params p) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int i = threadIdx.x;
+    const double* __restrict__ means = p.means + (size_t)blockIdx.x * 2 * p.num_labels;      // one block per image (hand)
     if (p.means_copy)
-        for (int j = i; j < 2 * p.num_labels; j += RF_MAX_FINGERTIPS) p.means_copy[j] = p.means[j];
+        for (int j = i; j < 2 * p.num_labels; j += RF_MAX_FINGERTIPS) p.means_copy[(size_t)blockIdx.x * 2 * p.num_labels + j] = means[j];
     if (i >= p.n) return;
     double out = __longlong_as_double(0x7ff8000000000000ll);
     const int f = p.idx[i];
     if (f >= 1 && f <= p.num_labels) {
         // `px *= LABELS_REDUCE` on an np.int32 scalar promotes to int64 under the NumPy the reference needs (< 1.24, Linux), so
         // a NaN centroid (INT_MIN) stays negative and resets the fingertip instead of wrapping to pixel 0
-        const long long px = rf_astype_int32(p.means[2 * (f - 1) + 0]) * (long long)p.r;
-        const long long py = rf_astype_int32(p.means[2 * (f - 1) + 1]) * (long long)p.r;
+        const long long px = rf_astype_int32(means[2 * (f - 1) + 0]) * (long long)p.r;
+        const long long py = rf_astype_int32(means[2 * (f - 1) + 1]) * (long long)p.r;
         if (!(px < 0 || py < 0 || px >= p.W || py >= p.H)) {
             const float z = (float)p.raw[(size_t)py * p.W + px];
             const float x = __fdiv_rn(__fsub_rn((float)px, p.ppx), p.fx);
@@ -345,16 +346,16 @@ __global__ void __launch_bounds__(RF_MAX_FINGERTIPS) rdf_fingertip_z_kernel(cons
             out = -acc;
         }
     }
-    p.z_out[i] = out;
+    p.z_out[(size_t)blockIdx.x * p.n + i] = out;
 }
 
-extern "C" int rdf_fingertip_z(const double* means_dev, int num_labels, const int* fingertip_labels, int num_fingertips, int labels_reduce,
+extern "C" int rdf_fingertip_z(const double* means_dev, int num_images, int num_labels, const int* fingertip_labels, int num_fingertips, int labels_reduce,
                                const uint16_t* raw_depth_dev, int dim_x, int dim_y, float ppx, float ppy, float fx, float fy,
                                const float* plane_dev, double* z_out, double* means_copy_out, void* stream) {
     RDF_REQUIRE(means_dev && fingertip_labels && raw_depth_dev && plane_dev && z_out, "rdf_fingertip_z: NULL argument");
     RDF_REQUIRE(num_fingertips >= 1 && num_fingertips <= RF_MAX_FINGERTIPS, "rdf_fingertip_z: num_fingertips=%d outside 1..%d", num_fingertips,
                 RF_MAX_FINGERTIPS);
-    RDF_REQUIRE(num_labels >= 1 && labels_reduce >= 1 && dim_x > 0 && dim_y > 0, "rdf_fingertip_z: bad shape");
+    RDF_REQUIRE(num_images >= 1 && num_labels >= 1 && labels_reduce >= 1 && dim_x > 0 && dim_y > 0, "rdf_fingertip_z: bad shape");
     rf_fingertip_params p;
     memset(&p, 0, sizeof(p));
     p.means = means_dev; p.raw = raw_depth_dev; p.plane = plane_dev; p.z_out = z_out; p.means_copy = means_copy_out;
@@ -362,7 +363,7 @@ extern "C" int rdf_fingertip_z(const double* means_dev, int num_labels, const in
     p.ppx = ppx; p.ppy = ppy; p.fx = fx; p.fy = fy;
     for (int i = 0; i < num_fingertips; i++) p.idx[i] = fingertip_labels[i];
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(1, 1, 1);
+    cfg.gridDim = dim3(num_images, 1, 1);
     cfg.blockDim = dim3(RF_MAX_FINGERTIPS, 1, 1);
     cfg.stream = rdf_stream(stream);
     cudaLaunchAttribute attr[1];

@@ -53,7 +53,9 @@ struct rdf_layered_params {
     int W, H, w, h, r;
     int tiles_x;
     float scale;
-    int flip_out;              // composite written mirrored in x (the left hand of the live product, src/3d_bz.py:439-446)
+    unsigned flip_mask;        // bit n: composite of image n is written mirrored in x (the left hand of the live product,
+                               // src/3d_bz.py:439-446)
+    size_t depth_stride, label_stride;   // elements between consecutive images of a batch (blockIdx.y)
 };
 
 template <int WARP_W, bool SCALE1, bool FORCE_EXACT>
@@ -65,9 +67,11 @@ __global__ void __launch_bounds__(256) rdf_layered_kernel(const __grid_constant_
     const int x = tile_x * 32 + (warp % WARPS_X) * WARP_W + (lane % WARP_W);
     const int y = tile_y * 8 + (warp / WARPS_X) * WARP_H + (lane / WARP_W);
     if (x >= p.w || y >= p.h) return;
-    const size_t li = (size_t)y * p.w + x;
+    const size_t lbase = (size_t)blockIdx.y * p.label_stride;
+    const size_t li = lbase + (size_t)y * p.w + x;
+    const uint16_t* __restrict__ depth = p.depth + (size_t)blockIdx.y * p.depth_stride;
     const int X = x * p.r, Y = y * p.r;
-    const unsigned d = __ldg(p.depth + (size_t)Y * p.W + X);
+    const unsigned d = __ldg(depth + (size_t)Y * p.W + X);
     const bool valid = !(d == 0u || d == RDF_NO_PIXEL);
 
     // per-layer labels of this pixel, 16 bits each, packed so the layer loop can stay rolled (RDF_MAX_LAYERS == 8)
@@ -90,7 +94,7 @@ __global__ void __launch_bounds__(256) rdf_layered_kernel(const __grid_constant_
         if (fm >= 0 && p.filter_class[i] != -1) run = run && ((int)get_lab(fm) == p.filter_class[i]);
         unsigned l = RDF_NO_PIXEL;
         if (run) {
-            l = (unsigned)rdf_eval_pixel<SCALE1, FORCE_EXACT>(p.fv[i], p.depth, p.W, p.H, X, Y, d, p.scale, nullptr);
+            l = (unsigned)rdf_eval_pixel<SCALE1, FORCE_EXACT>(p.fv[i], depth, p.W, p.H, X, Y, d, p.scale, nullptr);
             set_lab(i, l);
         }
         p.layer_labels[i][li] = (uint16_t)l;
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(256) rdf_layered_kernel(const __grid_constant_
         }
         off = tv.y;
     }
-    p.composite[p.flip_out ? (size_t)y * p.w + (p.w - 1 - x) : li] = (uint16_t)comp;
+    p.composite[((p.flip_mask >> blockIdx.y) & 1u) ? lbase + (size_t)y * p.w + (p.w - 1 - x) : li] = (uint16_t)comp;
 }
 
 // ---- latency path: one thread per (pixel, tree walk) ---------------------------------------------------------------
@@ -148,11 +152,13 @@ __global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_co
     const int x = tile_x * 8 + (lane & 7), y = tile_y * 4 + (lane >> 3);     // warp = 8x4 patch of labels pixels
     const bool inside = x < p.w && y < p.h;
     const int X = x * p.r, Y = y * p.r;
+    const uint16_t* __restrict__ depth = p.depth + (size_t)blockIdx.y * p.depth_stride;
     unsigned d = RDF_NO_PIXEL;
-    if (inside) d = __ldg(p.depth + (size_t)Y * p.W + X);
+    if (inside) d = __ldg(depth + (size_t)Y * p.W + X);
     const bool valid = inside && d != 0u && d != RDF_NO_PIXEL;
-    const size_t li = (size_t)y * p.w + x;
-    const size_t lo = p.flip_out ? (size_t)y * p.w + (p.w - 1 - x) : li;   // where the composite label of this pixel goes
+    const size_t lbase = (size_t)blockIdx.y * p.label_stride;
+    const size_t li = lbase + (size_t)y * p.w + x;
+    const size_t lo = ((p.flip_mask >> blockIdx.y) & 1u) ? lbase + (size_t)y * p.w + (p.w - 1 - x) : li;   // composite label goes here
     if (__syncthreads_or(valid) == 0) {                                   // nothing to evaluate in this tile: pre-fill only
         if (walk == 0 && inside) {
             for (int i = 0; i < p.L; i++) p.layer_labels[i][li] = (uint16_t)RDF_NO_PIXEL;
@@ -179,8 +185,8 @@ __global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_co
                 sz = __fmul_rn(p.scale, sz); sw = __fmul_rn(p.scale, sw);
             }
             int f;
-            if (FORCE_EXACT || (h.b.w & RDF_FLAG_EXACT_DIV)) f = rdf_feature_i<true>(p.depth, p.W, p.H, X, Y, df, rcp, xm, ym, sx, sy, sz, sw);
-            else f = rdf_feature_i<false>(p.depth, p.W, p.H, X, Y, df, rcp, xm, ym, sx, sy, sz, sw);
+            if (FORCE_EXACT || (h.b.w & RDF_FLAG_EXACT_DIV)) f = rdf_feature_i<true>(depth, p.W, p.H, X, Y, df, rcp, xm, ym, sx, sy, sz, sw);
+            else f = rdf_feature_i<false>(depth, p.W, p.H, X, Y, df, rcp, xm, ym, sx, sy, sz, sw);
             const bool go_left = f < h.b.x;
             const int next = go_left ? h.b.y : h.b.z;
             if (next < 0) {
@@ -258,9 +264,11 @@ __global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_co
 static int rdf_layered_run_impl(const rdf_forest_t* const* forests, int num_layers, const int* filter_model,
                                const int* filter_class, const uint16_t* depth_dev, int dim_x, int dim_y,
                                uint16_t* const* labels_per_layer, const int32_t* conditions_dev, int n_cond,
-                               uint16_t* composite_dev, int labels_reduce, float scale, int composite_flip_x, void* stream) {
+                               uint16_t* composite_dev, int labels_reduce, float scale, int num_images, unsigned flip_mask,
+                               void* stream) {
     RDF_REQUIRE(forests && filter_model && filter_class && depth_dev && labels_per_layer && conditions_dev && composite_dev,
                 "rdf_layered_run: NULL argument");
+    RDF_REQUIRE(num_images >= 1 && num_images <= 32, "rdf_layered_run: num_images=%d outside 1..32", num_images);
     RDF_REQUIRE(num_layers >= 1 && num_layers <= RDF_MAX_LAYERS, "rdf_layered_run: num_layers=%d outside 1..%d", num_layers,
                 RDF_MAX_LAYERS);
     RDF_REQUIRE(dim_x > 0 && dim_y > 0 && labels_reduce >= 1 && n_cond >= 1, "rdf_layered_run: bad shape");
@@ -290,7 +298,9 @@ static int rdf_layered_run_impl(const rdf_forest_t* const* forests, int num_laye
     if (p.w == 0 || p.h == 0) return RDF_OK;
     p.tiles_x = (p.w + 31) / 32;
     p.scale = scale;
-    p.flip_out = composite_flip_x ? 1 : 0;
+    p.flip_mask = flip_mask;
+    p.depth_stride = (size_t)dim_x * dim_y;
+    p.label_stride = (size_t)p.w * p.h;
     const int tiles_y = (p.h + 7) / 8;
     RDF_REQUIRE((int64_t)dim_x * dim_y < ((int64_t)1 << 31), "rdf_layered_run: image of %dx%d pixels is too large", dim_x, dim_y);
     const bool fast = rdf_scale_fastfloor_ok(scale) && dim_x <= 65535 && dim_y <= 65535;   // see rdf_common.cuh
@@ -313,7 +323,7 @@ static int rdf_layered_run_impl(const rdf_forest_t* const* forests, int num_laye
         const int nb = q.base.tiles_x * ((p.h + 3) / 4);
         dim3 block(32, num_walks, 1);
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(nb, 1, 1);
+        cfg.gridDim = dim3(nb, num_images, 1);
         cfg.blockDim = block;
         cfg.dynamicSmemBytes = 0;
         cfg.stream = rdf_stream(stream);
@@ -332,11 +342,11 @@ static int rdf_layered_run_impl(const rdf_forest_t* const* forests, int num_laye
     }
     const int nblk = p.tiles_x * tiles_y;
     if (!fast)
-        rdf_layered_kernel<8, false, true><<<nblk, 256, 0, rdf_stream(stream)>>>(p);
+        rdf_layered_kernel<8, false, true><<<dim3(nblk, num_images, 1), 256, 0, rdf_stream(stream)>>>(p);
     else if (scale == 1.f)
-        rdf_layered_kernel<8, true, false><<<nblk, 256, 0, rdf_stream(stream)>>>(p);
+        rdf_layered_kernel<8, true, false><<<dim3(nblk, num_images, 1), 256, 0, rdf_stream(stream)>>>(p);
     else
-        rdf_layered_kernel<8, false, false><<<nblk, 256, 0, rdf_stream(stream)>>>(p);
+        rdf_layered_kernel<8, false, false><<<dim3(nblk, num_images, 1), 256, 0, rdf_stream(stream)>>>(p);
     RDF_LAUNCH_CHECK("rdf_layered_kernel");
     return RDF_OK;
 }
@@ -346,15 +356,16 @@ extern "C" int rdf_layered_run(const rdf_forest_t* const* forests, int num_layer
                                uint16_t* const* labels_per_layer, const int32_t* conditions_dev, int n_cond,
                                uint16_t* composite_dev, int labels_reduce, float scale, void* stream) {
     return rdf_layered_run_impl(forests, num_layers, filter_model, filter_class, depth_dev, dim_x, dim_y, labels_per_layer,
-                                conditions_dev, n_cond, composite_dev, labels_reduce, scale, 0, stream);
+                                conditions_dev, n_cond, composite_dev, labels_reduce, scale, 1, 0u, stream);
 }
 
-extern "C" int rdf_layered_run_hand(const rdf_forest_t* const* forests, int num_layers, const int* filter_model,
-                                    const int* filter_class, const uint16_t* depth_dev, int dim_x, int dim_y,
-                                    uint16_t* const* labels_per_layer, const int32_t* conditions_dev, int n_cond,
-                                    uint16_t* composite_dev, int labels_reduce, float scale, int composite_flip_x, void* stream) {
+extern "C" int rdf_layered_run_batch(const rdf_forest_t* const* forests, int num_layers, const int* filter_model,
+                                     const int* filter_class, const uint16_t* depth_dev, int num_images, int dim_x, int dim_y,
+                                     uint16_t* const* labels_per_layer, const int32_t* conditions_dev, int n_cond,
+                                     uint16_t* composite_dev, int labels_reduce, float scale, unsigned composite_flip_x_mask,
+                                     void* stream) {
     return rdf_layered_run_impl(forests, num_layers, filter_model, filter_class, depth_dev, dim_x, dim_y, labels_per_layer,
-                                conditions_dev, n_cond, composite_dev, labels_reduce, scale, composite_flip_x, stream);
+                                conditions_dev, n_cond, composite_dev, labels_reduce, scale, num_images, composite_flip_x_mask, stream);
 }
 
 // ---- frame upload as a kernel ------------------------------------------------------------------------------------------

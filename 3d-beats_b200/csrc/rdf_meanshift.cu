@@ -528,6 +528,7 @@ struct rdf_ms3_params {
     double* means_out;
     int w, h, K, rounds, R;
     unsigned long long* trace;   // optional: %globaltimer stamps of class 0 / rank 0 (workspace head), phase by phase
+    // batch: cluster c serves class c % K of image c / K (labels + image * w*h, means_out + image * 2K)
 };
 #define MS3_TRACE(slot)                                                              \
     do {                                                                             \
@@ -538,7 +539,9 @@ __global__ void __launch_bounds__(MS3_THREADS, 1) rdf_mean_shift_v3_kernel(const
     cg::cluster_group cluster = cg::this_cluster();
     const int R = p.R;
     const int rank = R > 1 ? (int)cluster.block_rank() : 0;
-    const int k = blockIdx.x / R;                                            // class of this cluster (label k + 1)
+    const int ck = blockIdx.x / R;
+    const int img = ck / p.K;                                                // image of this cluster (batched launch)
+    const int k = ck - img * p.K;                                            // class of this cluster (label k + 1)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     extern __shared__ __align__(16) unsigned char ms_smem[];
@@ -549,6 +552,7 @@ __global__ void __launch_bounds__(MS3_THREADS, 1) rdf_mean_shift_v3_kernel(const
 
     asm volatile("griddepcontrol.wait;" ::: "memory");                        // programmatic dependent launch (see v2)
     const int npx = p.w * p.h;
+    const uint16_t* __restrict__ labels = p.labels + (size_t)img * npx;
     const unsigned want = (unsigned)k + 1u;
     MS3_TRACE(0);
 
@@ -559,11 +563,11 @@ __global__ void __launch_bounds__(MS3_THREADS, 1) rdf_mean_shift_v3_kernel(const
         const int q = ((g * MS3_THREADS + tid) * R + rank) * 8;
         px[g] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
         if (q + 8 <= npx) {
-            px[g] = __ldg(reinterpret_cast<const uint4*>(p.labels + q));
+            px[g] = __ldg(reinterpret_cast<const uint4*>(labels + q));
         } else if (q < npx) {
             unsigned short tmp[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) tmp[j] = q + j < npx ? __ldg(p.labels + q + j) : (unsigned short)0xffff;
+            for (int j = 0; j < 8; j++) tmp[j] = q + j < npx ? __ldg(labels + q + j) : (unsigned short)0xffff;
             px[g] = make_uint4(tmp[0] | (tmp[1] << 16), tmp[2] | (tmp[3] << 16), tmp[4] | (tmp[5] << 16), tmp[6] | (tmp[7] << 16));
         }
     }
@@ -703,8 +707,8 @@ __global__ void __launch_bounds__(MS3_THREADS, 1) rdf_mean_shift_v3_kernel(const
     }
     MS3_TRACE(14);
     if (rank == 0 && tid == 0) {
-        p.means_out[2 * k] = mx;
-        p.means_out[2 * k + 1] = my;
+        p.means_out[2 * ck] = mx;
+        p.means_out[2 * ck + 1] = my;
     }
     if (R > 1) cluster.sync();   // no CTA may exit while peers can still address its shared memory
 }
@@ -741,9 +745,10 @@ extern "C" int rdf_mean_shift_workspace_bytes(int dim_x, int dim_y, int num_labe
     return RDF_OK;
 }
 
-extern "C" int rdf_mean_shift(const uint16_t* labels_dev, int dim_x, int dim_y, int num_labels, const float* variances_dev,
-                              int rounds, double* means_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+static int rdf_mean_shift_impl(const uint16_t* labels_dev, int num_images, int dim_x, int dim_y, int num_labels, const float* variances_dev,
+                               int rounds, double* means_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
     RDF_REQUIRE(labels_dev && variances_dev && means_dev && workspace_dev, "rdf_mean_shift: NULL argument");
+    RDF_REQUIRE(num_images >= 1 && num_images <= 64, "rdf_mean_shift: num_images=%d outside 1..64", num_images);
     RDF_REQUIRE(dim_x > 0 && dim_y > 0 && dim_x <= 65535 && dim_y <= 65535, "rdf_mean_shift: bad image shape %dx%d", dim_x, dim_y);
     RDF_REQUIRE(num_labels >= 1 && num_labels <= RDF_MAX_CLASSES, "rdf_mean_shift: num_labels=%d outside 1..%d", num_labels,
                 RDF_MAX_CLASSES);
@@ -754,8 +759,19 @@ extern "C" int rdf_mean_shift(const uint16_t* labels_dev, int dim_x, int dim_y, 
     RDF_REQUIRE((int64_t)dim_x * dim_y < (1LL << 30), "rdf_mean_shift: image too large");
 
     const int npx = dim_x * dim_y;
-    // class-parallel latency path (v3 above): one small cluster per class
-    if (npx <= MS3_MAX_R * MS3_CAP && (reinterpret_cast<uintptr_t>(labels_dev) & 15u) == 0 && !getenv("RDF_MS_V1") && !getenv("RDF_MS_V2")) {
+    const bool v3_ok = npx <= MS3_MAX_R * MS3_CAP && (reinterpret_cast<uintptr_t>(labels_dev) & 15u) == 0 && !getenv("RDF_MS_V1") &&
+                       !getenv("RDF_MS_V2");
+    if (num_images > 1 && !(v3_ok && (npx & 7) == 0)) {
+        // no batched form of the other paths: one launch per image (same results, the workspace is reused in stream order)
+        for (int n = 0; n < num_images; n++) {
+            const int rc = rdf_mean_shift_impl(labels_dev + (size_t)n * npx, 1, dim_x, dim_y, num_labels, variances_dev, rounds,
+                                               means_dev + (size_t)n * num_labels * 2, workspace_dev, workspace_bytes, stream);
+            if (rc != RDF_OK) return rc;
+        }
+        return RDF_OK;
+    }
+    // class-parallel latency path (v3 above): one small cluster per class (and per image)
+    if (v3_ok) {
         // CTAs per class: enough that a CTA scans at most ~12 800 pixels (52 KB of shared memory: such CTAs can be scheduled
         // beside the still-running layered kernel under programmatic dependent launch, and the scan of the label image is
         // spread over more SMs).  Measured on cfg2 (424 x 240 labels): R = 2 / 4 / 8 -> 28.7 / 26.6 / 22.6-24.6 us per launch,
@@ -774,6 +790,12 @@ extern "C" int rdf_mean_shift(const uint16_t* labels_dev, int dim_x, int dim_y, 
         }
         if (R == 3) R = 4;                                            // cluster sizes: 1, 2, 4, 8
         if (R > 4 && R < 8) R = 8;
+        // a CTA of this kernel owns an SM: keep all clusters of a batch co-resident when the image capacity allows it (two hands
+        // x 11 classes x 8 CTAs would queue behind each other on 148 SMs; measured 114 -> 106 us per product frame with R = 4)
+        {
+            const int r_cap = (npx + MS3_CAP - 1) / MS3_CAP;
+            while (R > 1 && R / 2 >= r_cap && (long long)num_images * num_labels * R > 148) R /= 2;
+        }
         rdf_ms3_params q;
         q.labels = labels_dev; q.variances = variances_dev; q.means_out = means_dev;
         q.w = dim_x; q.h = dim_y; q.K = num_labels; q.rounds = rounds; q.R = R;
@@ -783,7 +805,7 @@ extern "C" int rdf_mean_shift(const uint16_t* labels_dev, int dim_x, int dim_y, 
         const size_t smem3 = ms3_smem_bytes(chunk);
         RDF_ENSURE_DYN_SMEM(rdf_mean_shift_v3_kernel, smem3);
         cudaLaunchConfig_t cfg3 = {};
-        cfg3.gridDim = dim3(num_labels * R, 1, 1);
+        cfg3.gridDim = dim3(num_images * num_labels * R, 1, 1);
         cfg3.blockDim = dim3(MS3_THREADS, 1, 1);
         cfg3.dynamicSmemBytes = smem3;
         cfg3.stream = rdf_stream(stream);
@@ -888,4 +910,17 @@ extern "C" int rdf_mean_shift(const uint16_t* labels_dev, int dim_x, int dim_y, 
     cfg.numAttrs = 1;
     RDF_CUDA(cudaLaunchKernelEx(&cfg, rdf_mean_shift_kernel, p));
     return RDF_OK;
+}
+
+extern "C" int rdf_mean_shift(const uint16_t* labels_dev, int dim_x, int dim_y, int num_labels, const float* variances_dev,
+                              int rounds, double* means_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    return rdf_mean_shift_impl(labels_dev, 1, dim_x, dim_y, num_labels, variances_dev, rounds, means_dev, workspace_dev, workspace_bytes,
+                               stream);
+}
+
+extern "C" int rdf_mean_shift_batch(const uint16_t* labels_dev, int num_images, int dim_x, int dim_y, int num_labels,
+                                    const float* variances_dev, int rounds, double* means_dev, void* workspace_dev,
+                                    size_t workspace_bytes, void* stream) {
+    return rdf_mean_shift_impl(labels_dev, num_images, dim_x, dim_y, num_labels, variances_dev, rounds, means_dev, workspace_dev,
+                               workspace_bytes, stream);
 }

@@ -39,11 +39,12 @@ SIGNATURES = {
     'rdf_composite': [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     'rdf_layered_run': [ctypes.POINTER(c_void_p), c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_void_p, c_int, c_int,
                         ctypes.POINTER(c_void_p), c_void_p, c_int, c_void_p, c_int, c_float, c_void_p],
-    'rdf_layered_run_hand': [ctypes.POINTER(c_void_p), c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_void_p, c_int, c_int,
-                             ctypes.POINTER(c_void_p), c_void_p, c_int, c_void_p, c_int, c_float, c_int, c_void_p],
+    'rdf_layered_run_batch': [ctypes.POINTER(c_void_p), c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_void_p, c_int, c_int, c_int,
+                              ctypes.POINTER(c_void_p), c_void_p, c_int, c_void_p, c_int, c_float, ctypes.c_uint, c_void_p],
     'rdf_upload_frame': [c_void_p, c_void_p, c_size_t, c_void_p],
     'rdf_mean_shift_workspace_bytes': [c_int, c_int, c_int, ctypes.POINTER(c_size_t)],
     'rdf_mean_shift': [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p],
+    'rdf_mean_shift_batch': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p],
     'rdf_group_hands': [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p],
     'rdf_condition_depth': [c_void_p, c_int, c_int, c_float, c_float, c_float, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p,
                             c_void_p, c_void_p],
@@ -53,7 +54,7 @@ SIGNATURES = {
     'rdf_flip_x': [c_void_p, c_int, c_int, c_void_p, c_void_p],
     'rdf_labels_to_rgba': [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p],
     'rdf_depth_to_rgba': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
-    'rdf_fingertip_z': [c_void_p, c_int, ctypes.POINTER(c_int), c_int, c_int, c_void_p, c_int, c_int, c_float, c_float, c_float,
+    'rdf_fingertip_z': [c_void_p, c_int, c_int, ctypes.POINTER(c_int), c_int, c_int, c_void_p, c_int, c_int, c_float, c_float, c_float,
                         c_float, c_void_p, c_void_p, c_void_p, c_void_p],
     'rdf_synth_depth': [c_void_p, c_int, c_int, c_int, c_int, c_uint32, c_int, c_void_p],
     'rdf_synth_forest': [c_void_p, c_int, c_int, c_int, c_uint32, c_void_p],

@@ -253,26 +253,31 @@ class LayeredDecisionForest():
         self._c_label_ptrs = (ctypes.c_void_p * L)(*[i.cu().ptr for i in self.label_images])
         self._n_cond = int(labels_conditions.shape[0])
 
-    def run(self, depth_image, labels_image, scale_factor=1., composite_flip_x=False, label_images=None):
+    def run(self, depth_image, labels_image, scale_factor=1., composite_flip_x=None, label_images=None):
         """src/decision_tree.py:233-264 in one launch.  Two keyword extensions for the live product's per-hand loop
-        (src/3d_bz.py:387-446): composite_flip_x writes the composite label image mirrored in x (the reference's
-        labels_image_2.set + flip_x after the left hand's run); label_images = another set of per-layer label buffers than
-        self.label_images, so that two hands can be evaluated concurrently on two streams."""
+        (src/3d_bz.py:387-446), which runs this once per hand: with composite_flip_x = a sequence of N flags, depth_image holds N
+        images (uint16[N,H,W]), labels_image N composite images and label_images = per-layer buffers uint16[N,h,w] (other than
+        self.label_images, which hold one image); image n's composite is written mirrored in x when its flag is set (the
+        reference's labels_image_2.set + flip_x after the left hand's run)."""
         depth = as_gpuarray(depth_image)
         labels = as_gpuarray(labels_image)
         assert depth.dtype == np.uint16 and labels.dtype == np.uint16
-        assert depth.size == self.depth_dims[0] * self.depth_dims[1], 'depth image dims'
-        assert labels.size == self.labels_dims[0] * self.labels_dims[1], 'labels image dims'
+        N = 1 if composite_flip_x is None else len(composite_flip_x)
+        assert depth.size == N * self.depth_dims[0] * self.depth_dims[1], 'depth image dims'
+        assert labels.size == N * self.labels_dims[0] * self.labels_dims[1], 'labels image dims'
         L = self.num_models
         handles = (ctypes.c_void_p * L)(*[m.handle().value for m, _, _ in self.m])
         label_ptrs = self._c_label_ptrs
         if label_images is not None:
-            assert len(label_images) == L
+            assert len(label_images) == L and all(as_gpuarray(i).size == N * self.labels_dims[0] * self.labels_dims[1] for i in label_images)
             label_ptrs = (ctypes.c_void_p * L)(*[as_gpuarray(i).ptr for i in label_images])
-        _capi.check(self.eval._lib.rdf_layered_run_hand(
-            handles, L, self._c_filter_model, self._c_filter_class, _capi.dptr(depth), self.depth_dims[1], self.depth_dims[0],
+        else:
+            assert N == 1, 'a batch needs its own per-layer label buffers (label_images=...)'
+        mask = 0 if composite_flip_x is None else sum(1 << n for n, f in enumerate(composite_flip_x) if f)
+        _capi.check(self.eval._lib.rdf_layered_run_batch(
+            handles, L, self._c_filter_model, self._c_filter_class, _capi.dptr(depth), N, self.depth_dims[1], self.depth_dims[0],
             label_ptrs, _capi.dptr(self.labels_conditions_cu.cu()), self._n_cond, _capi.dptr(labels),
-            int(self.labels_reduce), float(scale_factor), int(bool(composite_flip_x)), _capi.stream_ptr()))
+            int(self.labels_reduce), float(scale_factor), mask, _capi.stream_ptr()))
 
     def run_unfused(self, depth_image, labels_image, scale_factor=1.):
         """The reference's launch sequence verbatim (fills, one forest eval per layer, composite): kept for parity tests

@@ -18,16 +18,19 @@ class MeanShift:
         self._workspace = None
         self._variances = None
 
-    def _ensure(self, num_labels, dim_x, dim_y):
-        if self.means is None or self.means.shape != (num_labels, 2):
-            self.means = GPUArray((num_labels, 2), dtype=np.float64)
+    def _ensure(self, num_labels, dim_x, dim_y, num_images=1):
+        shape = (num_labels, 2) if num_images == 1 else (num_images, num_labels, 2)
+        if self.means is None or self.means.shape != shape:
+            self.means = GPUArray(shape, dtype=np.float64)
         need = ctypes.c_size_t()
         _capi.check(self._lib.rdf_mean_shift_workspace_bytes(dim_x, dim_y, num_labels, ctypes.byref(need)))
         if self._workspace is None or self._workspace.nbytes < need.value:
             self._workspace = GPUArray(((need.value + 3) // 4,), dtype=np.uint32)
 
-    def run_async(self, num_rounds, labels, num_labels, variances, means_out=None):
+    def run_async(self, num_rounds, labels, num_labels, variances, means_out=None, batch=False):
         """Enqueue the whole mean shift on the current stream; returns the device array float64[num_labels,2].
+        batch=True: labels is uint16[N,h,w], one independent mean shift per image in the same launch (the two hands of the
+        product frame), result float64[N,num_labels,2].
         means_out: optional pinned-host torch tensor float64[num_labels,2]; the kernel then writes the centroids straight into
         host memory (zero-copy over PCIe, 16 bytes per class), which saves the D2H copy node of a per-frame pipeline."""
         labels = as_gpuarray(labels)
@@ -40,15 +43,17 @@ class MeanShift:
             variances = self._variances
         variances = as_gpuarray(variances)
         assert variances.dtype == np.float32 and variances.size >= num_labels
-        self._ensure(num_labels, dim_x, dim_y)
+        num_images = int(labels.shape[0]) if batch else 1
+        assert labels.size == num_images * dim_x * dim_y
+        self._ensure(num_labels, dim_x, dim_y, num_images)
         if means_out is not None:
-            assert means_out.is_pinned() and means_out.dtype == torch.float64 and means_out.numel() == 2 * num_labels
+            assert means_out.is_pinned() and means_out.dtype == torch.float64 and means_out.numel() == 2 * num_labels * num_images
             out_ptr = ctypes.c_void_p(means_out.data_ptr())          # unified addressing: pinned host memory is device-visible
         else:
             out_ptr = _capi.dptr(self.means)
-        _capi.check(self._lib.rdf_mean_shift(_capi.dptr(labels), dim_x, dim_y, int(num_labels), _capi.dptr(variances),
-                                             int(num_rounds), out_ptr, _capi.dptr(self._workspace),
-                                             self._workspace.nbytes, _capi.stream_ptr()))
+        _capi.check(self._lib.rdf_mean_shift_batch(_capi.dptr(labels), num_images, dim_x, dim_y, int(num_labels), _capi.dptr(variances),
+                                                   int(num_rounds), out_ptr, _capi.dptr(self._workspace),
+                                                   self._workspace.nbytes, _capi.stream_ptr()))
         return self.means if means_out is None else means_out
 
     def run(self, num_rounds, labels, num_labels, variances):

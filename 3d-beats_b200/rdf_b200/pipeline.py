@@ -152,16 +152,21 @@ class LiveFramePipeline:
 class HandsFramePipeline:
     """One raw camera frame in, both hands' fingertip centroids and plane-space depths out: the device work that
     `App_3d_bz.tick` (src/3d_bz.py:129-300) and its two `run_per_hand_pipeline` calls (:387-522) issue as ~45 launches, 8 frame-sized
-    copies, one D2H + C++ flood fill + H2D round trip and 28 blocking mean-shift transfers is 10 launches here (upload,
-    conditioning, grouping, stencil, then per hand layered forest -> mean shift -> read-out on two concurrent branches), captured
-    once as a CUDA graph.  Defaults are the product's settings (src/3d_bz.py:49-113)."""
+    copies, one D2H + C++ flood fill + H2D round trip and 28 blocking mean-shift transfers is SEVEN launches here - upload,
+    conditioning, grouping, stencil (both hands), layered forest (both hands), mean shift (both hands), read-out (both hands) -
+    chained by programmatic dependent launch and captured once as a CUDA graph.  Defaults are the product's settings
+    (src/3d_bz.py:49-113).
+
+    batch_hands=False keeps one layered / mean-shift / read-out launch per hand (on two concurrent branches of the graph when
+    concurrent_hands is set): the reference's structure, kept for comparison (measured: 106-114 us against the batched chain)."""
 
     def __init__(self, layered_forest, variances, pp, focal, plane, fx=None, fy=None, num_rounds=6, plane_z_threshold=40.,
                  gauss_sigma=2.0, k_size=5, mm_level=3, group_min_size=0.06, fingertip_idxes=(2, 3, 4, 5, 6), scale_factor=1.,
-                 use_graph=True, concurrent_hands=True, upload='kernel'):
+                 use_graph=True, batch_hands=True, concurrent_hands=True, upload='kernel'):
         """upload: 'kernel' = upload kernel into depth_raw, then conditioning; 'fused' = the conditioning kernel (and the read-out)
-        read the pinned host frame themselves (zero-copy over PCIe), no device copy of the raw frame exists."""
+        read the pinned host frame themselves (zero-copy over PCIe; measured 4x slower: 2-byte tile reads over PCIe)."""
         self.upload = upload
+        self.batch_hands = bool(batch_hands)
         self.ldf = layered_forest
         H, W = layered_forest.depth_dims
         h, w = layered_forest.labels_dims
@@ -193,18 +198,19 @@ class HandsFramePipeline:
         self.depth_image_mm_groups_2 = GpuBuffer((mh, mw), np.uint16)   # stencil before grow_groups
         self.g_info = GpuBuffer((2, 3), np.float32)
         self.depth_image_hands = GpuBuffer((nh, H, W), np.uint16)       # depth_image_2 of each hand
-        self.labels_image = [GpuBuffer((1, h, w), np.uint16) for _ in range(nh)]
-        self.label_images = [[GpuBuffer((h, w), np.uint16) for _ in range(layered_forest.num_models)] for _ in range(nh)]
+        self.labels_images = GpuBuffer((nh, h, w), np.uint16)           # labels_image of each hand (un-mirrored)
+        self.layer_images = [GpuBuffer((nh, h, w), np.uint16) for _ in range(layered_forest.num_models)]
         self.mean_shift = [MeanShift() for _ in range(nh)]
         self.plane = GPUArray((4, 4), dtype=np.float32)
         self.set_plane(plane)
         self.variances = GPUArray((len(variances),), dtype=np.float32)
         self.variances.set(np.ascontiguousarray(variances, dtype=np.float32))
         self.stream = torch.cuda.Stream()
-        self.side = [torch.cuda.Stream() for _ in range(nh - 1)] if concurrent_hands else []
+        self.side = [torch.cuda.Stream() for _ in range(nh - 1)] if (concurrent_hands and not batch_hands) else []
         self.graph = None
         self.h2d_bytes = H * W * 2
         self.d2h_bytes = nh * (self.K * 2 + nf) * 8
+        self.kernels_per_frame = (4 if upload == 'kernel' else 3) + (3 if batch_hands else 3 * nh)
         with torch.cuda.stream(self.stream):
             self._enqueue()                                       # eager pass: function attributes, mean-shift scratch
         self.stream.synchronize()
@@ -218,13 +224,19 @@ class HandsFramePipeline:
         invalidate the captured graph."""
         self.plane.set(np.ascontiguousarray(plane, dtype=np.float32).reshape(4, 4))
 
+    def labels_image(self, i):
+        """composite label image of hand i, uint16[h,w] (device view)"""
+        return self.labels_images.cu()[i]
+
+    def _raw(self):
+        return self.depth_host if self.upload == 'fused' else self.depth_raw
+
     def _hand(self, i):
         g_id, flip = self.hands[i]
-        depth_i = self.depth_image_hands.cu()[i]
-        self.ldf.run(depth_i, self.labels_image[i], self.scale, composite_flip_x=flip, label_images=self.label_images[i])
-        means = self.mean_shift[i].run_async(self.rounds, self.labels_image[i].cu(), self.K, self.variances)
-        raw = self.depth_host if self.upload == 'fused' else self.depth_raw
-        self.ops.fingertip_z(means, self.fingertips, self.ldf.labels_reduce, raw, self.pp, self.fx, self.fy, self.plane,
+        self.ldf.run(self.depth_image_hands.cu()[i], self.labels_images.cu()[i], self.scale, composite_flip_x=[flip],
+                     label_images=[b.cu()[i] for b in self.layer_images])
+        means = self.mean_shift[i].run_async(self.rounds, self.labels_images.cu()[i], self.K, self.variances)
+        self.ops.fingertip_z(means, self.fingertips, self.ldf.labels_reduce, self._raw(), self.pp, self.fx, self.fy, self.plane,
                              self.z_host[i], means_copy=self.means_host[i])
 
     def _enqueue(self):
@@ -232,11 +244,18 @@ class HandsFramePipeline:
         if self.upload != 'fused':
             _capi.check(_capi.load().rdf_upload_frame(ctypes.c_void_p(self.depth_host.data_ptr()), _capi.dptr(self.depth_raw.cu()),
                                                       self.depth_host.numel() * 2, _capi.stream_ptr()))
-        self.ops.condition_depth(self.depth_host if self.upload == 'fused' else self.depth_raw, self.depth_image, self.depth_image_mm, self.pp, self.focal, self.plane, self.thresh,
+        self.ops.condition_depth(self._raw(), self.depth_image, self.depth_image_mm, self.pp, self.focal, self.plane, self.thresh,
                                  self.sigma, self.k_size, self.mm_level)
         self.grouping.make_groups_cu(self.depth_image_mm, self.depth_image_mm_groups_2, self.g_info, self.group_min_size)
         self.ops.stencil_hands(self.depth_image, self.depth_image_mm_groups_2, self.mm_level, self.hands, self.depth_image_hands,
                                grow=True)
+        if self.batch_hands:
+            self.ldf.run(self.depth_image_hands, self.labels_images, self.scale, composite_flip_x=[f for _, f in self.hands],
+                         label_images=self.layer_images)
+            means = self.mean_shift[0].run_async(self.rounds, self.labels_images.cu(), self.K, self.variances, batch=True)
+            self.ops.fingertip_z(means, self.fingertips, self.ldf.labels_reduce, self._raw(), self.pp, self.fx, self.fy, self.plane,
+                                 self.z_host, means_copy=self.means_host)
+            return
         main = torch.cuda.current_stream()
         if self.side:
             fork = torch.cuda.Event()

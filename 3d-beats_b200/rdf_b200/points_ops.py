@@ -126,8 +126,9 @@ class PointsOps():
         _capi.check(self._lib.rdf_depth_to_rgba(_capi.dptr(depth), w, h, int(d_min), int(d_max), _capi.dptr(rgba), _capi.stream_ptr()))
 
     def fingertip_z(self, means, fingertip_idxes, labels_reduce, raw_depth, pp, fx, fy, plane, z_out, means_copy=None):
-        """src/3d_bz.py:503-522 in one launch: z_out float64[len(fingertip_idxes)] (device array or pinned host tensor), NaN where
-        the reference resets the fingertip; means_copy (optional, same kinds) receives a copy of `means`."""
+        """src/3d_bz.py:503-522 in one launch: means float64[K,2] or [N,K,2] (N hands), z_out float64[(N,) len(fingertip_idxes)]
+        (device array or pinned host tensor), NaN where the reference resets the fingertip; means_copy (optional, same kinds)
+        receives a copy of `means`."""
         means, plane = as_gpuarray(means), as_gpuarray(plane)
         if not (isinstance(raw_depth, torch.Tensor) and not raw_depth.is_cuda):    # else: pinned host frame, read zero-copy
             raw_depth = as_gpuarray(raw_depth)
@@ -136,6 +137,7 @@ class PointsOps():
         H, W = raw_depth.shape[-2:]
         n = len(fingertip_idxes)
         idx = (ctypes.c_int * n)(*[int(i) for i in fingertip_idxes])
-        _capi.check(self._lib.rdf_fingertip_z(_capi.dptr(means), means.size // 2, idx, n, int(labels_reduce), _out_ptr(raw_depth), W, H,
+        num_images = means.shape[0] if len(means.shape) == 3 else 1
+        _capi.check(self._lib.rdf_fingertip_z(_capi.dptr(means), num_images, means.shape[-2], idx, n, int(labels_reduce), _out_ptr(raw_depth), W, H,
                                               float(pp[0]), float(pp[1]), float(fx), float(fy), _capi.dptr(plane), _out_ptr(z_out),
                                               None if means_copy is None else _out_ptr(means_copy), _capi.stream_ptr()))

@@ -346,6 +346,18 @@ def train_cfg4(level=8, iters=2):
             'what': 'rdf_train_bucket + rdf_train_hist_bucketed + rdf_train_pick_best, inputs resident'}
 
 
+def hands_frame(iters=500):
+    """SURVEY 8(f) ranks 1, 2, 4 around configs[1]: one WHOLE product frame (raw camera frame in pinned host memory -> plane clip +
+    zero-aware gaussian + 1/8 image -> hand grouping -> both hands: stencil, 2-layer forest, mean shift, fingertip depths -> pinned
+    host memory), seven launches in one CUDA-graph replay, checked against the oracles; beside it the reference's own kernels and
+    host sequence on the same GPU (tools/bench_hands_frame.py)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('bench_hands_frame', os.path.join(ROOT, 'tools', 'bench_hands_frame.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.run(iters=iters)
+
+
 def ref_gpu_rate(forest_canon, depth_dev, frames, H, W, steps=2):
     """The reference's evaluate_image_using_forest (compiled unchanged, its own launch geometry) on a sub-batch."""
     import torch
@@ -562,6 +574,10 @@ def main():
             line['train_cfg4'] = train_cfg4()
         except Exception as e:
             line['train_cfg4'] = {'error': repr(e)}
+        try:
+            line['hands_frame'] = hands_frame()
+        except Exception as e:
+            line['hands_frame'] = {'error': repr(e)}
     print(json.dumps(line), flush=True)
 
 

@@ -131,14 +131,15 @@ RDF_API int rdf_layered_run(const rdf_forest_t* const* forests, int num_layers, 
                     uint16_t* const* labels_per_layer, const int32_t* conditions_dev, int n_cond,
                     uint16_t* composite_dev, int labels_reduce, float scale, void* stream);
 
-/* rdf_layered_run_hand: rdf_layered_run with one more switch for the live product's left hand, which is evaluated on an x-mirrored
- * depth image and whose composite label image is mirrored back before mean shift (labels_image_2.set + flip_x,
- * src/3d_bz.py:439-446): composite_flip_x != 0 writes the composite label of pixel (y,x) at (y, w-1-x).  Per-layer label images
- * stay unmirrored, as in the reference. */
-RDF_API int rdf_layered_run_hand(const rdf_forest_t* const* forests, int num_layers, const int* filter_model,
-                         const int* filter_class, const uint16_t* depth_dev, int dim_x, int dim_y,
-                         uint16_t* const* labels_per_layer, const int32_t* conditions_dev, int n_cond,
-                         uint16_t* composite_dev, int labels_reduce, float scale, int composite_flip_x, void* stream);
+/* rdf_layered_run_batch: rdf_layered_run over num_images images in one launch (depth_dev uint16[N,dim_y,dim_x], every
+ * labels_per_layer[i] and composite_dev uint16[N,h,w]) - the two hands of the live product, which the reference evaluates one
+ * after the other (src/3d_bz.py:281-285).  Bit n of composite_flip_x_mask writes the composite label of image n mirrored in x,
+ * i.e. pixel (y,x) at (y, w-1-x): the left hand is evaluated on an x-mirrored depth image and its label image is mirrored back
+ * before mean shift (labels_image_2.set + flip_x, src/3d_bz.py:439-446).  Per-layer label images stay unmirrored. */
+RDF_API int rdf_layered_run_batch(const rdf_forest_t* const* forests, int num_layers, const int* filter_model,
+                          const int* filter_class, const uint16_t* depth_dev, int num_images, int dim_x, int dim_y,
+                          uint16_t* const* labels_per_layer, const int32_t* conditions_dev, int n_cond,
+                          uint16_t* composite_dev, int labels_reduce, float scale, unsigned composite_flip_x_mask, void* stream);
 
 /* rdf_upload_frame: the live frame's host-to-device copy (depth_image.cu().set(np), src/3d_bz.py:156-157) as a kernel that
  * reads PINNED, device-mapped host memory and writes device memory; both 16-byte aligned.  In a per-frame CUDA graph it chains
@@ -154,6 +155,12 @@ RDF_API int rdf_upload_frame(const void* host_pinned, void* dev, size_t bytes, v
 RDF_API int rdf_mean_shift_workspace_bytes(int dim_x, int dim_y, int num_labels, size_t* bytes);
 RDF_API int rdf_mean_shift(const uint16_t* labels_dev, int dim_x, int dim_y, int num_labels, const float* variances_dev,
                    int rounds, double* means_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* rdf_mean_shift_batch: rdf_mean_shift over num_images label images in one launch (labels_dev uint16[N,h,w], means_dev
+ * float64[N,K,2]; the two hands of the live product, src/3d_bz.py:458-462 called once per hand).  Same workspace size. */
+RDF_API int rdf_mean_shift_batch(const uint16_t* labels_dev, int num_images, int dim_x, int dim_y, int num_labels,
+                         const float* variances_dev, int rounds, double* means_dev, void* workspace_dev, size_t workspace_bytes,
+                         void* stream);
 
 /* ---- hand grouping (the step before the forest in the live product) -------------------------------
  * rdf_group_hands replaces the D2H copy + CppGrouping.make_groups (src/cpp_grouping/grouping.cpp:80-191, binding
@@ -205,14 +212,15 @@ RDF_API int rdf_labels_to_rgba(const uint16_t* labels_dev, int dim_x, int dim_y,
                        uint8_t* rgba_dev, void* stream);
 RDF_API int rdf_depth_to_rgba(const uint16_t* depth_dev, int dim_x, int dim_y, int d_min, int d_max, uint8_t* rgba_dev, void* stream);
 
-/* rdf_fingertip_z replaces the per-fingertip host loop after mean shift (src/3d_bz.py:503-522): for fingertip i with class
+/* rdf_fingertip_z replaces the per-fingertip host loop after mean shift (src/3d_bz.py:503-522), for num_images hands at once
+ * (means_dev float64[num_images,num_labels,2], all looked up in the same raw frame): for fingertip i with class
  * f = fingertip_labels[i] (host array, 1-based label ids): (px,py) = int32(means[f-1]) * labels_reduce; outside the frame (or a
  * NaN centroid) -> z_out[i] = NaN (the reference's reset_positions()); else z = raw_depth[py,px], deprojected with
  * (ppx,ppy,fx,fy) in fp32 like rs2_deproject_pixel_to_point without distortion, z_out[i] = -(plane[2,:] . (pt,1)) in fp64.
- * z_out float64[num_fingertips] and means_copy_out (nullable, float64[num_labels,2], receives a copy of means_dev) may be
- * device memory or pinned host memory, so that this launch is the frame's only writer to the host. */
-RDF_API int rdf_fingertip_z(const double* means_dev, int num_labels, const int* fingertip_labels, int num_fingertips, int labels_reduce,
-                    const uint16_t* raw_depth_dev, int dim_x, int dim_y, float ppx, float ppy, float fx, float fy,
+ * z_out float64[num_images,num_fingertips] and means_copy_out (nullable, float64[num_images,num_labels,2], receives a copy of
+ * means_dev) may be device memory or pinned host memory, so that this launch is the frame's only writer to the host. */
+RDF_API int rdf_fingertip_z(const double* means_dev, int num_images, int num_labels, const int* fingertip_labels, int num_fingertips,
+                    int labels_reduce, const uint16_t* raw_depth_dev, int dim_x, int dim_y, float ppx, float ppy, float fx, float fy,
                     const float* plane_dev, double* z_out, double* means_copy_out, void* stream);
 
 /* ---- synthetic inputs (bench / tests; bit-exact twins of rdf_b200/synth.py) -------------------------------

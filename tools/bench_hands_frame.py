@@ -103,11 +103,14 @@ def stages(pipe, n=300):
         'group_hands_us': stage(lambda: p.grouping.make_groups_cu(p.depth_image_mm, p.depth_image_mm_groups_2, p.g_info, p.group_min_size)),
         'stencil_hands_us': stage(lambda: p.ops.stencil_hands(p.depth_image, p.depth_image_mm_groups_2, p.mm_level, p.hands,
                                                               p.depth_image_hands, grow=True)),
-        'layered_one_hand_us': stage(lambda: p.ldf.run(p.depth_image_hands.cu()[0], p.labels_image[0], p.scale,
-                                                       label_images=p.label_images[0])),
-        'mean_shift_one_hand_us': stage(lambda: p.mean_shift[0].run_async(p.rounds, p.labels_image[0].cu(), p.K, p.variances)),
+        'layered_both_hands_us': stage(lambda: p.ldf.run(p.depth_image_hands, p.labels_images, p.scale, composite_flip_x=[f for _, f in p.hands],
+                                                         label_images=p.layer_images)),
+        'mean_shift_both_hands_us': stage(lambda: p.mean_shift[0].run_async(p.rounds, p.labels_images.cu(), p.K, p.variances, batch=True)),
+        'layered_one_hand_us': stage(lambda: p.ldf.run(p.depth_image_hands.cu()[0], p.labels_images.cu()[0], p.scale, composite_flip_x=[False],
+                                                       label_images=[b.cu()[0] for b in p.layer_images])),
+        'mean_shift_one_hand_us': stage(lambda: p.mean_shift[1].run_async(p.rounds, p.labels_images.cu()[0], p.K, p.variances)),
         'fingertip_z_us': stage(lambda: p.ops.fingertip_z(p.mean_shift[0].means, p.fingertips, p.ldf.labels_reduce, p.depth_raw, p.pp, p.fx,
-                                                          p.fy, p.plane, p.z_host[0], means_copy=p.means_host[0])),
+                                                          p.fy, p.plane, p.z_host, means_copy=p.means_host)),
         'note': 'each stage replayed alone as a 1-node CUDA graph, back to back; includes per-graph launch latency',
     }
 
@@ -199,25 +202,19 @@ def reference_sequence(scene, forests, cfg, variances, iters=20, r=2, rounds=6, 
     return percentiles(times), last
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--iters', type=int, default=1000)
-    ap.add_argument('--no-ref', action='store_true')
-    ap.add_argument('--upload', default='kernel', choices=['kernel', 'fused'])
-    ap.add_argument('--sequential', action='store_true', help='hands one after the other on one stream')
-    args = ap.parse_args()
-    pipe, scene, forests, cfg, variances = build(concurrent_hands=not args.sequential, upload=args.upload)
+def run(iters=1000, per_hand=None, upload='kernel', with_ref=True):
+    pipe, scene, forests, cfg, variances = build(batch_hands=per_hand is None, concurrent_hands=per_hand == 'concurrent', upload=upload)
     means, z = pipe.run(scene['depth_raw'])
     res = {'workload': 'whole product frame: raw 848x480 frame -> plane clip + 5x5 zero-aware gaussian + 1/8 image -> hand grouping -> '
                        'per hand: stencil(+mirror), L1 (T3 D16 C3) -> L2 (T3 D16 C11), labels_reduce 2, mean shift 6 rounds x 11 classes, '
                        '5 fingertip depths; one CUDA-graph replay per frame',
-           'e2e_host_frame': measure(pipe, scene, args.iters, min(100, args.iters)),
-           'h2d_bytes': pipe.h2d_bytes, 'd2h_bytes': pipe.d2h_bytes, 'kernels_per_frame': 10 if args.upload == 'kernel' else 9, 'upload': args.upload,
-           'stages': stages(pipe)}
+           'e2e_host_frame': measure(pipe, scene, iters, min(100, iters)),
+           'h2d_bytes': pipe.h2d_bytes, 'd2h_bytes': pipe.d2h_bytes, 'kernels_per_frame': pipe.kernels_per_frame, 'upload': upload,
+           'hands': per_hand or 'batched', 'stages': stages(pipe)}
     exp_means, exp_z, exp_labels = expected(scene, forests, cfg, variances)
     ok = ~np.isnan(exp_means)
     res['parity'] = {
-        'labels_bit_exact_vs_oracle': bool(all(np.array_equal(pipe.labels_image[i].cu().get()[0], exp_labels[i]) for i in range(2))),
+        'labels_bit_exact_vs_oracle': bool(all(np.array_equal(pipe.labels_image(i).get(), exp_labels[i]) for i in range(2))),
         'centroids_within_1e-5': bool(np.array_equal(np.isnan(means), np.isnan(exp_means)) and np.max(np.abs(means[ok] - exp_means[ok])) <= 1e-5),
         'fingertip_z_max_abs_err': float(np.nanmax(np.abs(z - exp_z))) if np.isfinite(exp_z).any() else None,
         'fingertip_nan_pattern_equal': bool(np.array_equal(np.isnan(z), np.isnan(exp_z))),
@@ -225,7 +222,7 @@ def main():
         'fingertips_found_per_hand': [int(np.isfinite(z[i]).sum()) for i in range(2)],
         'evaluated_pixels_per_hand': [int((pipe.depth_image_hands.cu().get()[i][::2, ::2] != 65535).sum()) for i in range(2)],
     }
-    if not args.no_ref:
+    if with_ref:
         try:
             ref = reference_sequence(scene, forests, cfg, variances)
             if ref is not None:
@@ -239,7 +236,17 @@ def main():
                                                          fingertip_z_max_abs_diff=float(np.nanmax(np.abs(rz - z))) if np.isfinite(rz).any() else None)
         except Exception as e:
             res['reference_kernels_same_gpu'] = {'error': repr(e)}
-    print(json.dumps({'hands_frame': res}))
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--iters', type=int, default=1000)
+    ap.add_argument('--no-ref', action='store_true')
+    ap.add_argument('--upload', default='kernel', choices=['kernel', 'fused'])
+    ap.add_argument('--per-hand', choices=['concurrent', 'sequential'], help='one launch per hand and stage instead of batched hands')
+    args = ap.parse_args()
+    print(json.dumps({'hands_frame': run(args.iters, args.per_hand, args.upload, not args.no_ref)}))
 
 
 if __name__ == '__main__':
