@@ -21,13 +21,16 @@
 //     w'  = same with row 3
 // and for the filter:  w_non0 += w (add), sum = fma(float(d), w, sum), taps in (dy, dx) raster order, IEEE divide, floor.
 #include "rdf_common.cuh"
+#include "rdf_fingertip.cuh"
 
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
 #define RF_TILE_W 32
-#define RF_TILE_H 8
+#define RF_TILE_H 16          // output rows per CTA; RF_ROWS_PER_THREAD of them per thread
+#define RF_THREADS_Y 8
+#define RF_ROWS_PER_THREAD (RF_TILE_H / RF_THREADS_Y)
 #define RF_MAX_K 41            // reference: PointsOps.MAX_FILTER_SIZE, src/cuda/points_ops.py:34
 #define RF_MAX_HANDS 4
 
@@ -57,7 +60,7 @@ __device__ __forceinline__ unsigned rf_clip(unsigned d, int x, int y, const rf_c
 }
 
 template <int K>   // K > 0: compile-time window; K == 0: run-time p.k; K == -1: no filter
-__global__ void __launch_bounds__(RF_TILE_W * RF_TILE_H) rdf_condition_kernel(const __grid_constant__ rf_condition_params p) {
+__global__ void __launch_bounds__(RF_TILE_W * RF_THREADS_Y) rdf_condition_kernel(const __grid_constant__ rf_condition_params p) {
     // may have been scheduled early behind the kernel that produces the frame (rdf_upload_frame)
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -73,46 +76,56 @@ __global__ void __launch_bounds__(RF_TILE_W * RF_TILE_H) rdf_condition_kernel(co
     const float m20 = __ldg(p.plane + 8), m21 = __ldg(p.plane + 9), m22 = __ldg(p.plane + 10), m23 = __ldg(p.plane + 11);
     const float m30 = __ldg(p.plane + 12), m31 = __ldg(p.plane + 13), m32 = __ldg(p.plane + 14), m33 = __ldg(p.plane + 15);
     if (K >= 0)
-        for (int i = tid; i < k * k; i += RF_TILE_W * RF_TILE_H) wk[i] = __ldg(p.gauss + i);
-    for (int i = tid; i < tw * th; i += RF_TILE_W * RF_TILE_H) {
+        for (int i = tid; i < k * k; i += RF_TILE_W * RF_THREADS_Y) wk[i] = __ldg(p.gauss + i);
+    bool any = false;
+    for (int i = tid; i < tw * th; i += RF_TILE_W * RF_THREADS_Y) {
         const int cy = i / tw, cx = i - cy * tw;
         const int gx = x0 - R + cx, gy = y0 - R + cy;
         int v = -1;
         if (gx >= 0 && gx < p.W && gy >= 0 && gy < p.H)
             v = (int)rf_clip(__ldg(p.in + (size_t)gy * p.W + gx), gx, gy, p, m20, m21, m22, m23, m30, m31, m32, m33);
         tile[i] = v;
+        any = any || v > 0;
     }
-    __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    if (x >= p.W || y >= p.H) return;
-    unsigned v;
-    if (K < 0) {
-        v = (unsigned)tile[threadIdx.y * tw + threadIdx.x];
-    } else {
-        float w0 = 0.f, wn = 0.f, s = 0.f;
+    // most of a live frame is table (clipped to 0): a tile whose whole neighbourhood is 0 filters to 0 whatever the weights
+    // (w_non0 = sum = 0: either w_0 > 0 selects 0, or 0/0 = NaN floors to 0)
+    const bool all_zero = __syncthreads_or(any) == 0;
+    const int x = x0 + threadIdx.x;
+    if (x >= p.W) return;
 #pragma unroll
-        for (int dy = 0; dy < k; dy++) {
+    for (int rr = 0; rr < RF_ROWS_PER_THREAD; rr++) {
+        const int ty = threadIdx.y + rr * RF_THREADS_Y, y = y0 + ty;
+        if (y >= p.H) break;
+        unsigned v;
+        if (K < 0) {
+            v = (unsigned)tile[ty * tw + threadIdx.x];
+        } else if (all_zero) {
+            v = 0u;
+        } else {
+            // branch-free taps: a tap outside the image contributes weight 0 to every sum, a zero sample adds +0 to the non-zero
+            // sums and a non-zero sample +0 to the zero sum - x + 0 == x exactly, so the sums equal the reference's skipping loop
+            float w0 = 0.f, wn = 0.f, s = 0.f;
 #pragma unroll
-            for (int dx = 0; dx < k; dx++) {
-                const int d = tile[(threadIdx.y + dy) * tw + threadIdx.x + dx];
-                const float w = wk[dy * k + dx];
-                if (d < 0) continue;
-                if (d == 0) {
-                    w0 = __fadd_rn(w0, w);
-                } else {
-                    wn = __fadd_rn(wn, w);
-                    s = __fmaf_rn((float)d, w, s);
+            for (int dy = 0; dy < k; dy++) {
+#pragma unroll
+                for (int dx = 0; dx < k; dx++) {
+                    const int d = tile[(ty + dy) * tw + threadIdx.x + dx];
+                    const float w = wk[dy * k + dx];
+                    const float wz = d == 0 ? w : 0.f, wp = d > 0 ? w : 0.f;
+                    w0 = __fadd_rn(w0, wz);
+                    wn = __fadd_rn(wn, wp);
+                    s = __fmaf_rn((float)max(d, 0), wp, s);
                 }
             }
+            v = w0 > wn ? 0u : (__float2uint_rd(__fdiv_rn(s, wn)) & 0xffffu);
         }
-        v = w0 > wn ? 0u : (__float2uint_rd(__fdiv_rn(s, wn)) & 0xffffu);
-    }
-    p.out[(size_t)y * p.W + x] = (uint16_t)v;
-    if (p.mm) {
-        const int f = 1 << p.level;
-        if ((x & (f - 1)) == 0 && (y & (f - 1)) == 0) {
-            const int xo = x >> p.level, yo = y >> p.level, wo = p.W >> p.level, ho = p.H >> p.level;
-            if (xo < wo && yo < ho) p.mm[(size_t)yo * wo + xo] = (uint16_t)v;
+        p.out[(size_t)y * p.W + x] = (uint16_t)v;
+        if (p.mm) {
+            const int f = 1 << p.level;
+            if ((x & (f - 1)) == 0 && (y & (f - 1)) == 0) {
+                const int xo = x >> p.level, yo = y >> p.level, wo = p.W >> p.level, ho = p.H >> p.level;
+                if (xo < wo && yo < ho) p.mm[(size_t)yo * wo + xo] = (uint16_t)v;
+            }
         }
     }
 }
@@ -131,7 +144,7 @@ extern "C" int rdf_condition_depth(const uint16_t* depth_in_dev, int dim_x, int 
     p.ppx = ppx; p.ppy = ppy; p.focal = focal; p.thresh = plane_z_threshold;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((dim_x + RF_TILE_W - 1) / RF_TILE_W, (dim_y + RF_TILE_H - 1) / RF_TILE_H, 1);
-    cfg.blockDim = dim3(RF_TILE_W, RF_TILE_H, 1);
+    cfg.blockDim = dim3(RF_TILE_W, RF_THREADS_Y, 1);
     cfg.stream = rdf_stream(stream);
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -182,25 +195,57 @@ struct rf_stencil_params {
     int flip[RF_MAX_HANDS];
 };
 
+template <bool VEC8>   // VEC8: W % 8 == 0, every thread moves 8 consecutive pixels with 128-bit accesses
 __global__ void __launch_bounds__(256) rdf_stencil_hands_kernel(const __grid_constant__ rf_stencil_params p) {
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    constexpr int PX = VEC8 ? 8 : 1;
+    const int x = (blockIdx.x * 64 + (threadIdx.x & 63)) * PX;
     const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
     if (x >= p.W || y >= p.H) return;
     const int gw = p.W >> p.level, gh = p.H >> p.level;
-    const int gx = x >> p.level, gy = y >> p.level;
+    const int gy = y >> p.level;
+    unsigned d[PX], g[PX];
+    if (VEC8) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.depth + (size_t)y * p.W + x));
+        d[0] = v.x & 0xffffu; d[1] = v.x >> 16; d[2] = v.y & 0xffffu; d[3] = v.y >> 16;
+        d[4] = v.z & 0xffffu; d[5] = v.z >> 16; d[6] = v.w & 0xffffu; d[7] = v.w >> 16;
+    } else {
+        d[0] = __ldg(p.depth + (size_t)y * p.W + x);
+    }
     // stencil_depth_image_by_group reads the group image through Array2d: outside -> 0, which matches no hand
-    unsigned g = 0u;
-    if (gx < gw && gy < gh) g = p.grow ? rf_grown(p.groups, gw, gh, gx, gy) : (unsigned)__ldg(p.groups + gy * gw + gx);
-    const unsigned d = __ldg(p.depth + (size_t)y * p.W + x);
+#pragma unroll
+    for (int j = 0; j < PX; j++) {
+        const int gx = (x + j) >> p.level;
+        if (j > 0 && gx == ((x + j - 1) >> p.level)) {
+            g[j] = g[j - 1];
+            continue;
+        }
+        g[j] = 0u;
+        if (gx < gw && gy < gh) g[j] = p.grow ? rf_grown(p.groups, gw, gh, gx, gy) : (unsigned)__ldg(p.groups + gy * gw + gx);
+    }
 #pragma unroll
     for (int hnd = 0; hnd < RF_MAX_HANDS; hnd++) {
         if (hnd >= p.num_hands) break;
-        unsigned v = ((int)g == p.group[hnd]) ? d : 0u;
-        if (v == 0u) v = RDF_NO_PIXEL;                                   // convert_0s_to_maxuint
-        const int xo = p.flip[hnd] ? p.W - 1 - x : x;                    // flip_x
-        p.out[((size_t)hnd * p.H + y) * p.W + xo] = (uint16_t)v;
+        unsigned v[PX];
+#pragma unroll
+        for (int j = 0; j < PX; j++) {
+            v[j] = ((int)g[j] == p.group[hnd]) ? d[j] : 0u;
+            if (v[j] == 0u) v[j] = RDF_NO_PIXEL;                         // convert_0s_to_maxuint
+        }
+        uint16_t* row = p.out + ((size_t)hnd * p.H + y) * p.W;
+        if (VEC8) {
+            uint4 o;
+            if (p.flip[hnd]) {                                           // flip_x: pixel x + j lands at W - 1 - x - j
+                o = make_uint4(v[7] | (v[6] << 16), v[5] | (v[4] << 16), v[3] | (v[2] << 16), v[1] | (v[0] << 16));
+                *reinterpret_cast<uint4*>(row + (p.W - 8 - x)) = o;
+            } else {
+                o = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+                *reinterpret_cast<uint4*>(row + x) = o;
+            }
+        } else {
+            row[p.flip[hnd] ? p.W - 1 - x : x] = (uint16_t)v[0];
+        }
     }
 }
 
@@ -215,7 +260,8 @@ extern "C" int rdf_stencil_hands(const uint16_t* depth_dev, int dim_x, int dim_y
     p.W = dim_x; p.H = dim_y; p.level = mipmap_level; p.grow = grow ? 1 : 0; p.num_hands = num_hands;
     for (int i = 0; i < num_hands; i++) { p.group[i] = group_ids[i]; p.flip[i] = flip_x[i] ? 1 : 0; }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((dim_x + 63) / 64, (dim_y + 3) / 4, 1);
+    const bool vec8 = (dim_x & 7) == 0 && ((uintptr_t)depth_dev & 15u) == 0 && ((uintptr_t)out_dev & 15u) == 0;
+    cfg.gridDim = dim3(((vec8 ? dim_x / 8 : dim_x) + 63) / 64, (dim_y + 3) / 4, 1);
     cfg.blockDim = dim3(256, 1, 1);
     cfg.stream = rdf_stream(stream);
     cudaLaunchAttribute attr[1];
@@ -223,7 +269,8 @@ extern "C" int rdf_stencil_hands(const uint16_t* depth_dev, int dim_x, int dim_y
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = getenv("RDF_NO_PDL") ? 0 : 1;
-    RDF_CUDA(cudaLaunchKernelEx(&cfg, rdf_stencil_hands_kernel, p));
+    if (vec8) RDF_CUDA(cudaLaunchKernelEx(&cfg, rdf_stencil_hands_kernel<true>, p));
+    else RDF_CUDA(cudaLaunchKernelEx(&cfg, rdf_stencil_hands_kernel<false>, p));
     return RDF_OK;
 }
 
@@ -304,64 +351,50 @@ extern "C" int rdf_depth_to_rgba(const uint16_t* depth_dev, int dim_x, int dim_y
 // x86 gives); outside the frame -> "reset" (NaN here);  z = raw_depth[py, px];  pt = rs2_deproject_pixel_to_point (no distortion:
 // fp32 x = (px-ppx)/fx, y = (py-ppy)/fy, point = (z*x, z*y, z));  -(plane[2,:] . (pt, 1)) accumulated in fp64 like numpy's matmul
 // of a float32 matrix with a Python-float vector.
-#define RF_MAX_FINGERTIPS 32
 struct rf_fingertip_params {
     const double* means;
-    const uint16_t* raw;
-    const float* plane;
-    double* z_out;
-    double* means_copy;        // nullable
-    int num_labels, n, r, W, H;
-    float ppx, ppy, fx, fy;
-    int idx[RF_MAX_FINGERTIPS];
+    int num_labels;
+    rf_fingertip_spec ft;
 };
-
-__device__ __forceinline__ long long rf_astype_int32(double v) {
-    // numpy float64 -> int32 on x86-64 (cvttsd2si): truncation toward zero, NaN / out of range -> INT_MIN
-    if (!(v > -2147483649.0 && v < 2147483648.0)) return -2147483648ll;
-    return (long long)(int)v;
-}
 
 __global__ void __launch_bounds__(RF_MAX_FINGERTIPS) rdf_fingertip_z_kernel(const __grid_constant__ rf_fingertip_params p) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int i = threadIdx.x;
     const double* __restrict__ means = p.means + (size_t)blockIdx.x * 2 * p.num_labels;      // one block per image (hand)
-    if (p.means_copy)
-        for (int j = i; j < 2 * p.num_labels; j += RF_MAX_FINGERTIPS) p.means_copy[(size_t)blockIdx.x * 2 * p.num_labels + j] = means[j];
-    if (i >= p.n) return;
+    if (p.ft.means_copy)
+        for (int j = i; j < 2 * p.num_labels; j += RF_MAX_FINGERTIPS) p.ft.means_copy[(size_t)blockIdx.x * 2 * p.num_labels + j] = means[j];
+    if (i >= p.ft.n) return;
     double out = __longlong_as_double(0x7ff8000000000000ll);
-    const int f = p.idx[i];
-    if (f >= 1 && f <= p.num_labels) {
-        // `px *= LABELS_REDUCE` on an np.int32 scalar promotes to int64 under the NumPy the reference needs (< 1.24, Linux), so
-        // a NaN centroid (INT_MIN) stays negative and resets the fingertip instead of wrapping to pixel 0
-        const long long px = rf_astype_int32(means[2 * (f - 1) + 0]) * (long long)p.r;
-        const long long py = rf_astype_int32(means[2 * (f - 1) + 1]) * (long long)p.r;
-        if (!(px < 0 || py < 0 || px >= p.W || py >= p.H)) {
-            const float z = (float)p.raw[(size_t)py * p.W + px];
-            const float x = __fdiv_rn(__fsub_rn((float)px, p.ppx), p.fx);
-            const float y = __fdiv_rn(__fsub_rn((float)py, p.ppy), p.fy);
-            const double ptx = (double)__fmul_rn(z, x), pty = (double)__fmul_rn(z, y), ptz = (double)z;
-            const double m0 = (double)p.plane[8], m1 = (double)p.plane[9], m2 = (double)p.plane[10], m3 = (double)p.plane[11];
-            const double acc = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(m0, ptx), __dmul_rn(m1, pty)), __dmul_rn(m2, ptz)), m3);
-            out = -acc;
-        }
-    }
-    p.z_out[(size_t)blockIdx.x * p.n + i] = out;
+    const int f = p.ft.idx[i];
+    if (f >= 1 && f <= p.num_labels) out = rf_fingertip_eval(p.ft, means[2 * (f - 1) + 0], means[2 * (f - 1) + 1]);
+    p.ft.z_out[(size_t)blockIdx.x * p.ft.n + i] = out;
 }
 
-extern "C" int rdf_fingertip_z(const double* means_dev, int num_images, int num_labels, const int* fingertip_labels, int num_fingertips, int labels_reduce,
-                               const uint16_t* raw_depth_dev, int dim_x, int dim_y, float ppx, float ppy, float fx, float fy,
-                               const float* plane_dev, double* z_out, double* means_copy_out, void* stream) {
-    RDF_REQUIRE(means_dev && fingertip_labels && raw_depth_dev && plane_dev && z_out, "rdf_fingertip_z: NULL argument");
-    RDF_REQUIRE(num_fingertips >= 1 && num_fingertips <= RF_MAX_FINGERTIPS, "rdf_fingertip_z: num_fingertips=%d outside 1..%d", num_fingertips,
+int rdf_fingertip_fill_spec(rf_fingertip_spec* ft, const char* who, const int* fingertip_labels, int num_fingertips, int labels_reduce,
+                            const uint16_t* raw_depth_dev, int dim_x, int dim_y, float ppx, float ppy, float fx, float fy,
+                            const float* plane_dev, double* z_out, double* means_copy_out) {
+    RDF_REQUIRE(fingertip_labels && raw_depth_dev && plane_dev && z_out, "%s: NULL argument", who);
+    RDF_REQUIRE(num_fingertips >= 1 && num_fingertips <= RF_MAX_FINGERTIPS, "%s: num_fingertips=%d outside 1..%d", who, num_fingertips,
                 RF_MAX_FINGERTIPS);
-    RDF_REQUIRE(num_images >= 1 && num_labels >= 1 && labels_reduce >= 1 && dim_x > 0 && dim_y > 0, "rdf_fingertip_z: bad shape");
+    RDF_REQUIRE(labels_reduce >= 1 && dim_x > 0 && dim_y > 0, "%s: bad shape", who);
+    memset(ft, 0, sizeof(*ft));
+    ft->raw = raw_depth_dev; ft->plane = plane_dev; ft->z_out = z_out; ft->means_copy = means_copy_out;
+    ft->n = num_fingertips; ft->r = labels_reduce; ft->W = dim_x; ft->H = dim_y;
+    ft->ppx = ppx; ft->ppy = ppy; ft->fx = fx; ft->fy = fy;
+    for (int i = 0; i < num_fingertips; i++) ft->idx[i] = fingertip_labels[i];
+    return RDF_OK;
+}
+
+extern "C" int rdf_fingertip_z(const double* means_dev, int num_images, int num_labels, const int* fingertip_labels, int num_fingertips,
+                               int labels_reduce, const uint16_t* raw_depth_dev, int dim_x, int dim_y, float ppx, float ppy, float fx,
+                               float fy, const float* plane_dev, double* z_out, double* means_copy_out, void* stream) {
+    RDF_REQUIRE(means_dev && num_images >= 1 && num_labels >= 1, "rdf_fingertip_z: bad means argument");
     rf_fingertip_params p;
-    memset(&p, 0, sizeof(p));
-    p.means = means_dev; p.raw = raw_depth_dev; p.plane = plane_dev; p.z_out = z_out; p.means_copy = means_copy_out;
-    p.num_labels = num_labels; p.n = num_fingertips; p.r = labels_reduce; p.W = dim_x; p.H = dim_y;
-    p.ppx = ppx; p.ppy = ppy; p.fx = fx; p.fy = fy;
-    for (int i = 0; i < num_fingertips; i++) p.idx[i] = fingertip_labels[i];
+    p.means = means_dev;
+    p.num_labels = num_labels;
+    const int rc = rdf_fingertip_fill_spec(&p.ft, "rdf_fingertip_z", fingertip_labels, num_fingertips, labels_reduce, raw_depth_dev, dim_x,
+                                           dim_y, ppx, ppy, fx, fy, plane_dev, z_out, means_copy_out);
+    if (rc != RDF_OK) return rc;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(num_images, 1, 1);
     cfg.blockDim = dim3(RF_MAX_FINGERTIPS, 1, 1);

@@ -9,6 +9,8 @@
 // only mandatory host round trip of the live frame.
 #include "rdf_common.cuh"
 
+#include <stdlib.h>
+
 #define GR_THREADS 1024
 #define GR_MAX_PIXELS 16384
 
@@ -20,6 +22,18 @@ __device__ __forceinline__ int gr_find(volatile int* parent, int i) {
         if (gp != p) parent[i] = gp;        // benign race: any ancestor is a valid parent
         i = p;
         p = gp;
+    }
+    return i;
+}
+
+// read-only find for the flatten pass: there every thread overwrites its OWN entry with the root, so a concurrent path-halving
+// write of another thread (an ancestor that is not the root) landing afterwards would undo it - seen as a few pixels missing from
+// the stencil on tall narrow images, where chains are long (tools/stress_grouping.py)
+__device__ __forceinline__ int gr_find_ro(const volatile int* parent, int i) {
+    int p = parent[i];
+    while (p != i) {
+        i = p;
+        p = parent[i];
     }
     return i;
 }
@@ -44,47 +58,78 @@ __device__ __forceinline__ void gr_unite(int* parent, int a, int b) {
 }
 
 // Phases (one CTA):
-//   1. one thread per ROW: horizontal runs of non-zero pixels; every pixel of a run points at the run's first pixel, which
-//      holds the run's length and x-sum (so later statistics cost one atomic per run, not per pixel: a 1500-pixel hand blob
-//      would otherwise serialise 1500 shared-memory atomics on one address);
+//   1. a bit mask of the non-zero pixels per row (warp ballots), then one thread per PIXEL: the start of its horizontal run from
+//      the mask (count-leading-zeros over at most a few words); every pixel of a run points at the run's first pixel, which holds
+//      the run's length and x-sum (so later statistics cost one atomic per run, not per pixel: a 1500-pixel hand blob would
+//      otherwise serialise 1500 shared-memory atomics on one address);
 //   2. vertical unions between runs of neighbouring rows (only where an overlap segment starts);
 //   3. run statistics are added to their component's root; 4. every pixel is pointed at its root;
-//   5. selection over roots; 6. y-sums of the two selected components (one thread per row); 7. stencil + g_info.
+//   5. selection over roots; 6. y-sums of the two selected components (warp-reduced, one atomic per warp); 7. stencil + g_info.
 __global__ void __launch_bounds__(GR_THREADS) rdf_group_hands_kernel(const uint16_t* __restrict__ img, int w, int h, float pct_thresh,
                                                                      uint16_t* __restrict__ stencil, float* __restrict__ g_info) {
+    // the kernel that consumes the stencil may be scheduled now (it waits for this grid itself); this grid may have been
+    // scheduled early behind the kernel that produces img
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     extern __shared__ int gr_smem[];
     const int N = w * h;
+    const int wpr = (w + 31) >> 5;      // mask words per row
     int* parent = gr_smem;              // [N]  -1 = background
     int* cnt = parent + N;              // [N]  run length at run starts, then component size at roots
     int* sumx = cnt + N;                // [N]  run x-sum at run starts, then component x-sum at roots
+    unsigned* rowmask = reinterpret_cast<unsigned*>(sumx + N);   // [h * wpr]  bit x & 31 of word x >> 5: pixel x of the row is non-zero
     __shared__ unsigned long long best[2];      // per side: size << 32 | ~root
     __shared__ int sumy[2];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (int i = tid; i < N; i += GR_THREADS) {
-        parent[i] = __ldg(img + i) != 0 ? i : -1;                  // grouping.cpp:107-108
-        cnt[i] = 0;
-        sumx[i] = 0;
+    for (int t = warp; t < h * wpr; t += GR_THREADS / 32) {        // 1a. masks (grouping.cpp:107-108: non-zero = foreground)
+        const int y = t / wpr, x = (t - y * wpr) * 32 + lane;
+        const unsigned m = __ballot_sync(0xffffffffu, x < w && __ldg(img + y * w + x) != 0);
+        if (lane == 0) rowmask[t] = m;
     }
     if (tid < 2) {
         best[tid] = 0ull;
         sumy[tid] = 0;
     }
     __syncthreads();
-    for (int y = tid; y < h; y += GR_THREADS) {                    // 1. runs
-        int start = -1;
-        for (int x = 0; x <= w; x++) {
-            const bool fg = x < w && parent[y * w + x] >= 0;
-            if (fg) {
-                if (start < 0) start = x;
-                parent[y * w + x] = y * w + start;
-            } else if (start >= 0) {
-                const int len = x - start;
-                cnt[y * w + start] = len;
-                sumx[y * w + start] = (start + x - 1) * len / 2;   // start + ... + (x - 1)
-                start = -1;
+    for (int i = tid; i < N; i += GR_THREADS) {                    // 1b. runs
+        const int y = i / w, x = i - y * w;
+        const unsigned* rm = rowmask + y * wpr;
+        const int wi = x >> 5, bi = x & 31;
+        int par = -1, len = 0, sx = 0;
+        if ((rm[wi] >> bi) & 1u) {
+            // start of my run: one past the last background pixel to my left
+            int start = 0;
+            unsigned z = ~rm[wi] & ((1u << bi) - 1u);
+            for (int wj = wi;;) {
+                if (z) {
+                    start = wj * 32 + 32 - __clz(z);
+                    break;
+                }
+                if (--wj < 0) break;
+                z = ~rm[wj];
+            }
+            par = y * w + start;
+            if (start == x) {                                      // first pixel of the run: its end = first background pixel to my right
+                int end = w;
+                unsigned z2 = ~rm[wi] & ~((2u << bi) - 1u);        // bits above bi (2u << 31 wraps to 0: mask becomes all ones -> none)
+                if (bi == 31) z2 = 0u;
+                for (int wj = wi;;) {
+                    if (z2) {
+                        end = wj * 32 + __ffs(z2) - 1;
+                        break;
+                    }
+                    if (++wj >= wpr) break;
+                    z2 = ~rm[wj];
+                }
+                if (end > w) end = w;                              // mask bits beyond the row are background
+                len = end - start;
+                sx = (start + end - 1) * len / 2;                  // start + ... + (end - 1)
             }
         }
+        parent[i] = par;
+        cnt[i] = len;
+        sumx[i] = sx;
     }
     __syncthreads();
     for (int i = tid; i < N - w; i += GR_THREADS) {                // 2. 4-connectivity (grouping.cpp:82-87): down edges between runs
@@ -104,7 +149,7 @@ __global__ void __launch_bounds__(GR_THREADS) rdf_group_hands_kernel(const uint1
         }
     }
     __syncthreads();
-    for (int i = tid; i < N; i += GR_THREADS) parent[i] = parent[i] < 0 ? -1 : gr_find(parent, i);   // 4. flatten
+    for (int i = tid; i < N; i += GR_THREADS) parent[i] = parent[i] < 0 ? -1 : gr_find_ro(parent, i);   // 4. flatten
     __syncthreads();
     for (int i = tid; i < N; i += GR_THREADS) {                    // 5. selection
         if (parent[i] != i) continue;                              // roots only, one per component
@@ -122,19 +167,17 @@ __global__ void __launch_bounds__(GR_THREADS) rdf_group_hands_kernel(const uint1
         seln[s] = (int)(best[s] >> 32);
         sel[s] = seln[s] ? (int)(0xffffffffu - (unsigned)(best[s] & 0xffffffffull)) : -2;
     }
-    for (int y = tid; y < h; y += GR_THREADS) {                    // 6. y-sums
-        int c0 = 0, c1 = 0;
-        for (int x = 0; x < w; x++) {
-            const int r = parent[y * w + x];
-            c0 += r == sel[0];
-            c1 += r == sel[1];
+    for (int i0 = 0; i0 < N; i0 += GR_THREADS) {                   // 6. y-sums + 7. stencil (src/3d_bz.py:243-250)
+        const int i = i0 + tid;
+        const int r = i < N ? parent[i] : -1;
+        const int y = i / w;
+        const int c0 = __reduce_add_sync(0xffffffffu, r == sel[0] ? y : 0);
+        const int c1 = __reduce_add_sync(0xffffffffu, r == sel[1] ? y : 0);
+        if (lane == 0) {
+            if (c0) atomicAdd(&sumy[0], c0);
+            if (c1) atomicAdd(&sumy[1], c1);
         }
-        if (c0) atomicAdd(&sumy[0], y * c0);
-        if (c1) atomicAdd(&sumy[1], y * c1);
-    }
-    for (int i = tid; i < N; i += GR_THREADS) {                    // 7. stencil (src/3d_bz.py:243-250)
-        const int r = parent[i];
-        stencil[i] = (unsigned short)(r < 0 ? 0 : r == sel[0] ? 1 : r == sel[1] ? 2 : 0);
+        if (i < N) stencil[i] = (unsigned short)(r < 0 ? 0 : r == sel[0] ? 1 : r == sel[1] ? 2 : 0);
     }
     __syncthreads();
     if (tid < 2) {
@@ -161,9 +204,22 @@ extern "C" int rdf_group_hands(const uint16_t* img_dev, int dim_x, int dim_y, fl
                       "1/8-resolution image)", dim_x, dim_y, GR_MAX_PIXELS);
         return RDF_ERR_UNSUPPORTED;
     }
-    const size_t smem = sizeof(int) * 3 * (size_t)n;
-    if (smem > 48 * 1024) RDF_ENSURE_DYN_SMEM(rdf_group_hands_kernel, sizeof(int) * 3 * GR_MAX_PIXELS);
-    rdf_group_hands_kernel<<<1, GR_THREADS, smem, rdf_stream(stream)>>>(img_dev, dim_x, dim_y, pct_thresh, stencil_dev, g_info_dev);
-    RDF_LAUNCH_CHECK("rdf_group_hands_kernel");
+    const size_t smem = sizeof(int) * (3 * (size_t)n + (size_t)dim_y * ((dim_x + 31) / 32));
+    if (smem > 227 * 1024) {                                       // only degenerate shapes (16384 rows of one pixel)
+        rdf_set_error("rdf_group_hands: %dx%d needs %zu bytes of shared memory", dim_x, dim_y, smem);
+        return RDF_ERR_UNSUPPORTED;
+    }
+    if (smem > 48 * 1024) RDF_ENSURE_DYN_SMEM(rdf_group_hands_kernel, smem);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1, 1, 1);
+    cfg.blockDim = dim3(GR_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = rdf_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = getenv("RDF_NO_PDL") ? 0 : 1;
+    RDF_CUDA(cudaLaunchKernelEx(&cfg, rdf_group_hands_kernel, img_dev, dim_x, dim_y, pct_thresh, stencil_dev, g_info_dev));
     return RDF_OK;
 }

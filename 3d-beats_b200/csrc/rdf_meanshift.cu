@@ -14,6 +14,7 @@
 #include <stdlib.h>
 
 #include "rdf_common.cuh"
+#include "rdf_fingertip.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -529,6 +530,8 @@ struct rdf_ms3_params {
     int w, h, K, rounds, R;
     unsigned long long* trace;   // optional: %globaltimer stamps of class 0 / rank 0 (workspace head), phase by phase
     // batch: cluster c serves class c % K of image c / K (labels + image * w*h, means_out + image * 2K)
+    int with_fingertips;         // fused read-out (rdf_mean_shift_fingertips): ft below is valid
+    rf_fingertip_spec ft;
 };
 #define MS3_TRACE(slot)                                                              \
     do {                                                                             \
@@ -709,6 +712,14 @@ __global__ void __launch_bounds__(MS3_THREADS, 1) rdf_mean_shift_v3_kernel(const
     if (rank == 0 && tid == 0) {
         p.means_out[2 * ck] = mx;
         p.means_out[2 * ck + 1] = my;
+        if (p.with_fingertips) {                                             // src/3d_bz.py:503-522 for the fingertips of this class
+            if (p.ft.means_copy) {
+                p.ft.means_copy[2 * ck] = mx;
+                p.ft.means_copy[2 * ck + 1] = my;
+            }
+            for (int j = 0; j < p.ft.n; j++)
+                if (p.ft.idx[j] == k + 1) p.ft.z_out[(size_t)img * p.ft.n + j] = rf_fingertip_eval(p.ft, mx, my);
+        }
     }
     if (R > 1) cluster.sync();   // no CTA may exit while peers can still address its shared memory
 }
@@ -745,8 +756,15 @@ extern "C" int rdf_mean_shift_workspace_bytes(int dim_x, int dim_y, int num_labe
     return RDF_OK;
 }
 
+// defined in rdf_frame.cu
+int rdf_fingertip_fill_spec(rf_fingertip_spec* ft, const char* who, const int* fingertip_labels, int num_fingertips, int labels_reduce,
+                            const uint16_t* raw_depth_dev, int dim_x, int dim_y, float ppx, float ppy, float fx, float fy,
+                            const float* plane_dev, double* z_out, double* means_copy_out);
+
+// returns RDF_OK and sets *fused_done when the fused read-out ran inside the launch
 static int rdf_mean_shift_impl(const uint16_t* labels_dev, int num_images, int dim_x, int dim_y, int num_labels, const float* variances_dev,
-                               int rounds, double* means_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+                               int rounds, double* means_dev, void* workspace_dev, size_t workspace_bytes, void* stream,
+                               const rf_fingertip_spec* ft = nullptr, bool* fused_done = nullptr) {
     RDF_REQUIRE(labels_dev && variances_dev && means_dev && workspace_dev, "rdf_mean_shift: NULL argument");
     RDF_REQUIRE(num_images >= 1 && num_images <= 64, "rdf_mean_shift: num_images=%d outside 1..64", num_images);
     RDF_REQUIRE(dim_x > 0 && dim_y > 0 && dim_x <= 65535 && dim_y <= 65535, "rdf_mean_shift: bad image shape %dx%d", dim_x, dim_y);
@@ -765,7 +783,8 @@ static int rdf_mean_shift_impl(const uint16_t* labels_dev, int num_images, int d
         // no batched form of the other paths: one launch per image (same results, the workspace is reused in stream order)
         for (int n = 0; n < num_images; n++) {
             const int rc = rdf_mean_shift_impl(labels_dev + (size_t)n * npx, 1, dim_x, dim_y, num_labels, variances_dev, rounds,
-                                               means_dev + (size_t)n * num_labels * 2, workspace_dev, workspace_bytes, stream);
+                                               means_dev + (size_t)n * num_labels * 2, workspace_dev, workspace_bytes, stream, nullptr,
+                                               nullptr);
             if (rc != RDF_OK) return rc;
         }
         return RDF_OK;
@@ -800,6 +819,12 @@ static int rdf_mean_shift_impl(const uint16_t* labels_dev, int num_images, int d
         q.labels = labels_dev; q.variances = variances_dev; q.means_out = means_dev;
         q.w = dim_x; q.h = dim_y; q.K = num_labels; q.rounds = rounds; q.R = R;
         q.trace = getenv("RDF_MS_TRACE") ? reinterpret_cast<unsigned long long*>(workspace_dev) : nullptr;
+        q.with_fingertips = 0;
+        if (ft) {
+            q.with_fingertips = 1;
+            q.ft = *ft;
+            if (fused_done) *fused_done = true;
+        }
         const int ngroups = (npx + 7) / 8;
         const int chunk = ((ngroups + R - 1) / R) * 8;                // pixels (= upper bound of entries) per CTA
         const size_t smem3 = ms3_smem_bytes(chunk);
@@ -923,4 +948,24 @@ extern "C" int rdf_mean_shift_batch(const uint16_t* labels_dev, int num_images, 
                                     size_t workspace_bytes, void* stream) {
     return rdf_mean_shift_impl(labels_dev, num_images, dim_x, dim_y, num_labels, variances_dev, rounds, means_dev, workspace_dev,
                                workspace_bytes, stream);
+}
+
+extern "C" int rdf_mean_shift_fingertips(const uint16_t* labels_dev, int num_images, int dim_x, int dim_y, int num_labels,
+                                         const float* variances_dev, int rounds, double* means_dev, void* workspace_dev,
+                                         size_t workspace_bytes, const int* fingertip_labels, int num_fingertips, int labels_reduce,
+                                         const uint16_t* raw_depth_dev, int raw_dim_x, int raw_dim_y, float ppx, float ppy, float fx,
+                                         float fy, const float* plane_dev, double* z_out, double* means_copy_out, void* stream) {
+    rf_fingertip_spec ft;
+    int rc = rdf_fingertip_fill_spec(&ft, "rdf_mean_shift_fingertips", fingertip_labels, num_fingertips, labels_reduce, raw_depth_dev,
+                                     raw_dim_x, raw_dim_y, ppx, ppy, fx, fy, plane_dev, z_out, means_copy_out);
+    if (rc != RDF_OK) return rc;
+    // a fingertip id outside 1..num_labels has no class cluster to write it: handled by the separate read-out
+    bool all_inside = true;
+    for (int i = 0; i < num_fingertips; i++) all_inside = all_inside && fingertip_labels[i] >= 1 && fingertip_labels[i] <= num_labels;
+    bool fused = false;
+    rc = rdf_mean_shift_impl(labels_dev, num_images, dim_x, dim_y, num_labels, variances_dev, rounds, means_dev, workspace_dev,
+                             workspace_bytes, stream, all_inside ? &ft : nullptr, &fused);
+    if (rc != RDF_OK || fused) return rc;
+    return rdf_fingertip_z(means_dev, num_images, num_labels, fingertip_labels, num_fingertips, labels_reduce, raw_depth_dev, raw_dim_x,
+                           raw_dim_y, ppx, ppy, fx, fy, plane_dev, z_out, means_copy_out, stream);
 }

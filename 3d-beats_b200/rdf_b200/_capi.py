@@ -56,6 +56,9 @@ SIGNATURES = {
     'rdf_depth_to_rgba': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     'rdf_fingertip_z': [c_void_p, c_int, c_int, ctypes.POINTER(c_int), c_int, c_int, c_void_p, c_int, c_int, c_float, c_float, c_float,
                         c_float, c_void_p, c_void_p, c_void_p, c_void_p],
+    'rdf_mean_shift_fingertips': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_size_t,
+                                  ctypes.POINTER(c_int), c_int, c_int, c_void_p, c_int, c_int, c_float, c_float, c_float, c_float,
+                                  c_void_p, c_void_p, c_void_p, c_void_p],
     'rdf_synth_depth': [c_void_p, c_int, c_int, c_int, c_int, c_uint32, c_int, c_void_p],
     'rdf_synth_forest': [c_void_p, c_int, c_int, c_int, c_uint32, c_void_p],
     'rdf_selftest_fastdiv': [ctypes.c_uint, c_uint32, ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)],

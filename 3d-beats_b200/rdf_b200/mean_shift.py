@@ -27,7 +27,15 @@ class MeanShift:
         if self._workspace is None or self._workspace.nbytes < need.value:
             self._workspace = GPUArray(((need.value + 3) // 4,), dtype=np.uint32)
 
-    def run_async(self, num_rounds, labels, num_labels, variances, means_out=None, batch=False):
+    def run_fingertips_async(self, num_rounds, labels, num_labels, variances, fingertip_idxes, labels_reduce, raw_depth, pp, fx, fy, plane,
+                             z_out, means_copy=None, batch=False):
+        """Mean shift + the product's fingertip read-out (src/3d_bz.py:458-462 + 503-522) in one launch (rdf_mean_shift_fingertips):
+        z_out float64[(N,) len(fingertip_idxes)] and means_copy (optional) may be device arrays or pinned host tensors; raw_depth is the
+        raw camera frame (device array or pinned host tensor).  Returns the device means like run_async."""
+        return self.run_async(num_rounds, labels, num_labels, variances, batch=batch,
+                              _fingertips=(fingertip_idxes, labels_reduce, raw_depth, pp, fx, fy, plane, z_out, means_copy))
+
+    def run_async(self, num_rounds, labels, num_labels, variances, means_out=None, batch=False, _fingertips=None):
         """Enqueue the whole mean shift on the current stream; returns the device array float64[num_labels,2].
         batch=True: labels is uint16[N,h,w], one independent mean shift per image in the same launch (the two hands of the
         product frame), result float64[N,num_labels,2].
@@ -51,6 +59,24 @@ class MeanShift:
             out_ptr = ctypes.c_void_p(means_out.data_ptr())          # unified addressing: pinned host memory is device-visible
         else:
             out_ptr = _capi.dptr(self.means)
+        if _fingertips is not None:
+            from .points_ops import _out_ptr
+            idxes, r, raw, pp, fx, fy, plane, z_out, means_copy = _fingertips
+            assert means_out is None
+            if not (isinstance(raw, torch.Tensor) and not raw.is_cuda):
+                raw = as_gpuarray(raw)
+                assert raw.dtype == np.uint16
+            plane = as_gpuarray(plane)
+            assert plane.dtype == np.float32 and plane.size == 16
+            H, W = raw.shape[-2:]
+            n = len(idxes)
+            idx = (ctypes.c_int * n)(*[int(i) for i in idxes])
+            _capi.check(self._lib.rdf_mean_shift_fingertips(
+                _capi.dptr(labels), num_images, dim_x, dim_y, int(num_labels), _capi.dptr(variances), int(num_rounds), out_ptr,
+                _capi.dptr(self._workspace), self._workspace.nbytes, idx, n, int(r), _out_ptr(raw), W, H, float(pp[0]), float(pp[1]),
+                float(fx), float(fy), _capi.dptr(plane), _out_ptr(z_out), None if means_copy is None else _out_ptr(means_copy),
+                _capi.stream_ptr()))
+            return self.means
         _capi.check(self._lib.rdf_mean_shift_batch(_capi.dptr(labels), num_images, dim_x, dim_y, int(num_labels), _capi.dptr(variances),
                                                    int(num_rounds), out_ptr, _capi.dptr(self._workspace),
                                                    self._workspace.nbytes, _capi.stream_ptr()))

@@ -152,8 +152,8 @@ class LiveFramePipeline:
 class HandsFramePipeline:
     """One raw camera frame in, both hands' fingertip centroids and plane-space depths out: the device work that
     `App_3d_bz.tick` (src/3d_bz.py:129-300) and its two `run_per_hand_pipeline` calls (:387-522) issue as ~45 launches, 8 frame-sized
-    copies, one D2H + C++ flood fill + H2D round trip and 28 blocking mean-shift transfers is SEVEN launches here - upload,
-    conditioning, grouping, stencil (both hands), layered forest (both hands), mean shift (both hands), read-out (both hands) -
+    copies, one D2H + C++ flood fill + H2D round trip and 28 blocking mean-shift transfers is SIX launches here - upload,
+    conditioning, grouping, stencil (both hands), layered forest (both hands), mean shift + read-out (both hands) -
     chained by programmatic dependent launch and captured once as a CUDA graph.  Defaults are the product's settings
     (src/3d_bz.py:49-113).
 
@@ -162,11 +162,12 @@ class HandsFramePipeline:
 
     def __init__(self, layered_forest, variances, pp, focal, plane, fx=None, fy=None, num_rounds=6, plane_z_threshold=40.,
                  gauss_sigma=2.0, k_size=5, mm_level=3, group_min_size=0.06, fingertip_idxes=(2, 3, 4, 5, 6), scale_factor=1.,
-                 use_graph=True, batch_hands=True, concurrent_hands=True, upload='kernel'):
+                 use_graph=True, batch_hands=True, concurrent_hands=True, upload='kernel', fused_readout=True):
         """upload: 'kernel' = upload kernel into depth_raw, then conditioning; 'fused' = the conditioning kernel (and the read-out)
         read the pinned host frame themselves (zero-copy over PCIe; measured 4x slower: 2-byte tile reads over PCIe)."""
         self.upload = upload
         self.batch_hands = bool(batch_hands)
+        self.fused_readout = bool(fused_readout) and self.batch_hands     # read-out inside the mean-shift launch
         self.ldf = layered_forest
         H, W = layered_forest.depth_dims
         h, w = layered_forest.labels_dims
@@ -210,7 +211,7 @@ class HandsFramePipeline:
         self.graph = None
         self.h2d_bytes = H * W * 2
         self.d2h_bytes = nh * (self.K * 2 + nf) * 8
-        self.kernels_per_frame = (4 if upload == 'kernel' else 3) + (3 if batch_hands else 3 * nh)
+        self.kernels_per_frame = (4 if upload == 'kernel' else 3) + ((2 if self.fused_readout else 3) if batch_hands else 3 * nh)
         with torch.cuda.stream(self.stream):
             self._enqueue()                                       # eager pass: function attributes, mean-shift scratch
         self.stream.synchronize()
@@ -252,6 +253,11 @@ class HandsFramePipeline:
         if self.batch_hands:
             self.ldf.run(self.depth_image_hands, self.labels_images, self.scale, composite_flip_x=[f for _, f in self.hands],
                          label_images=self.layer_images)
+            if self.fused_readout:
+                self.mean_shift[0].run_fingertips_async(self.rounds, self.labels_images.cu(), self.K, self.variances, self.fingertips,
+                                                        self.ldf.labels_reduce, self._raw(), self.pp, self.fx, self.fy, self.plane,
+                                                        self.z_host, means_copy=self.means_host, batch=True)
+                return
             means = self.mean_shift[0].run_async(self.rounds, self.labels_images.cu(), self.K, self.variances, batch=True)
             self.ops.fingertip_z(means, self.fingertips, self.ldf.labels_reduce, self._raw(), self.pp, self.fx, self.fy, self.plane,
                                  self.z_host, means_copy=self.means_host)

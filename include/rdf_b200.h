@@ -223,6 +223,15 @@ RDF_API int rdf_fingertip_z(const double* means_dev, int num_images, int num_lab
                     int labels_reduce, const uint16_t* raw_depth_dev, int dim_x, int dim_y, float ppx, float ppy, float fx, float fy,
                     const float* plane_dev, double* z_out, double* means_copy_out, void* stream);
 
+/* rdf_mean_shift_fingertips = rdf_mean_shift_batch + rdf_fingertip_z in ONE launch where the class-parallel mean-shift kernel
+ * applies (the thread that finishes a class' centroid reads its fingertip depth out at once), otherwise the two launches; same
+ * results as the two calls.  raw_dim_x / raw_dim_y: size of the raw frame (labels image size x labels_reduce in the product). */
+RDF_API int rdf_mean_shift_fingertips(const uint16_t* labels_dev, int num_images, int dim_x, int dim_y, int num_labels,
+                              const float* variances_dev, int rounds, double* means_dev, void* workspace_dev, size_t workspace_bytes,
+                              const int* fingertip_labels, int num_fingertips, int labels_reduce, const uint16_t* raw_depth_dev,
+                              int raw_dim_x, int raw_dim_y, float ppx, float ppy, float fx, float fy, const float* plane_dev,
+                              double* z_out, double* means_copy_out, void* stream);
+
 /* ---- synthetic inputs (bench / tests; bit-exact twins of rdf_b200/synth.py) -------------------------------
  * kind: 0 dense-smooth, 1 dense-noise, 2 live-mask.  Frames first_frame .. first_frame+N-1. */
 RDF_API int rdf_synth_depth(uint16_t* depth_dev, int kind, int num_images, int dim_x, int dim_y, uint32_t seed,

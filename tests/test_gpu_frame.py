@@ -234,10 +234,11 @@ def _expected_frame(scene, forests, cfg, variances, r, rounds, fingertips, scale
     return np.stack(means), np.stack(zs), labels, depth, grown
 
 
-@pytest.mark.parametrize('use_graph,batch,concurrent,num_hands,upload', [
-    (True, True, False, 2, 'kernel'), (False, True, False, 2, 'kernel'), (True, False, True, 2, 'kernel'), (False, False, False, 2, 'kernel'),
-    (True, True, False, 1, 'fused'), (True, True, False, 0, 'kernel'), (True, False, True, 1, 'fused')])
-def test_hands_frame_pipeline_matches_reference_sequence(tmp_path, use_graph, batch, concurrent, num_hands, upload):
+@pytest.mark.parametrize('use_graph,batch,concurrent,num_hands,upload,fused_readout', [
+    (True, True, False, 2, 'kernel', True), (False, True, False, 2, 'kernel', False), (True, False, True, 2, 'kernel', False),
+    (False, False, False, 2, 'kernel', False), (True, True, False, 1, 'fused', True), (True, True, False, 0, 'kernel', True),
+    (True, False, True, 1, 'fused', False), (True, True, False, 2, 'kernel', False)])
+def test_hands_frame_pipeline_matches_reference_sequence(tmp_path, use_graph, batch, concurrent, num_hands, upload, fused_readout):
     import torch
     from rdf_b200 import synth
     from rdf_b200 import decision_tree as dt
@@ -251,7 +252,7 @@ def test_hands_frame_pipeline_matches_reference_sequence(tmp_path, use_graph, ba
         scene['depth_raw'] = np.where(scene['depth_raw'] > 0, np.uint16(60000), np.uint16(0)).astype(np.uint16)  # far below the table
     fingertips = (2, 3, 4, 5, 6)
     pipe = HandsFramePipeline(ldf, variances, scene['pp'], scene['focal'], scene['plane'], fx=scene['fx'], fy=scene['fy'],
-                              fingertip_idxes=fingertips, use_graph=use_graph, batch_hands=batch, concurrent_hands=concurrent, upload=upload)
+                              fingertip_idxes=fingertips, use_graph=use_graph, batch_hands=batch, concurrent_hands=concurrent, upload=upload, fused_readout=fused_readout)
     for rep in range(2):                                              # replay twice: no state may leak between frames
         means, z = pipe.run(scene['depth_raw'])
     exp_means, exp_z, exp_labels, exp_depth, exp_grown = _expected_frame(scene, forests, cfg, variances, r, 6, fingertips)

@@ -19,7 +19,7 @@ def _ours(img, thresh):
     return to_np(st), gi.cpu().numpy()
 
 
-@pytest.mark.parametrize('h,w', [(60, 106), (30, 53), (120, 128), (7, 9)])
+@pytest.mark.parametrize('h,w', [(60, 106), (30, 53), (120, 128), (7, 9), (4, 300), (1, 500), (16, 1000), (200, 33), (33, 65), (64, 32)])
 @pytest.mark.parametrize('seed', range(4))
 def test_matches_reference_cpp_and_oracle(h, w, seed):
     from oracle import grouping_oracle as go

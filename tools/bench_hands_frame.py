@@ -109,6 +109,9 @@ def stages(pipe, n=300):
         'layered_one_hand_us': stage(lambda: p.ldf.run(p.depth_image_hands.cu()[0], p.labels_images.cu()[0], p.scale, composite_flip_x=[False],
                                                        label_images=[b.cu()[0] for b in p.layer_images])),
         'mean_shift_one_hand_us': stage(lambda: p.mean_shift[1].run_async(p.rounds, p.labels_images.cu()[0], p.K, p.variances)),
+        'mean_shift_fingertips_both_hands_us': stage(lambda: p.mean_shift[0].run_fingertips_async(
+            p.rounds, p.labels_images.cu(), p.K, p.variances, p.fingertips, p.ldf.labels_reduce, p.depth_raw, p.pp, p.fx, p.fy, p.plane,
+            p.z_host, means_copy=p.means_host, batch=True)),
         'fingertip_z_us': stage(lambda: p.ops.fingertip_z(p.mean_shift[0].means, p.fingertips, p.ldf.labels_reduce, p.depth_raw, p.pp, p.fx,
                                                           p.fy, p.plane, p.z_host, means_copy=p.means_host)),
         'note': 'each stage replayed alone as a 1-node CUDA graph, back to back; includes per-graph launch latency',
@@ -202,8 +205,9 @@ def reference_sequence(scene, forests, cfg, variances, iters=20, r=2, rounds=6, 
     return percentiles(times), last
 
 
-def run(iters=1000, per_hand=None, upload='kernel', with_ref=True):
-    pipe, scene, forests, cfg, variances = build(batch_hands=per_hand is None, concurrent_hands=per_hand == 'concurrent', upload=upload)
+def run(iters=1000, per_hand=None, upload='kernel', with_ref=True, fused_readout=True):
+    pipe, scene, forests, cfg, variances = build(batch_hands=per_hand is None, concurrent_hands=per_hand == 'concurrent', upload=upload,
+                                                 fused_readout=fused_readout)
     means, z = pipe.run(scene['depth_raw'])
     res = {'workload': 'whole product frame: raw 848x480 frame -> plane clip + 5x5 zero-aware gaussian + 1/8 image -> hand grouping -> '
                        'per hand: stencil(+mirror), L1 (T3 D16 C3) -> L2 (T3 D16 C11), labels_reduce 2, mean shift 6 rounds x 11 classes, '
@@ -244,9 +248,10 @@ def main():
     ap.add_argument('--iters', type=int, default=1000)
     ap.add_argument('--no-ref', action='store_true')
     ap.add_argument('--upload', default='kernel', choices=['kernel', 'fused'])
+    ap.add_argument('--separate-readout', action='store_true')
     ap.add_argument('--per-hand', choices=['concurrent', 'sequential'], help='one launch per hand and stage instead of batched hands')
     args = ap.parse_args()
-    print(json.dumps({'hands_frame': run(args.iters, args.per_hand, args.upload, not args.no_ref)}))
+    print(json.dumps({'hands_frame': run(args.iters, args.per_hand, args.upload, not args.no_ref, not args.separate_readout)}))
 
 
 if __name__ == '__main__':
