@@ -63,14 +63,22 @@ __device__ __forceinline__ void gr_unite(int* parent, int a, int b) {
 //      the run's length and x-sum (so later statistics cost one atomic per run, not per pixel: a 1500-pixel hand blob would
 //      otherwise serialise 1500 shared-memory atomics on one address);
 //   2. vertical unions between runs of neighbouring rows (only where an overlap segment starts);
-//   3. run statistics are added to their component's root; 4. every pixel is pointed at its root;
+//   3. run statistics are added to their component's root (path-halving finds shorten every chain);
 //   5. selection over roots; 6. y-sums of the two selected components (warp-reduced, one atomic per warp); 7. stencil + g_info.
+#define GR_TRACE(slot)                                                    \
+    do {                                                                  \
+        if (trace && threadIdx.x == 0) trace[slot] = clock64();           \
+    } while (0)
+
 __global__ void __launch_bounds__(GR_THREADS) rdf_group_hands_kernel(const uint16_t* __restrict__ img, int w, int h, float pct_thresh,
-                                                                     uint16_t* __restrict__ stencil, float* __restrict__ g_info) {
+                                                                     uint16_t* __restrict__ stencil, float* __restrict__ g_info,
+                                                                     long long* __restrict__ trace /* debug: RDF_GR_TRACE */) {
+    GR_TRACE(0);
     // the kernel that consumes the stencil may be scheduled now (it waits for this grid itself); this grid may have been
     // scheduled early behind the kernel that produces img
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    GR_TRACE(15);
     extern __shared__ int gr_smem[];
     const int N = w * h;
     const int wpr = (w + 31) >> 5;      // mask words per row
@@ -82,16 +90,29 @@ __global__ void __launch_bounds__(GR_THREADS) rdf_group_hands_kernel(const uint1
     __shared__ int sumy[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (int t = warp; t < h * wpr; t += GR_THREADS / 32) {        // 1a. masks (grouping.cpp:107-108: non-zero = foreground)
-        const int y = t / wpr, x = (t - y * wpr) * 32 + lane;
-        const unsigned m = __ballot_sync(0xffffffffu, x < w && __ldg(img + y * w + x) != 0);
-        if (lane == 0) rowmask[t] = m;
+    // 1a. masks (grouping.cpp:107-108: non-zero = foreground).  Eight words per warp and trip with all loads issued before the
+    // first ballot: the image comes out of L2 / HBM, one latency per trip instead of one per word
+    for (int t0 = warp; t0 < h * wpr; t0 += 8 * (GR_THREADS / 32)) {
+        unsigned v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int t = t0 + j * (GR_THREADS / 32);
+            const int y = t / wpr, x = (t - y * wpr) * 32 + lane;
+            v[j] = (t < h * wpr && x < w) ? (unsigned)__ldg(img + y * w + x) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int t = t0 + j * (GR_THREADS / 32);
+            const unsigned m = __ballot_sync(0xffffffffu, v[j] != 0u);
+            if (lane == 0 && t < h * wpr) rowmask[t] = m;
+        }
     }
     if (tid < 2) {
         best[tid] = 0ull;
         sumy[tid] = 0;
     }
     __syncthreads();
+    GR_TRACE(1);
     for (int i = tid; i < N; i += GR_THREADS) {                    // 1b. runs
         const int y = i / w, x = i - y * w;
         const unsigned* rm = rowmask + y * wpr;
@@ -132,6 +153,7 @@ __global__ void __launch_bounds__(GR_THREADS) rdf_group_hands_kernel(const uint1
         sumx[i] = sx;
     }
     __syncthreads();
+    GR_TRACE(2);
     for (int i = tid; i < N - w; i += GR_THREADS) {                // 2. 4-connectivity (grouping.cpp:82-87): down edges between runs
         if (parent[i] < 0 || parent[i + w] < 0) continue;
         const int x = i % w;
@@ -139,6 +161,7 @@ __global__ void __launch_bounds__(GR_THREADS) rdf_group_hands_kernel(const uint1
         gr_unite(parent, i, i + w);
     }
     __syncthreads();
+    GR_TRACE(3);
     for (int i = tid; i < N; i += GR_THREADS) {                    // 3. run statistics -> root (roots keep their own run in place)
         const int len = cnt[i];
         if (len == 0) continue;
@@ -149,8 +172,9 @@ __global__ void __launch_bounds__(GR_THREADS) rdf_group_hands_kernel(const uint1
         }
     }
     __syncthreads();
-    for (int i = tid; i < N; i += GR_THREADS) parent[i] = parent[i] < 0 ? -1 : gr_find_ro(parent, i);   // 4. flatten
-    __syncthreads();
+    GR_TRACE(4);
+    // (4. no flatten pass: the stencil pass below walks to the root itself; after the path-halving finds of pass 3 that is a hop or
+    //  two, and nothing writes `parent` any more, so no pass can undo another's result - see gr_find_ro)
     for (int i = tid; i < N; i += GR_THREADS) {                    // 5. selection
         if (parent[i] != i) continue;                              // roots only, one per component
         const int n = cnt[i];
@@ -161,6 +185,7 @@ __global__ void __launch_bounds__(GR_THREADS) rdf_group_hands_kernel(const uint1
         atomicMax(&best[side], ((unsigned long long)(unsigned)n << 32) | (unsigned long long)(0xffffffffu - (unsigned)i));
     }
     __syncthreads();
+    GR_TRACE(6);
     int sel[2], seln[2];
 #pragma unroll
     for (int s = 0; s < 2; s++) {
@@ -169,7 +194,7 @@ __global__ void __launch_bounds__(GR_THREADS) rdf_group_hands_kernel(const uint1
     }
     for (int i0 = 0; i0 < N; i0 += GR_THREADS) {                   // 6. y-sums + 7. stencil (src/3d_bz.py:243-250)
         const int i = i0 + tid;
-        const int r = i < N ? parent[i] : -1;
+        const int r = (i < N && parent[i] >= 0) ? gr_find_ro(parent, i) : -1;
         const int y = i / w;
         const int c0 = __reduce_add_sync(0xffffffffu, r == sel[0] ? y : 0);
         const int c1 = __reduce_add_sync(0xffffffffu, r == sel[1] ? y : 0);
@@ -180,6 +205,7 @@ __global__ void __launch_bounds__(GR_THREADS) rdf_group_hands_kernel(const uint1
         if (i < N) stencil[i] = (unsigned short)(r < 0 ? 0 : r == sel[0] ? 1 : r == sel[1] ? 2 : 0);
     }
     __syncthreads();
+    GR_TRACE(7);
     if (tid < 2) {
         const int s = tid;
         float n = 0.f, cx = 0.f, cy = 0.f;
@@ -192,6 +218,7 @@ __global__ void __launch_bounds__(GR_THREADS) rdf_group_hands_kernel(const uint1
         g_info[3 * s + 1] = cx;
         g_info[3 * s + 2] = cy;
     }
+    GR_TRACE(8);
 }
 
 extern "C" int rdf_group_hands(const uint16_t* img_dev, int dim_x, int dim_y, float pct_thresh, uint16_t* stencil_dev,
@@ -220,6 +247,17 @@ extern "C" int rdf_group_hands(const uint16_t* img_dev, int dim_x, int dim_y, fl
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = getenv("RDF_NO_PDL") ? 0 : 1;
-    RDF_CUDA(cudaLaunchKernelEx(&cfg, rdf_group_hands_kernel, img_dev, dim_x, dim_y, pct_thresh, stencil_dev, g_info_dev));
+    static long long* trace_dev = nullptr;                         // debug aid: RDF_GR_TRACE=1 prints clock64 deltas per phase (synchronises)
+    const bool tracing = getenv("RDF_GR_TRACE") != nullptr;
+    if (tracing && !trace_dev) RDF_CUDA(cudaMalloc(&trace_dev, 16 * sizeof(long long)));
+    long long* trace_arg = tracing ? trace_dev : nullptr;
+    RDF_CUDA(cudaLaunchKernelEx(&cfg, rdf_group_hands_kernel, img_dev, dim_x, dim_y, pct_thresh, stencil_dev, g_info_dev, trace_arg));
+    if (tracing) {
+        long long t[16];
+        RDF_CUDA(cudaMemcpy(t, trace_dev, sizeof(t), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "rdf_group_hands phases (cycles): wait %lld |", t[15] - t[0]);
+        for (int i = 1; i <= 8; i++) fprintf(stderr, " %lld", t[i] - (i == 1 ? t[15] : t[i - 1]));
+        fprintf(stderr, "\n");
+    }
     return RDF_OK;
 }
