@@ -110,3 +110,23 @@ def test_plain_c_program_device_path(tmp_path):
     exe = _build_c_smoke(tmp_path)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and 'device path' in out.stdout, out.stdout + out.stderr
+
+
+def test_frame_entry_points_validate_arguments_without_gpu():
+    """The live-frame entry points refuse bad arguments with a message, on a box without a GPU."""
+    from rdf_b200 import _capi
+    lib = _capi.load()
+    p16 = ctypes.c_void_p(16)
+    assert lib.rdf_condition_depth(None, 8, 8, 0., 0., 1., p16, 40., None, 5, 3, p16, None, None) == -1
+    assert b'rdf_condition_depth' in lib.rdf_last_error()
+    assert lib.rdf_condition_depth(p16, 8, 8, 0., 0., 1., p16, 40., None, 5, 3, p16, None, None) == -1          # in == out
+    assert b'alias' in lib.rdf_last_error()
+    assert lib.rdf_condition_depth(p16, 8, 8, 0., 0., 1., p16, 40., p16, 4, 3, ctypes.c_void_p(32), None, None) == -1   # even window
+    assert b'k_size' in lib.rdf_last_error()
+    ids = (ctypes.c_int * 5)(1, 2, 3, 4, 5)
+    assert lib.rdf_stencil_hands(p16, 8, 8, p16, 3, 1, 5, ids, ids, ctypes.c_void_p(32), None) == -1               # > 4 hands
+    assert b'num_hands' in lib.rdf_last_error()
+    assert lib.rdf_fingertip_z(p16, 1, 11, ids, 0, 2, p16, 8, 8, 0., 0., 1., 1., p16, p16, None, None) == -1
+    assert b'num_fingertips' in lib.rdf_last_error()
+    assert lib.rdf_flip_x(p16, 8, 8, p16, None) == -1 and lib.rdf_grow_groups(p16, 8, 8, p16, None) == -1       # aliased
+    assert lib.rdf_mean_shift_batch(None, 2, 8, 8, 2, None, 1, None, None, 0, None) == -1

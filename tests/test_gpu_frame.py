@@ -272,3 +272,71 @@ def test_hands_frame_pipeline_matches_reference_sequence(tmp_path, use_graph, ba
         assert ok[0].any() and ok[1].any() and okz.any()
     if num_hands == 0:
         assert not ok.any() and not okz.any()
+
+
+@pytest.mark.parametrize('h,w,K,N', [(240, 424, 11, 2), (120, 212, 11, 3), (33, 57, 3, 2), (30, 53, 30, 4), (480, 848, 11, 2)])
+def test_batched_mean_shift_equals_per_image(h, w, K, N):
+    """rdf_mean_shift_batch: one launch over N label images == N single calls (the batched class-parallel kernel where the image
+    size allows 128-bit rows per image, a loop of launches otherwise); the fused read-out == the separate one."""
+    import torch
+    from rdf_b200.mean_shift import MeanShift
+    from rdf_b200.points_ops import PointsOps
+    from rdf_b200.buffers import GPUArray
+    from oracle import numpy_oracle as no
+    rng = np.random.default_rng(h * 1000 + w)
+    labels = np.full((N, h, w), 65535, dtype=np.uint16)
+    for n in range(N):
+        m = rng.random((h, w)) < 0.12
+        labels[n][m] = rng.integers(0, K + 2, size=int(m.sum())).astype(np.uint16)       # 0 and K+1 are ignored
+    variances = (4.0 + 10.0 * rng.random(K)).astype(np.float32)
+    L = GPUArray(labels.shape, dtype=np.uint16); L.set(labels)
+    batched = MeanShift().run_async(5, L, K, variances, batch=True).get()
+    single = MeanShift()
+    for n in range(N):
+        one = single.run(5, L[n], K, variances)
+        exp = no.mean_shift(labels[n], K, variances, 5)
+        assert np.array_equal(np.isnan(one), np.isnan(exp)) and np.nanmax(np.abs(one - exp)) <= 1e-5
+        assert np.array_equal(np.isnan(batched[n]), np.isnan(exp)) and np.nanmax(np.abs(batched[n] - exp)) <= 1e-5
+    # fused read-out against the separate kernel on the same centroids
+    r = 2
+    raw = rng.integers(0, 9000, size=(h * r, w * r)).astype(np.uint16)
+    raw_dev = GPUArray(raw.shape, dtype=np.uint16); raw_dev.set(raw)
+    plane = GPUArray((4, 4), dtype=np.float32); plane.set(rng.normal(size=(4, 4)).astype(np.float32))
+    idx = [1, K, 2, 1] if K >= 2 else [1]
+    z_fused = GPUArray((N, len(idx)), dtype=np.float64)
+    z_sep = GPUArray((N, len(idx)), dtype=np.float64)
+    mc = GPUArray((N, K, 2), dtype=np.float64)
+    ms = MeanShift()
+    means = ms.run_fingertips_async(5, L, K, variances, idx, r, raw_dev, (w * r / 2 + 0.5, h * r / 2 - 0.25), 400.0, 401.0, plane, z_fused,
+                                    means_copy=mc, batch=True)
+    PointsOps().fingertip_z(means, idx, r, raw_dev, (w * r / 2 + 0.5, h * r / 2 - 0.25), 400.0, 401.0, plane, z_sep)
+    torch.cuda.synchronize()
+    assert np.array_equal(z_fused.get(), z_sep.get(), equal_nan=True)
+    assert np.array_equal(mc.get(), means.get(), equal_nan=True) and np.array_equal(means.get(), batched, equal_nan=True)
+
+
+@pytest.mark.parametrize('H,W,r,N,scale', [(120, 212, 2, 3, 0.5), (97, 131, 1, 2, 1.0)])
+def test_batched_layered_equals_per_image(tmp_path, H, W, r, N, scale):
+    """rdf_layered_run_batch over N images with per-image mirroring == N single runs (+ flip_x of the composite)."""
+    import torch
+    from rdf_b200 import synth
+    from rdf_b200 import decision_tree as dt
+    from rdf_b200.buffers import GPUArray
+    forests, cfg, _ = synth.layered_cfg2(seed=5, max_depth=9)
+    ldf = dt.LayeredDecisionForest.load(synth.write_layered_model(str(tmp_path), forests, cfg), (H, W), r)
+    depth = np.concatenate([synth.depth_frames('live-mask', 1, H, W, seed=40 + n) for n in range(N)])
+    flips = [bool(n & 1) for n in range(N)]
+    h, w = H // r, W // r
+    d = GPUArray((N, H, W), dtype=np.uint16); d.set(depth)
+    comp = GPUArray((N, h, w), dtype=np.uint16); comp.fill(1234)
+    layers = [GPUArray((N, h, w), dtype=np.uint16) for _ in range(ldf.num_models)]
+    ldf.run(d, comp, scale, composite_flip_x=flips, label_images=layers)
+    got, got_layers = comp.get(), [l.get() for l in layers]
+    one = GPUArray((1, h, w), dtype=np.uint16)
+    for n in range(N):
+        ldf.run(d[n], one, scale)
+        torch.cuda.synchronize()
+        exp = one.get()[0]
+        assert np.array_equal(got[n], exp[:, ::-1] if flips[n] else exp), n
+        for li in range(ldf.num_models):
+            assert np.array_equal(got_layers[li][n], ldf.label_images[li].cu().get()), (n, li)     # per-layer images stay unmirrored
