@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(256) rdf_layered_kernel(const __grid_constant_
 // the depth probes of the current node are in flight, so a level costs about one L2 round trip instead of two.
 // Results are identical: gating only decides which labels are kept.
 #define RL2_MAX_WALKS 32
+#define RL2_MAX_SUB 4
 
 struct rdf_layered2_params {
     rdf_layered_params base;
@@ -145,10 +146,15 @@ __global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_co
     // ... and this grid may itself have been scheduled early behind the kernel that produces the depth frame
     // (rdf_upload_frame in the live pipeline): nothing of the frame is read before that kernel has completed
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    __shared__ int leaf_s[RL2_MAX_WALKS][32];
-    __shared__ unsigned short lab_s[RDF_MAX_LAYERS][32];
-    const int lane = threadIdx.x, walk = threadIdx.y;
-    const int tile_y = blockIdx.x / p.tiles_x, tile_x = blockIdx.x - tile_y * p.tiles_x;
+    // blockDim = (32 lanes, walks, S sub-tiles): S patches of 8x4 pixels per CTA (S x walks <= 32 warps).  On a live frame nine tiles
+    // out of ten hold no valid pixel and cost a CTA launch each (6.5 us for the 3180 empty CTAs of a 424x240 label image), but S > 1
+    // measured slower (see the launch code): the default is S = 1.
+    __shared__ int leaf_s[RL2_MAX_WALKS][32];                                // [sub * walks + walk][lane]
+    __shared__ unsigned short lab_s[RL2_MAX_SUB][RDF_MAX_LAYERS][32];
+    const int lane = threadIdx.x, walk = threadIdx.y, sub = threadIdx.z;
+    const int stile_y = blockIdx.x / p.tiles_x, stile_x = blockIdx.x - stile_y * p.tiles_x;
+    const int sub_w = blockDim.z >= 2 ? 2 : 1;                               // sub-tiles side by side
+    const int tile_x = stile_x * sub_w + (sub & (sub_w - 1)), tile_y = stile_y * (blockDim.z / sub_w) + sub / sub_w;
     const int x = tile_x * 8 + (lane & 7), y = tile_y * 4 + (lane >> 3);     // warp = 8x4 patch of labels pixels
     const bool inside = x < p.w && y < p.h;
     const int X = x * p.r, Y = y * p.r;
@@ -159,13 +165,14 @@ __global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_co
     const size_t lbase = (size_t)blockIdx.y * p.label_stride;
     const size_t li = lbase + (size_t)y * p.w + x;
     const size_t lo = ((p.flip_mask >> blockIdx.y) & 1u) ? lbase + (size_t)y * p.w + (p.w - 1 - x) : li;   // composite label goes here
-    if (__syncthreads_or(valid) == 0) {                                   // nothing to evaluate in this tile: pre-fill only
+    if (__syncthreads_or(valid) == 0) {                                   // nothing to evaluate in this super-tile: pre-fill only
         if (walk == 0 && inside) {
             for (int i = 0; i < p.L; i++) p.layer_labels[i][li] = (uint16_t)RDF_NO_PIXEL;
             p.composite[lo] = (uint16_t)RDF_NO_PIXEL;
         }
         return;
     }
+    const int wbase = sub * q.num_walks;                                     // this patch's rows of leaf_s
     const int layer = q.walk_layer[walk], t = q.walk_tree[walk];
     const rdf_forest_view& fv = p.fv[layer];
     int leaf = RDF_NO_LEAF;                                                  // ~leaf_id once the walk has ended
@@ -196,7 +203,7 @@ __global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_co
             h = go_left ? hl : hr;
         }
     }
-    leaf_s[walk][lane] = leaf;
+    leaf_s[wbase + walk][lane] = leaf;
     __syncthreads();
     // vote of each layer by the thread that owns the layer's first walk (speculative: gating is applied below)
     if (walk == q.first_walk[layer] && valid) {
@@ -205,7 +212,7 @@ __global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_co
         for (int c = 0; c < fv.CP; c += 4) {
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int tt = 0; tt < fv.T; tt++) {
-                const int lf = leaf_s[walk + tt][lane];
+                const int lf = leaf_s[wbase + walk + tt][lane];
                 if (lf != RDF_NO_LEAF) {
                     const float4 v = __ldg(reinterpret_cast<const float4*>(fv.pdf + (size_t)(unsigned)(~lf) * fv.CP + c));
                     s.x = __fadd_rn(s.x, v.x); s.y = __fadd_rn(s.y, v.y); s.z = __fadd_rn(s.z, v.z); s.w = __fadd_rn(s.w, v.w);
@@ -216,7 +223,7 @@ __global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_co
             if (s.z > best) { best = s.z; lab = c + 2; }
             if (s.w > best) { best = s.w; lab = c + 3; }
         }
-        lab_s[layer][lane] = (unsigned short)lab;
+        lab_s[sub][layer][lane] = (unsigned short)lab;
     }
     __syncthreads();
     if (walk != 0 || !inside) return;
@@ -238,7 +245,7 @@ __global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_co
         if (fm >= 0 && p.filter_class[i] != -1) run = run && ((int)get_lab(fm) == p.filter_class[i]);
         unsigned l = RDF_NO_PIXEL;
         if (run) {
-            l = lab_s[i][lane];
+            l = lab_s[sub][i][lane];
             set_lab(i, l);
         }
         p.layer_labels[i][li] = (uint16_t)l;
@@ -310,7 +317,12 @@ static int rdf_layered_run_impl(const rdf_forest_t* const* forests, int num_laye
     if (num_walks <= RL2_MAX_WALKS && !getenv("RDF_LAYERED_V1")) {
         rdf_layered2_params q;
         q.base = p;
-        q.base.tiles_x = (p.w + 7) / 8;
+        // 8x4 patches per CTA (S x walks <= 32 warps).  Measured (RDF_LAYERED_SUB = 1 / 2 / 4): product frame 98.0 / 98.8 / 104.3 us, cfg2
+        // frame 69.6 / 70.3 / 70.6 us - fewer, fatter CTAs save launches of empty tiles but wait for their slowest patch: one patch it is
+        int S = 1;
+        if (const char* e = getenv("RDF_LAYERED_SUB")) { const int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && v * num_walks <= 32) S = v; }
+        const int sub_w = S >= 2 ? 2 : 1, sub_h = S / sub_w;
+        q.base.tiles_x = (p.w + 8 * sub_w - 1) / (8 * sub_w);
         q.num_walks = num_walks;
         int wi = 0;
         for (int i = 0; i < num_layers; i++) {
@@ -320,8 +332,8 @@ static int rdf_layered_run_impl(const rdf_forest_t* const* forests, int num_laye
                 q.walk_tree[wi] = t;
             }
         }
-        const int nb = q.base.tiles_x * ((p.h + 3) / 4);
-        dim3 block(32, num_walks, 1);
+        const int nb = q.base.tiles_x * ((p.h + 4 * sub_h - 1) / (4 * sub_h));
+        dim3 block(32, num_walks, S);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(nb, num_images, 1);
         cfg.blockDim = block;

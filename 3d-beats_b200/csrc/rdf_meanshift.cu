@@ -813,7 +813,15 @@ static int rdf_mean_shift_impl(const uint16_t* labels_dev, int num_images, int d
         // x 11 classes x 8 CTAs would queue behind each other on 148 SMs; measured 114 -> 106 us per product frame with R = 4)
         {
             const int r_cap = (npx + MS3_CAP - 1) / MS3_CAP;
-            while (R > 1 && R / 2 >= r_cap && (long long)num_images * num_labels * R > 148) R /= 2;
+            const long long clusters = (long long)num_images * num_labels;
+            if (clusters * R > 148) {                                   // any cluster size works (measured 3 / 4 / 5 / 6 CTAs: 100.8 / 99.1 /
+                int fit = (int)(148 / clusters);                        // 98.9 / 98.2 us per product frame)
+                if (fit < r_cap) fit = r_cap;
+                if (fit < 1) fit = 1;
+                if (fit < R) R = fit;
+            }
+            const char* e = getenv("RDF_MS3_RFINAL");                   // experiments: any cluster size 1..8 that holds the image
+            if (e && atoi(e) >= r_cap && atoi(e) >= 1 && atoi(e) <= MS3_MAX_R) R = atoi(e);
         }
         rdf_ms3_params q;
         q.labels = labels_dev; q.variances = variances_dev; q.means_out = means_dev;
