@@ -24,3 +24,10 @@ for ln in sys.stdin:
     else: print(d)"
 python tools/bench_train_tree.py 2>/dev/null | tail -1
 python tools/bench_grouping.py 2>/dev/null | tail -1
+python tools/bench_hands_frame.py --iters 500 2>/dev/null | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1])['hands_frame']
+r = d.get('reference_kernels_same_gpu', {})
+print('product frame e2e p50 %.1f us p99 %.1f (device p50 %.1f, %d launches) | reference kernels + host sequence p50 %s us | parity %s' % (
+    d['e2e_host_frame']['p50_us'], d['e2e_host_frame']['p99_us'], d['e2e_host_frame']['device_p50_us'], d['kernels_per_frame'],
+    r.get('p50_us'), d['parity']))"
