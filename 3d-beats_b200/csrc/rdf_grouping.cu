@@ -26,9 +26,9 @@ __device__ __forceinline__ int gr_find(volatile int* parent, int i) {
     return i;
 }
 
-// read-only find for the flatten pass: there every thread overwrites its OWN entry with the root, so a concurrent path-halving
-// write of another thread (an ancestor that is not the root) landing afterwards would undo it - seen as a few pixels missing from
-// the stencil on tall narrow images, where chains are long (tools/stress_grouping.py)
+// read-only find for the passes in which other threads must not see their results undone: a path-halving write (an ancestor that
+// is not the root) landing after a thread had recorded its root showed up as a few pixels missing from the stencil on tall narrow
+// images, where chains are long (tools/stress_grouping.py)
 __device__ __forceinline__ int gr_find_ro(const volatile int* parent, int i) {
     int p = parent[i];
     while (p != i) {
@@ -57,14 +57,50 @@ __device__ __forceinline__ void gr_unite(int* parent, int a, int b) {
     } while (!done);
 }
 
-// Phases (one CTA):
-//   1. a bit mask of the non-zero pixels per row (warp ballots), then one thread per PIXEL: the start of its horizontal run from
-//      the mask (count-leading-zeros over at most a few words); every pixel of a run points at the run's first pixel, which holds
-//      the run's length and x-sum (so later statistics cost one atomic per run, not per pixel: a 1500-pixel hand blob would
-//      otherwise serialise 1500 shared-memory atomics on one address);
-//   2. vertical unions between runs of neighbouring rows (only where an overlap segment starts);
-//   3. run statistics are added to their component's root (path-halving finds shorten every chain);
-//   5. selection over roots; 6. y-sums of the two selected components (warp-reduced, one atomic per warp); 7. stencil + g_info.
+// ---- row bit masks: bit x & 31 of word x >> 5 of a row is set when pixel x is non-zero; bits beyond the row are clear -----------
+// first pixel of the horizontal run that contains foreground pixel x
+__device__ __forceinline__ int gr_run_start(const unsigned* rm, int x) {
+    int wj = x >> 5;
+    unsigned z = ~rm[wj] & ((1u << (x & 31)) - 1u);              // background pixels to my left in this word
+    for (;;) {
+        if (z) return wj * 32 + 32 - __clz(z);                   // one past the last of them
+        if (--wj < 0) return 0;
+        z = ~rm[wj];
+    }
+}
+
+// one past the last pixel of the run that contains foreground pixel x
+__device__ __forceinline__ int gr_run_end(const unsigned* rm, int wpr, int w, int x) {
+    int wj = x >> 5;
+    const int bi = x & 31;
+    unsigned z = bi == 31 ? 0u : (~rm[wj] & ~((2u << bi) - 1u)); // background pixels to my right in this word
+    for (;;) {
+        if (z) {
+            const int e = wj * 32 + __ffs(z) - 1;
+            return e < w ? e : w;
+        }
+        if (++wj >= wpr) return w;
+        z = ~rm[wj];
+    }
+}
+
+// first pixels of the runs that begin in word wi of a row
+__device__ __forceinline__ unsigned gr_starts(const unsigned* rm, int wi) {
+    const unsigned m = rm[wi];
+    return m & ~((m << 1) | (wi > 0 ? rm[wi - 1] >> 31 : 0u));
+}
+
+// Everything after the masks works on horizontal RUNS (a few hundred on a product frame) instead of pixels (6360): one thread per
+// mask word (row, 32 columns) enumerates the runs that begin in its word.  The first version did every pass per pixel and was bound
+// by the issue rate of the one SM it runs on (58 k warp instructions, 17 us).  Union-find entries exist only at the first pixel of a
+// run (indexed by pixel, so the smallest root is the component's first pixel in raster order - the reference's tie rule).
+//   0. masks (warp ballots over the image);
+//   1. per run: parent = itself, cnt = length, sumx = sum of its x;
+//   2. per run: unions with the runs of the next row it touches (one per overlap segment);
+//   3. per run: statistics added to the root (path-halving finds shorten every chain);
+//   5. per root: the reference's selection (size threshold, side by centroid x, largest wins, ties -> first in raster order);
+//   6. per run: label (1 right / 2 left / 0) into cnt, y-sums of the selected components;
+//   7. per pixel: stencil = label of its run; g_info.
 #define GR_TRACE(slot)                                                    \
     do {                                                                  \
         if (trace && threadIdx.x == 0) trace[slot] = clock64();           \
@@ -82,29 +118,30 @@ __global__ void __launch_bounds__(GR_THREADS) rdf_group_hands_kernel(const uint1
     extern __shared__ int gr_smem[];
     const int N = w * h;
     const int wpr = (w + 31) >> 5;      // mask words per row
-    int* parent = gr_smem;              // [N]  -1 = background
-    int* cnt = parent + N;              // [N]  run length at run starts, then component size at roots
-    int* sumx = cnt + N;                // [N]  run x-sum at run starts, then component x-sum at roots
-    unsigned* rowmask = reinterpret_cast<unsigned*>(sumx + N);   // [h * wpr]  bit x & 31 of word x >> 5: pixel x of the row is non-zero
+    const int nwords = h * wpr;
+    int* parent = gr_smem;              // [N]  valid at run starts only
+    int* cnt = parent + N;              // [N]  run length at run starts, component size at roots; from pass 6 on: the run's label
+    int* sumx = cnt + N;                // [N]  run x-sum at run starts, component x-sum at roots
+    unsigned* rowmask = reinterpret_cast<unsigned*>(sumx + N);   // [h * wpr]
     __shared__ unsigned long long best[2];      // per side: size << 32 | ~root
     __shared__ int sumy[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // 1a. masks (grouping.cpp:107-108: non-zero = foreground).  Eight words per warp and trip with all loads issued before the
+    // 0. masks (grouping.cpp:107-108: non-zero = foreground).  Eight words per warp and trip with all loads issued before the
     // first ballot: the image comes out of L2 / HBM, one latency per trip instead of one per word
-    for (int t0 = warp; t0 < h * wpr; t0 += 8 * (GR_THREADS / 32)) {
+    for (int t0 = warp; t0 < nwords; t0 += 8 * (GR_THREADS / 32)) {
         unsigned v[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const int t = t0 + j * (GR_THREADS / 32);
             const int y = t / wpr, x = (t - y * wpr) * 32 + lane;
-            v[j] = (t < h * wpr && x < w) ? (unsigned)__ldg(img + y * w + x) : 0u;
+            v[j] = (t < nwords && x < w) ? (unsigned)__ldg(img + y * w + x) : 0u;
         }
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const int t = t0 + j * (GR_THREADS / 32);
             const unsigned m = __ballot_sync(0xffffffffu, v[j] != 0u);
-            if (lane == 0 && t < h * wpr) rowmask[t] = m;
+            if (lane == 0 && t < nwords) rowmask[t] = m;
         }
     }
     if (tid < 2) {
@@ -113,98 +150,99 @@ __global__ void __launch_bounds__(GR_THREADS) rdf_group_hands_kernel(const uint1
     }
     __syncthreads();
     GR_TRACE(1);
-    for (int i = tid; i < N; i += GR_THREADS) {                    // 1b. runs
-        const int y = i / w, x = i - y * w;
+    for (int t = tid; t < nwords; t += GR_THREADS) {               // 1. runs
+        const int y = t / wpr, wi = t - y * wpr;
         const unsigned* rm = rowmask + y * wpr;
-        const int wi = x >> 5, bi = x & 31;
-        int par = -1, len = 0, sx = 0;
-        if ((rm[wi] >> bi) & 1u) {
-            // start of my run: one past the last background pixel to my left
-            int start = 0;
-            unsigned z = ~rm[wi] & ((1u << bi) - 1u);
-            for (int wj = wi;;) {
-                if (z) {
-                    start = wj * 32 + 32 - __clz(z);
-                    break;
-                }
-                if (--wj < 0) break;
-                z = ~rm[wj];
-            }
-            par = y * w + start;
-            if (start == x) {                                      // first pixel of the run: its end = first background pixel to my right
-                int end = w;
-                unsigned z2 = ~rm[wi] & ~((2u << bi) - 1u);        // bits above bi (2u << 31 wraps to 0: mask becomes all ones -> none)
-                if (bi == 31) z2 = 0u;
-                for (int wj = wi;;) {
-                    if (z2) {
-                        end = wj * 32 + __ffs(z2) - 1;
-                        break;
-                    }
-                    if (++wj >= wpr) break;
-                    z2 = ~rm[wj];
-                }
-                if (end > w) end = w;                              // mask bits beyond the row are background
-                len = end - start;
-                sx = (start + end - 1) * len / 2;                  // start + ... + (end - 1)
-            }
+        for (unsigned st = gr_starts(rm, wi); st; st &= st - 1) {
+            const int x = wi * 32 + __ffs(st) - 1;
+            const int len = gr_run_end(rm, wpr, w, x) - x;
+            const int i = y * w + x;
+            parent[i] = i;
+            cnt[i] = len;
+            sumx[i] = (2 * x + len - 1) * len / 2;                 // x + ... + (x + len - 1)
         }
-        parent[i] = par;
-        cnt[i] = len;
-        sumx[i] = sx;
     }
     __syncthreads();
     GR_TRACE(2);
-    for (int i = tid; i < N - w; i += GR_THREADS) {                // 2. 4-connectivity (grouping.cpp:82-87): down edges between runs
-        if (parent[i] < 0 || parent[i + w] < 0) continue;
-        const int x = i % w;
-        if (x > 0 && parent[i - 1] >= 0 && parent[i + w - 1] >= 0) continue;   // same pair of runs as the pixel to the left
-        gr_unite(parent, i, i + w);
+    for (int t = tid; t < nwords - wpr; t += GR_THREADS) {         // 2. 4-connectivity (grouping.cpp:82-87): runs of row y with row y + 1
+        const int y = t / wpr, wi = t - y * wpr;
+        const unsigned* rm = rowmask + y * wpr;
+        const unsigned* rb = rm + wpr;
+        for (unsigned st = gr_starts(rm, wi); st; st &= st - 1) {
+            const int x = wi * 32 + __ffs(st) - 1;
+            const int end = gr_run_end(rm, wpr, w, x);
+            for (int wj = wi; wj * 32 < end; wj++) {
+                const int lo = max(x - wj * 32, 0), hi = min(end - wj * 32, 32);            // my columns in word wj: bits [lo, hi)
+                const unsigned rng = (hi == 32 ? 0xffffffffu : (1u << hi) - 1u) & ~((1u << lo) - 1u);
+                const unsigned below = rb[wj];
+                const unsigned bprev = (below << 1) | (wj > 0 ? rb[wj - 1] >> 31 : 0u);
+                // one union per overlap segment: a pixel below me whose left neighbour is background, or the one under my first pixel
+                unsigned cand = below & rng & (~bprev | (wj == wi ? 1u << (x & 31) : 0u));
+                for (; cand; cand &= cand - 1) {
+                    const int xb = wj * 32 + __ffs(cand) - 1;
+                    gr_unite(parent, y * w + x, (y + 1) * w + gr_run_start(rb, xb));
+                }
+            }
+        }
     }
     __syncthreads();
     GR_TRACE(3);
-    for (int i = tid; i < N; i += GR_THREADS) {                    // 3. run statistics -> root (roots keep their own run in place)
-        const int len = cnt[i];
-        if (len == 0) continue;
-        const int r = gr_find(parent, i);
-        if (r != i) {
-            atomicAdd(&cnt[r], len);
-            atomicAdd(&sumx[r], sumx[i]);
+    for (int t = tid; t < nwords; t += GR_THREADS) {               // 3. run statistics -> root (roots keep their own run in place)
+        const int y = t / wpr, wi = t - y * wpr;
+        for (unsigned st = gr_starts(rowmask + y * wpr, wi); st; st &= st - 1) {
+            const int i = y * w + wi * 32 + __ffs(st) - 1;
+            const int r = gr_find(parent, i);
+            if (r != i) {
+                atomicAdd(&cnt[r], cnt[i]);
+                atomicAdd(&sumx[r], sumx[i]);
+            }
         }
     }
     __syncthreads();
     GR_TRACE(4);
-    // (4. no flatten pass: the stencil pass below walks to the root itself; after the path-halving finds of pass 3 that is a hop or
-    //  two, and nothing writes `parent` any more, so no pass can undo another's result - see gr_find_ro)
-    for (int i = tid; i < N; i += GR_THREADS) {                    // 5. selection
-        if (parent[i] != i) continue;                              // roots only, one per component
-        const int n = cnt[i];
-        if (__fdiv_rn((float)n, (float)N) <= pct_thresh) continue;            // grouping.cpp:137
-        const float cx = __fdiv_rn((float)sumx[i], (float)n);                 // grouping.cpp:148
-        const int side = cx < __fdiv_rn((float)w, 2.f) ? 0 : 1;              // grouping.cpp:150
-        // strictly largest wins, so among equal sizes the component met first in raster order = smallest root (grouping.cpp:151,157)
-        atomicMax(&best[side], ((unsigned long long)(unsigned)n << 32) | (unsigned long long)(0xffffffffu - (unsigned)i));
+    for (int t = tid; t < nwords; t += GR_THREADS) {               // 5. selection
+        const int y = t / wpr, wi = t - y * wpr;
+        for (unsigned st = gr_starts(rowmask + y * wpr, wi); st; st &= st - 1) {
+            const int i = y * w + wi * 32 + __ffs(st) - 1;
+            if (parent[i] != i) continue;                          // roots only, one per component
+            const int n = cnt[i];
+            if (__fdiv_rn((float)n, (float)N) <= pct_thresh) continue;            // grouping.cpp:137
+            const float cx = __fdiv_rn((float)sumx[i], (float)n);                 // grouping.cpp:148
+            const int side = cx < __fdiv_rn((float)w, 2.f) ? 0 : 1;              // grouping.cpp:150
+            // strictly largest wins, so among equal sizes the component met first in raster order = smallest root (grouping.cpp:151,157)
+            atomicMax(&best[side], ((unsigned long long)(unsigned)n << 32) | (unsigned long long)(0xffffffffu - (unsigned)i));
+        }
     }
     __syncthreads();
-    GR_TRACE(6);
+    GR_TRACE(5);
     int sel[2], seln[2];
 #pragma unroll
     for (int s = 0; s < 2; s++) {
         seln[s] = (int)(best[s] >> 32);
         sel[s] = seln[s] ? (int)(0xffffffffu - (unsigned)(best[s] & 0xffffffffull)) : -2;
     }
-    for (int i0 = 0; i0 < N; i0 += GR_THREADS) {                   // 6. y-sums + 7. stencil (src/3d_bz.py:243-250)
-        const int i = i0 + tid;
-        const int r = (i < N && parent[i] >= 0) ? gr_find_ro(parent, i) : -1;
-        const int y = i / w;
-        const int c0 = __reduce_add_sync(0xffffffffu, r == sel[0] ? y : 0);
-        const int c1 = __reduce_add_sync(0xffffffffu, r == sel[1] ? y : 0);
-        if (lane == 0) {
-            if (c0) atomicAdd(&sumy[0], c0);
-            if (c1) atomicAdd(&sumy[1], c1);
+    for (int t = tid; t < nwords; t += GR_THREADS) {               // 6. labels of the runs (into cnt, which nobody needs any more) + y-sums
+        const int y = t / wpr, wi = t - y * wpr;
+        const unsigned* rm = rowmask + y * wpr;
+        for (unsigned st = gr_starts(rm, wi); st; st &= st - 1) {
+            const int x = wi * 32 + __ffs(st) - 1;
+            const int i = y * w + x;
+            const int r = gr_find_ro(parent, i);
+            const int lab = r == sel[0] ? 1 : r == sel[1] ? 2 : 0;
+            if (lab) atomicAdd(&sumy[lab - 1], y * (gr_run_end(rm, wpr, w, x) - x));
+            cnt[i] = lab;
         }
-        if (i < N) stencil[i] = (unsigned short)(r < 0 ? 0 : r == sel[0] ? 1 : r == sel[1] ? 2 : 0);
     }
     __syncthreads();
+    GR_TRACE(6);
+    for (int t = warp; t < nwords; t += GR_THREADS / 32) {         // 7. stencil (src/3d_bz.py:243-250): a warp per mask word
+        const int y = t / wpr, wi = t - y * wpr;
+        const unsigned* rm = rowmask + y * wpr;
+        const int x = wi * 32 + lane;
+        unsigned short v = 0;
+        if ((rm[wi] >> lane) & 1u) v = (unsigned short)cnt[y * w + gr_run_start(rm, x)];
+        if (x < w) stencil[y * w + x] = v;
+    }
     GR_TRACE(7);
     if (tid < 2) {
         const int s = tid;
