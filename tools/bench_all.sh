@@ -6,7 +6,7 @@ cd "$(dirname "$0")/.."
 one() { python bench.py --no-extras "$@" 2>/dev/null | python -c "
 import sys, json
 d = json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('%-12s %9.1f Mpx/s  %9.4f ms/step  %6.0f G node-steps/s  parity=%s' % (sys.argv[1], d['value'], d['ms_per_step'], d['roofline']['node_steps_per_s'] / 1e9, d["parity_checked"]))" "$2"; }
+print('%-12s %9.1f Mpx/s  %9.4f ms/step  %6.0f G node-steps/s  parity=%s' % (sys.argv[1], d['value'], d['ms_per_step'], d['roofline']['node_steps_per_s'] / 1e9, d['parity_checked']))" "$2"; }
 one --workload cfg1 --steps 30
 one --workload cfg3 --frames 1024
 one --workload cfg3-noise --frames 512
