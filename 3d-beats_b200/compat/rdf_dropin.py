@@ -1,4 +1,6 @@
-"""Drop-in shim for the reference's scripts (run_live.py, run_live_layered.py, test_on_saved_model.py, train_model.py).
+"""Drop-in shim for the reference's scripts (run_live.py, run_live_layered.py, test_on_saved_model.py, train_model.py; for the
+product loop src/3d_bz.py also `cuda.points_ops` -> rdf_b200.points_ops (PointsOps, gaussian_kernel) and `cpp_grouping` ->
+rdf_b200.grouping (CppGrouping)).
 
 `import rdf_dropin` BEFORE the scripts' own imports: it registers the B200 implementation under the top-level module
 names the reference uses (`decision_tree`, `cuda.mean_shift`, `cuda.py_nvcc_utils`, `engine.buffer`), so that
@@ -19,7 +21,9 @@ if _PKG not in sys.path:
 
 import rdf_b200.buffers as _buffers  # noqa: E402
 import rdf_b200.decision_tree as _decision_tree  # noqa: E402
+import rdf_b200.grouping as _grouping  # noqa: E402
 import rdf_b200.mean_shift as _mean_shift  # noqa: E402
+import rdf_b200.points_ops as _points_ops  # noqa: E402
 import rdf_b200.py_nvcc_utils as _py_nvcc_utils  # noqa: E402
 
 
@@ -41,6 +45,9 @@ def install():
     cuda_pkg.py_nvcc_utils = _py_nvcc_utils
     sys.modules['cuda.mean_shift'] = _mean_shift
     sys.modules['cuda.py_nvcc_utils'] = _py_nvcc_utils
+    cuda_pkg.points_ops = _points_ops                  # from cuda.points_ops import *  (src/3d_bz.py:7)
+    sys.modules['cuda.points_ops'] = _points_ops
+    sys.modules['cpp_grouping'] = _grouping            # from cpp_grouping import CppGrouping  (src/3d_bz.py:22)
     engine_pkg = _package('engine')
     engine_pkg.buffer = _buffers                       # GpuBuffer(shape, dtype).cu()  (src/engine/buffer.py:10-39)
     sys.modules['engine.buffer'] = _buffers

@@ -21,6 +21,10 @@ assert DecisionTree.get_config(16, 4) == (65535, 65536, 15)
 p = argparse.ArgumentParser(); py_nvcc_utils.add_args(p)
 a = p.parse_args(['--fatbin_in', 'x']); py_nvcc_utils.config_compiler(a)       # accepted and ignored
 assert MeanShift.__module__ == 'rdf_b200.mean_shift' and GpuBuffer.__module__ == 'rdf_b200.buffers'
+from cuda.points_ops import *                     # src/3d_bz.py:7
+from cpp_grouping import CppGrouping              # src/3d_bz.py:22
+assert PointsOps.__module__ == 'rdf_b200.points_ops' and CppGrouping.__module__ == 'rdf_b200.grouping'
+assert gaussian_kernel(5, 2.0).shape == (5, 5)
 import cuda.bindings                              # cuda-python is still importable next to the shim
 print('ok')
 ''' % os.path.join(ROOT, '3d-beats_b200', 'compat')
