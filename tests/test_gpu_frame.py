@@ -340,3 +340,63 @@ def test_batched_layered_equals_per_image(tmp_path, H, W, r, N, scale):
         assert np.array_equal(got[n], exp[:, ::-1] if flips[n] else exp), n
         for li in range(ldf.num_models):
             assert np.array_equal(got_layers[li][n], ldf.label_images[li].cu().get()), (n, li)     # per-layer images stay unmirrored
+
+
+def test_hands_frame_pipeline_matches_reference_kernels_and_host_sequence():
+    """The whole product frame against the REFERENCE's own kernels (points_ops.cu, calibrated_plane.cu, tree_eval.cu, mean_shift.cu
+    compiled unchanged) and C++ flood fill, launched in the order and with the host round trips of src/3d_bz.py."""
+    import os
+    import sys
+    from oracle import ref_points as rp, ref_kernels as rk, grouping_oracle as go
+    if not (rp.available() and rk.available() and go.ref_available()):
+        pytest.skip('oracle/_ref not built')
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools'))
+    import bench_hands_frame as b
+    pipe, scene, forests, cfg, variances = b.build(depth=12, seed=99)
+    means, z = pipe.run(scene['depth_raw'])
+    _, (ref_means, ref_z) = b.reference_sequence(scene, forests, cfg, variances, iters=1)
+    assert np.array_equal(np.isnan(means), np.isnan(ref_means))
+    ok = ~np.isnan(ref_means)
+    assert ok.any() and np.max(np.abs(means[ok] - ref_means[ok])) <= 1e-5
+    assert np.array_equal(np.isnan(z), np.isnan(ref_z))
+    okz = ~np.isnan(ref_z)
+    assert okz.any() and np.max(np.abs(z[okz] - ref_z[okz])) <= 1e-6 * max(1.0, np.max(np.abs(ref_z[okz])))
+
+
+@pytest.mark.parametrize('seed', range(8))
+def test_condition_and_stencil_fuzz_shapes(seed):
+    """Random small shapes, window sizes, reduction levels and hand lists against the C oracle."""
+    import torch
+    from rdf_b200.points_ops import PointsOps
+    from rdf_b200.buffers import GPUArray
+    from rdf_b200 import synth
+    from oracle import frame_oracle as fo
+    rng = np.random.default_rng(5000 + seed)
+    H, W = int(rng.integers(1, 140)), int(rng.integers(1, 200))
+    if seed % 2:
+        W = (W + 7) // 8 * 8                                            # the 128-bit stencil path
+    level = int(rng.integers(0, 4))
+    k = int(rng.choice([1, 3, 5, 7, 9, 13]))
+    sigma = float(rng.choice([0.05, 0.5, 1.0, 2.0, 3.3]))
+    s = synth.live_scene(max(H, 2), max(W, 2), seed=seed)
+    d = np.ascontiguousarray(s['depth_raw'][:H, :W])
+    d[rng.random(d.shape) < 0.1] = 0
+    scene = dict(s, depth_raw=d)
+    got, got_mm = _condition(scene, sigma, k, level)
+    exp, exp_mm = fo.condition_frame(d, s['pp'], s['focal'], s['plane'], s['plane_z_threshold'], sigma, k, level)
+    assert np.array_equal(got, exp) and np.array_equal(got_mm, exp_mm)
+    gh, gw = H >> level, W >> level
+    if gh == 0 or gw == 0:
+        return
+    groups = rng.integers(0, 4, size=(gh, gw)).astype(np.uint16)
+    groups[rng.random(groups.shape) < 0.6] = 0
+    hands = [(int(rng.integers(0, 4)), bool(rng.integers(0, 2))) for _ in range(int(rng.integers(1, 5)))]
+    ops = PointsOps()
+    d_dev = GPUArray((H, W), dtype=np.uint16); d_dev.set(exp)
+    g_dev = GPUArray((gh, gw), dtype=np.uint16); g_dev.set(groups)
+    out = GPUArray((len(hands), H, W), dtype=np.uint16); out.fill(3)
+    ops.stencil_hands(d_dev, g_dev, level, hands, out, grow=True)
+    torch.cuda.synchronize()
+    grown = fo.grow_groups(groups)
+    for i, (gid, flip) in enumerate(hands):
+        assert np.array_equal(out.get()[i], fo.hand_depth_image(exp, grown, level, gid, flip)), (i, gid, flip)
