@@ -177,23 +177,31 @@ __global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_co
     const rdf_forest_view& fv = p.fv[layer];
     int leaf = RDF_NO_LEAF;                                                  // ~leaf_id once the walk has ended
     if (valid) {
+        // loop invariants pinned in registers: left to itself the compiler re-derives them every level from the parameter block
+        // (a chain of dependent constant-bank loads indexed by threadIdx.y / blockIdx.y in front of every header and probe address)
+        unsigned long long hdr_u = (unsigned long long)fv.hdr, depth_u = (unsigned long long)depth;
+        int levels = fv.D, imgW = p.W, imgH = p.H;
+        asm volatile("" : "+l"(hdr_u), "+l"(depth_u), "+r"(levels), "+r"(imgW), "+r"(imgH));
+        const rdf_node_hdr* hdrp = reinterpret_cast<const rdf_node_hdr*>(hdr_u);
+        const uint16_t* __restrict__ img = reinterpret_cast<const uint16_t*>(depth_u);
         const float df = (float)d;
         const float rcp = __frcp_rn(df);
         const float xm = (float)X + RDF_MAGIC_F, ym = (float)Y + RDF_MAGIC_F;
-        rdf_hdr_regs h = rdf_load_hdr(fv.hdr, t * fv.nodes_per_tree);
-        for (int j = 0; j < fv.D; j++) {
+        rdf_hdr_regs h = rdf_load_hdr(hdrp, t * fv.nodes_per_tree);
+        for (int j = 0; j < levels; j++) {
             // both children (when they are nodes) are requested while the probes of this node are in flight
-            rdf_hdr_regs hl = h, hr = h;
-            if (h.b.y >= 0) hl = rdf_load_hdr(fv.hdr, h.b.y);
-            if (h.b.z >= 0) hr = rdf_load_hdr(fv.hdr, h.b.z);
+            // (a leaf side loads node 0 instead - never used, the walk ends there - which keeps the loads unpredicated and spares
+            // the sixteen register moves of a default value)
+            const rdf_hdr_regs hl = rdf_load_hdr(hdrp, max(h.b.y, 0));
+            const rdf_hdr_regs hr = rdf_load_hdr(hdrp, max(h.b.z, 0));
             float sx = h.a.x, sy = h.a.y, sz = h.a.z, sw = h.a.w;
             if (!SCALE1) {
                 sx = __fmul_rn(p.scale, sx); sy = __fmul_rn(p.scale, sy);
                 sz = __fmul_rn(p.scale, sz); sw = __fmul_rn(p.scale, sw);
             }
             int f;
-            if (FORCE_EXACT || (h.b.w & RDF_FLAG_EXACT_DIV)) f = rdf_feature_i<true>(depth, p.W, p.H, X, Y, df, rcp, xm, ym, sx, sy, sz, sw);
-            else f = rdf_feature_i<false>(depth, p.W, p.H, X, Y, df, rcp, xm, ym, sx, sy, sz, sw);
+            if (FORCE_EXACT || (h.b.w & RDF_FLAG_EXACT_DIV)) f = rdf_feature_i<true>(img, imgW, imgH, X, Y, df, rcp, xm, ym, sx, sy, sz, sw);
+            else f = rdf_feature_i<false>(img, imgW, imgH, X, Y, df, rcp, xm, ym, sx, sy, sz, sw);
             const bool go_left = f < h.b.x;
             const int next = go_left ? h.b.y : h.b.z;
             if (next < 0) {
