@@ -560,11 +560,14 @@ __global__ void __launch_bounds__(MS3_THREADS, 1) rdf_mean_shift_v3_kernel(const
     MS3_TRACE(0);
 
     // ---- my 8-pixel groups (dealt round-robin to the R CTAs), all loads issued first ----
+    // groups a thread can own at all at this image size and cluster size (block-uniform): the rest of the unrolled code is skipped
+    const int gmax = ((npx + 7) / 8 + MS3_THREADS * R - 1) / (MS3_THREADS * R);
     uint4 px[MS3_GROUPS];
 #pragma unroll
     for (int g = 0; g < MS3_GROUPS; g++) {
         const int q = ((g * MS3_THREADS + tid) * R + rank) * 8;
         px[g] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        if (g >= gmax) continue;
         if (q + 8 <= npx) {
             px[g] = __ldg(reinterpret_cast<const uint4*>(labels + q));
         } else if (q < npx) {
@@ -579,6 +582,7 @@ __global__ void __launch_bounds__(MS3_THREADS, 1) rdf_mean_shift_v3_kernel(const
     unsigned long long mask = 0ull;
 #pragma unroll
     for (int g = 0; g < MS3_GROUPS; g++) {
+        if (g >= gmax) continue;
         const unsigned w0 = __vcmpeq2(px[g].x, want2), w1 = __vcmpeq2(px[g].y, want2), w2 = __vcmpeq2(px[g].z, want2),
                        w3 = __vcmpeq2(px[g].w, want2);                   // 0xffff per matching half-word
         const unsigned m8 = (w0 & 1u) | ((w0 >> 15) & 2u) | ((w1 & 1u) << 2) | ((w1 >> 13) & 8u) | ((w2 & 1u) << 4) | ((w2 >> 11) & 32u) |
@@ -610,13 +614,22 @@ __global__ void __launch_bounds__(MS3_THREADS, 1) rdf_mean_shift_v3_kernel(const
     MS3_TRACE(2);
     {
         int pos = (warp ? wtot[warp - 1] : 0) + incl - cnt;
-        unsigned long long m = mask;
-        while (m) {                                                          // only the matching pixels are visited
-            const int b = __ffsll((long long)m) - 1;
-            m &= m - 1;
-            const int q = (((b >> 3) * MS3_THREADS + tid) * R + rank) * 8 + (b & 7);
-            const int y = q / p.w, x = q - y * p.w;
-            entries[pos++] = (uint32_t)x | ((uint32_t)y << 16);
+        // only the matching pixels are visited; one division per 8-pixel group (its first pixel), not per pixel
+#pragma unroll
+        for (int g = 0; g < MS3_GROUPS; g++) {
+            if (g >= gmax) continue;
+            unsigned m8 = (unsigned)(mask >> (8 * g)) & 0xffu;
+            if (!m8) continue;
+            const int q0 = ((g * MS3_THREADS + tid) * R + rank) * 8;
+            const int y0 = q0 / p.w, x0 = q0 - y0 * p.w;
+            for (; m8; m8 &= m8 - 1) {
+                int x = x0 + __ffs(m8) - 1, y = y0;
+                while (x >= p.w) {                                           // the group wraps into the next row(s)
+                    x -= p.w;
+                    y++;
+                }
+                entries[pos++] = (uint32_t)x | ((uint32_t)y << 16);
+            }
         }
     }
     const float var = p.variances[k];
