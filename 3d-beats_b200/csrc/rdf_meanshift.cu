@@ -694,10 +694,13 @@ __global__ void __launch_bounds__(MS3_THREADS, 1) rdf_mean_shift_v3_kernel(const
             cluster.sync();
             if (it == 1) MS3_TRACE(23);
             if (owner) {
-                for (int r = 0; r < R; r++) {
-                    a += buf[r * 3 + 0];
-                    b += buf[r * 3 + 1];
-                    c += buf[r * 3 + 2];
+#pragma unroll
+                for (int r = 0; r < MS3_MAX_R; r++) {                        // unrolled: all loads in flight at once, sums in rank order
+                    if (r < R) {
+                        a += buf[r * 3 + 0];
+                        b += buf[r * 3 + 1];
+                        c += buf[r * 3 + 2];
+                    }
                 }
             }
         } else if (owner) {
@@ -716,8 +719,9 @@ __global__ void __launch_bounds__(MS3_THREADS, 1) rdf_mean_shift_v3_kernel(const
                     c += buf[r * 3 + 2];
                 }
             }
-            mx += a / c;                                                     // mean_shift.py:53-55 (0/0 -> NaN)
-            my += b / c;
+            const double inv = 1.0 / c;                                      // mean_shift.py:53-55 (0/0 -> NaN): one divide for x and y
+            mx += a * inv;
+            my += b * inv;
         }
         if (it == 1) MS3_TRACE(24);
     }
