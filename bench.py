@@ -535,7 +535,7 @@ def main():
                 'compulsory_hbm_frac': 4.0 * px_per_launch / (kernel_ms * 1e-3) / 1e9 / peak,
                 'node_steps_per_s': T * D * px_per_launch / (kernel_ms * 1e-3),
                 'note': 'logical-traffic roofline (SURVEY 8d): exceeds 1.0 because the forest is cache-resident; the binding '
-                        'resource is the L1 data pipe (90 % of peak under ncu, profiles/r01_ncu_eval_v2.md)'}
+                        'resource is the L1 data pipe (93 % of peak under ncu, profiles/r01_ncu_eval_v3.md)'}
 
     line = {
         'metric': 'forest_eval_mpixels_per_s', 'value': value, 'unit': 'Mpixels/s', 'n_gpus': world, 'steps': args.steps,
