@@ -400,3 +400,57 @@ def test_condition_and_stencil_fuzz_shapes(seed):
     grown = fo.grow_groups(groups)
     for i, (gid, flip) in enumerate(hands):
         assert np.array_equal(out.get()[i], fo.hand_depth_image(exp, grown, level, gid, flip)), (i, gid, flip)
+
+
+@pytest.mark.parametrize('H,W,level', [(61, 101, 2), (120, 208, 3), (37, 64, 1), (1, 1, 0), (480, 848, 3)])
+def test_frame_kernels_do_not_write_outside_their_outputs(H, W, level):
+    """Every output sits between two canary regions of one larger allocation (compute-sanitizer is not available on the GPU pool)."""
+    import torch
+    from rdf_b200 import synth
+    from rdf_b200.points_ops import PointsOps
+    from rdf_b200.grouping import CppGrouping
+    from rdf_b200.buffers import GPUArray
+    G = 4096                                                     # canary elements on each side
+
+    def guarded(shape, np_dtype, canary):
+        n = int(np.prod(shape))
+        whole = GPUArray((n + 2 * G,), dtype=np_dtype)
+        whole.fill(canary)
+        mid = GPUArray(tuple(shape), tensor=whole.tensor[G:G + n].view(*shape))
+        return whole, mid, n
+
+    def intact(whole, n, canary):
+        a = whole.get()
+        return bool((a[:G] == canary).all() and (a[G + n:] == canary).all())
+
+    s = synth.live_scene(max(H, 2), max(W, 2), seed=H + W)
+    d = np.ascontiguousarray(s['depth_raw'][:H, :W])
+    ops = PointsOps()
+    raw = GPUArray((H, W), dtype=np.uint16); raw.set(d)
+    plane = GPUArray((4, 4), dtype=np.float32); plane.set(s['plane'])
+    gh, gw = H >> level, W >> level
+    w_out, out, n_out = guarded((H, W), np.uint16, 0xABCD)
+    w_mm, mm, n_mm = guarded((max(gh, 1), max(gw, 1)), np.uint16, 0xABCD)
+    mm_arg = mm if gh * gw > 0 else None
+    ops.condition_depth(raw, out, mm_arg, s['pp'], s['focal'], plane, s['plane_z_threshold'], 2.0, 5, level)
+    torch.cuda.synchronize()
+    assert intact(w_out, n_out, 0xABCD) and intact(w_mm, n_mm, 0xABCD)
+    if gh * gw == 0:
+        return
+    w_st, st, n_st = guarded((gh, gw), np.uint16, 0xABCD)
+    w_gi, gi, n_gi = guarded((2, 3), np.float32, -7.0)
+    if gh * gw <= 16384:
+        CppGrouping().make_groups_cu(mm, st, gi, 0.01)
+    else:
+        st.fill(1)
+    w_gr, gr, n_gr = guarded((gh, gw), np.uint16, 0xABCD)
+    ops.grow_groups(st, gr)
+    w_h, hands, n_h = guarded((3, H, W), np.uint16, 0xABCD)
+    ops.stencil_hands(out, st, level, [(1, False), (2, True), (1, True)], hands, grow=True)
+    w_f, fl, n_f = guarded((H, W), np.uint16, 0xABCD)
+    ops.flip_x(out, fl)
+    torch.cuda.synchronize()
+    for whole, n, c in [(w_st, n_st, 0xABCD), (w_gi, n_gi, -7.0), (w_gr, n_gr, 0xABCD), (w_h, n_h, 0xABCD), (w_f, n_f, 0xABCD), (w_out, n_out, 0xABCD),
+                        (w_mm, n_mm, 0xABCD)]:
+        assert intact(whole, n, c)
+    assert not (hands.get() == 0xABCD).all()
