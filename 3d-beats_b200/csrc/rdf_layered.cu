@@ -135,6 +135,7 @@ struct rdf_layered2_params {
     int walk_tree[RL2_MAX_WALKS];
     int first_walk[RDF_MAX_LAYERS];
     int num_walks;
+    int max_cp;                // largest padded class count of the layers (uniform trip count of the vote loop)
 };
 
 template <bool SCALE1, bool FORCE_EXACT>
@@ -149,7 +150,6 @@ __global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_co
     // blockDim = (32 lanes, walks, S sub-tiles): S patches of 8x4 pixels per CTA (S x walks <= 32 warps).  On a live frame nine tiles
     // out of ten hold no valid pixel and cost a CTA launch each (6.5 us for the 3180 empty CTAs of a 424x240 label image), but S > 1
     // measured slower (see the launch code): the default is S = 1.
-    __shared__ int leaf_s[RL2_MAX_WALKS][32];                                // [sub * walks + walk][lane]
     __shared__ unsigned short lab_s[RL2_MAX_SUB][RDF_MAX_LAYERS][32];
     const int lane = threadIdx.x, walk = threadIdx.y, sub = threadIdx.z;
     const int stile_y = blockIdx.x / p.tiles_x, stile_x = blockIdx.x - stile_y * p.tiles_x;
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_co
         }
         return;
     }
-    const int wbase = sub * q.num_walks;                                     // this patch's rows of leaf_s
+    const int wbase = sub * q.num_walks;                                     // this patch's rows of pdf_s
     const int layer = q.walk_layer[walk], t = q.walk_tree[walk];
     const rdf_forest_view& fv = p.fv[layer];
     int leaf = RDF_NO_LEAF;                                                  // ~leaf_id once the walk has ended
@@ -211,28 +211,39 @@ __global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_co
             h = go_left ? hl : hr;
         }
     }
-    leaf_s[wbase + walk][lane] = leaf;
-    __syncthreads();
-    // vote of each layer by the thread that owns the layer's first walk (speculative: gating is applied below)
-    if (walk == q.first_walk[layer] && valid) {
-        float best = 0.f;
-        int lab = 0;
-        for (int c = 0; c < fv.CP; c += 4) {
-            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int tt = 0; tt < fv.T; tt++) {
-                const int lf = leaf_s[wbase + walk + tt][lane];
-                if (lf != RDF_NO_LEAF) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(fv.pdf + (size_t)(unsigned)(~lf) * fv.CP + c));
-                    s.x = __fadd_rn(s.x, v.x); s.y = __fadd_rn(s.y, v.y); s.z = __fadd_rn(s.z, v.z); s.w = __fadd_rn(s.w, v.w);
-                }
+    // ---- vote of each layer: leaf pdfs summed in tree order by the thread that owns the layer's first walk (speculative: gating is
+    // applied below).  Every walk loads ITS leaf's pdf row, one 16-byte chunk per pass, and hands it over through shared memory;
+    // the chunk of the next pass is requested before the barrier of this one, so all rows cost about one L2 round trip in total.
+    // (One thread fetching T x CP/4 chunks in a loop paid a full round trip per chunk: 9 in a row for 3 trees x 11 classes.)
+    extern __shared__ float4 pdf_s[];                                        // [2][blockDim.z * num_walks][32]
+    const int nrow = blockDim.z * q.num_walks;
+    const bool has_leaf = valid && leaf != RDF_NO_LEAF;
+    const int myCP = fv.CP, myT = fv.T;
+    const float* myrow = fv.pdf + (size_t)(unsigned)(~leaf) * myCP;          // dereferenced only when has_leaf
+    const bool voter = walk == q.first_walk[layer] && valid;
+    auto load_chunk = [&](int c) -> float4 {
+        return (has_leaf && c < myCP) ? __ldg(reinterpret_cast<const float4*>(myrow + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    float4 cur = load_chunk(0);
+    float best = 0.f;
+    int lab = 0;
+    for (int c = 0, k = 0; c < q.max_cp; c += 4, k ^= 1) {                   // q.max_cp: block-uniform, every warp meets every barrier
+        pdf_s[(k * nrow + wbase + walk) * 32 + lane] = cur;
+        if (c + 4 < q.max_cp) cur = load_chunk(c + 4);
+        __syncthreads();                                                     // double buffer: one barrier per pass is enough
+        if (voter && c < myCP) {
+            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int tt = 0; tt < myT; tt++) {                               // a walk without leaf contributed zeros: x + 0 == x
+                const float4 v = pdf_s[(k * nrow + wbase + walk + tt) * 32 + lane];
+                sum.x = __fadd_rn(sum.x, v.x); sum.y = __fadd_rn(sum.y, v.y); sum.z = __fadd_rn(sum.z, v.z); sum.w = __fadd_rn(sum.w, v.w);
             }
-            if (s.x > best) { best = s.x; lab = c; }
-            if (s.y > best) { best = s.y; lab = c + 1; }
-            if (s.z > best) { best = s.z; lab = c + 2; }
-            if (s.w > best) { best = s.w; lab = c + 3; }
+            if (sum.x > best) { best = sum.x; lab = c; }
+            if (sum.y > best) { best = sum.y; lab = c + 1; }
+            if (sum.z > best) { best = sum.z; lab = c + 2; }
+            if (sum.w > best) { best = sum.w; lab = c + 3; }
         }
-        lab_s[sub][layer][lane] = (unsigned short)lab;
     }
+    if (voter) lab_s[sub][layer][lane] = (unsigned short)lab;
     __syncthreads();
     if (walk != 0 || !inside) return;
     // gating in layer order + composite walk (tree_eval.cu:232-244), identical to the fused kernel
@@ -332,6 +343,8 @@ static int rdf_layered_run_impl(const rdf_forest_t* const* forests, int num_laye
         const int sub_w = S >= 2 ? 2 : 1, sub_h = S / sub_w;
         q.base.tiles_x = (p.w + 8 * sub_w - 1) / (8 * sub_w);
         q.num_walks = num_walks;
+        q.max_cp = 4;
+        for (int i = 0; i < num_layers; i++) q.max_cp = q.max_cp > forests[i]->CP ? q.max_cp : forests[i]->CP;
         int wi = 0;
         for (int i = 0; i < num_layers; i++) {
             q.first_walk[i] = wi;
@@ -345,7 +358,7 @@ static int rdf_layered_run_impl(const rdf_forest_t* const* forests, int num_laye
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(nb, num_images, 1);
         cfg.blockDim = block;
-        cfg.dynamicSmemBytes = 0;
+        cfg.dynamicSmemBytes = (size_t)2 * S * num_walks * 32 * sizeof(float4);   // vote exchange, <= 32 KB
         cfg.stream = rdf_stream(stream);
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see griddepcontrol.wait in the kernel
