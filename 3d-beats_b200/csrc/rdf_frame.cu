@@ -78,14 +78,40 @@ __global__ void __launch_bounds__(RF_TILE_W * RF_THREADS_Y) rdf_condition_kernel
     if (K >= 0)
         for (int i = tid; i < k * k; i += RF_TILE_W * RF_THREADS_Y) wk[i] = __ldg(p.gauss + i);
     bool any = false;
-    for (int i = tid; i < tw * th; i += RF_TILE_W * RF_THREADS_Y) {
-        const int cy = i / tw, cx = i - cy * tw;
-        const int gx = x0 - R + cx, gy = y0 - R + cy;
-        int v = -1;
-        if (gx >= 0 && gx < p.W && gy >= 0 && gy < p.H)
-            v = (int)rf_clip(__ldg(p.in + (size_t)gy * p.W + gx), gx, gy, p, m20, m21, m22, m23, m30, m31, m32, m33);
-        tile[i] = v;
-        any = any || v > 0;
+    if (K != 0) {
+        // compile-time window: the tile's loads are issued together (a plain loop pays one memory round trip per trip: the clip
+        // arithmetic of a sample depends on its load, and the next load is not hoisted above it)
+        constexpr int NTH = RF_TILE_W * RF_THREADS_Y;
+        constexpr int NIT = ((RF_TILE_W + 2 * RMAX) * (RF_TILE_H + 2 * RMAX) + NTH - 1) / NTH;
+        int dv[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; it++) {
+            const int i = tid + it * NTH;
+            const int cy = i / tw, cx = i - cy * tw;
+            const int gx = x0 - R + cx, gy = y0 - R + cy;
+            dv[it] = -1;
+            if (i < tw * th && gx >= 0 && gx < p.W && gy >= 0 && gy < p.H) dv[it] = (int)__ldg(p.in + (size_t)gy * p.W + gx);
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; it++) {
+            const int i = tid + it * NTH;
+            if (i >= tw * th) break;
+            const int cy = i / tw, cx = i - cy * tw;
+            int v = dv[it];
+            if (v > 0) v = (int)rf_clip((unsigned)v, x0 - R + cx, y0 - R + cy, p, m20, m21, m22, m23, m30, m31, m32, m33);
+            tile[i] = v;
+            any = any || v > 0;
+        }
+    } else {
+        for (int i = tid; i < tw * th; i += RF_TILE_W * RF_THREADS_Y) {
+            const int cy = i / tw, cx = i - cy * tw;
+            const int gx = x0 - R + cx, gy = y0 - R + cy;
+            int v = -1;
+            if (gx >= 0 && gx < p.W && gy >= 0 && gy < p.H)
+                v = (int)rf_clip(__ldg(p.in + (size_t)gy * p.W + gx), gx, gy, p, m20, m21, m22, m23, m30, m31, m32, m33);
+            tile[i] = v;
+            any = any || v > 0;
+        }
     }
     // most of a live frame is table (clipped to 0): a tile whose whole neighbourhood is 0 filters to 0 whatever the weights
     // (w_non0 = sum = 0: either w_0 > 0 selects 0, or 0/0 = NaN floors to 0)
@@ -161,13 +187,14 @@ extern "C" int rdf_condition_depth(const uint16_t* depth_in_dev, int dim_x, int 
 // ---- groups: grow by one pixel (points_ops.cu:407-438) -------------------------------------------------------------
 // DIRS order of the reference: (x-1,y), (x+1,y), (x,y-1), (x,y+1); outside the image reads 0.
 __device__ __forceinline__ unsigned rf_grown(const uint16_t* __restrict__ g, int w, int h, int x, int y) {
-    unsigned v = __ldg(g + y * w + x);
-    if (v) return v;
-    if (x > 0 && (v = __ldg(g + y * w + x - 1)) != 0u) return v;
-    if (x + 1 < w && (v = __ldg(g + y * w + x + 1)) != 0u) return v;
-    if (y > 0 && (v = __ldg(g + (y - 1) * w + x)) != 0u) return v;
-    if (y + 1 < h && (v = __ldg(g + (y + 1) * w + x)) != 0u) return v;
-    return 0u;
+    // all five cells are requested at once (a chain of "if zero, look at the next neighbour" pays one load latency per step),
+    // then the reference's order decides: centre, left, right, up, down
+    const unsigned c = __ldg(g + y * w + x);
+    const unsigned l = x > 0 ? (unsigned)__ldg(g + y * w + x - 1) : 0u;
+    const unsigned r = x + 1 < w ? (unsigned)__ldg(g + y * w + x + 1) : 0u;
+    const unsigned u = y > 0 ? (unsigned)__ldg(g + (y - 1) * w + x) : 0u;
+    const unsigned d = y + 1 < h ? (unsigned)__ldg(g + (y + 1) * w + x) : 0u;
+    return c ? c : l ? l : r ? r : u ? u : d;
 }
 
 __global__ void __launch_bounds__(256) rdf_grow_groups_kernel(const uint16_t* __restrict__ g_in, int w, int h, uint16_t* __restrict__ g_out) {
