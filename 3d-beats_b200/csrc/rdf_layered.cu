@@ -161,6 +161,11 @@ __global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_co
     const uint16_t* __restrict__ depth = p.depth + (size_t)blockIdx.y * p.depth_stride;
     unsigned d = RDF_NO_PIXEL;
     if (inside) d = __ldg(depth + (size_t)Y * p.W + X);
+    // the root header of this warp's tree does not depend on the pixel: requested together with the centre depth (the same few
+    // nodes for every CTA, so an empty tile pays an L1 hit for it)
+    const int layer = q.walk_layer[walk], t = q.walk_tree[walk];
+    const rdf_forest_view& fv = p.fv[layer];
+    const rdf_hdr_regs root = rdf_load_hdr(fv.hdr, t * fv.nodes_per_tree);
     const bool valid = inside && d != 0u && d != RDF_NO_PIXEL;
     const size_t lbase = (size_t)blockIdx.y * p.label_stride;
     const size_t li = lbase + (size_t)y * p.w + x;
@@ -173,8 +178,6 @@ __global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_co
         return;
     }
     const int wbase = sub * q.num_walks;                                     // this patch's rows of pdf_s
-    const int layer = q.walk_layer[walk], t = q.walk_tree[walk];
-    const rdf_forest_view& fv = p.fv[layer];
     int leaf = RDF_NO_LEAF;                                                  // ~leaf_id once the walk has ended
     if (valid) {
         // loop invariants pinned in registers: left to itself the compiler re-derives them every level from the parameter block
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(1024) rdf_layered_walks_kernel(const __grid_co
         const float df = (float)d;
         const float rcp = __frcp_rn(df);
         const float xm = (float)X + RDF_MAGIC_F, ym = (float)Y + RDF_MAGIC_F;
-        rdf_hdr_regs h = rdf_load_hdr(hdrp, t * fv.nodes_per_tree);
+        rdf_hdr_regs h = root;
         for (int j = 0; j < levels; j++) {
             // both children (when they are nodes) are requested while the probes of this node are in flight
             // (a leaf side loads node 0 instead - never used, the walk ends there - which keeps the loads unpredicated and spares
