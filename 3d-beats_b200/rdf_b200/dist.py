@@ -30,6 +30,31 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
+def bind_host_to_gpu(local_rank):
+    """Pin the calling process to the CPU cores next to its GPU (NVML's ideal CPU affinity), so that the pinned host buffers it
+    allocates afterwards are first-touched on the GPU's own NUMA node and its PCIe copies do not cross the socket link.  With eight
+    ranks moving 6.7 GB per pass through host memory this is what bounds the host-buffer path.  Returns the number of CPUs the
+    process is bound to, or 0 when NVML is not available (nothing changed)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = None
+        try:                                                         # NVML and CUDA may order the devices differently
+            pr = torch.cuda.get_device_properties(int(local_rank))
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(('%08x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)).encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(int(local_rank))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def shard_range(total, rank, world):
     """Contiguous block partition of `total` units (frames / images) over `world` ranks; sizes differ by at most one."""
     base, extra = divmod(int(total), int(world))

@@ -407,6 +407,11 @@ def main():
     from rdf_b200.pipeline import HostBatchEvaluator, pinned_like
 
     rank, world, local = rdist.init_from_env()
+    host_cpus_bound = 0
+    if world > 1 and not os.environ.get('RDF_NO_NUMA_BIND'):
+        # before any pinned host buffer is allocated (first touch decides the NUMA node); single-rank runs keep every core for the
+        # CPU baseline leg
+        host_cpus_bound = rdist.bind_host_to_gpu(local)
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device: the product path has no CPU fallback'
     torch.cuda.set_device(local)
     if args.latency_only:
@@ -547,6 +552,7 @@ def main():
                    'l2': ('a different frame every step, L2 flushed (256 MB written) before each step, per-step CUDA events' if single else
                           'inputs larger than L2 (depth + labels = %.1f GB per rank per step)' % (2 * my_frames * H * W * 2 / 1e9))},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': args.steps * launches_per_step, 'roofline': roofline,
+        'host_cpus_bound_per_rank': host_cpus_bound,
         'parity_checked': parity,
     }
 
