@@ -111,3 +111,16 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['unit'] == 'Mpixels/s' and line['value'] > 0
     assert line['cpu_baseline']['kind'] == 'port' and line['e2e']['h2d_bytes_per_step'] == 0
+
+
+def test_bind_host_to_gpu_is_harmless_without_nvml_devices():
+    """Without a GPU (or NVML) the NUMA binding helper changes nothing and reports 0; it never leaves an empty CPU set."""
+    import os
+    from rdf_b200 import dist as rdist
+    before = os.sched_getaffinity(0)
+    n = rdist.bind_host_to_gpu(0)
+    after = os.sched_getaffinity(0)
+    assert isinstance(n, int) and n >= 0 and len(after) > 0
+    if n == 0:
+        assert after == before
+    os.sched_setaffinity(0, before)
