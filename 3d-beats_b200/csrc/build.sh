@@ -15,5 +15,7 @@ for f in rdf_capi rdf_eval rdf_layered rdf_meanshift rdf_synth rdf_train rdf_gro
   fi
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o "$OUT" "$HERE"/_obj/*.o -gencode arch=compute_100a,code=sm_100a
+# --cudart shared: the static runtime would embed its whole symbol table in the .so; the shared one is already in every process
+# that loads this library next to torch (rpath covers plain-C hosts)
+$NVCC -shared --cudart shared -Xlinker -rpath=/usr/local/cuda/lib64 -o "$OUT" "$HERE"/_obj/*.o -gencode arch=compute_100a,code=sm_100a
 echo "built $OUT"

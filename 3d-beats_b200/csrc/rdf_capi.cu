@@ -48,7 +48,7 @@ __global__ void rdf_pack_kernel(const float* __restrict__ canon, rdf_node_hdr* _
 static int rdf_pack(rdf_forest* f, const float* canon_dev, cudaStream_t stream) {
     const int64_t total = f->nodes_per_tree * f->T;
     int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (blocks > rdf_sm_count() * 32) blocks = rdf_sm_count() * 32;
     RDF_CUDA(cudaMemsetAsync(f->exact_flag_dev, 0, sizeof(int), stream));
     rdf_pack_kernel<<<blocks, 256, 0, stream>>>(canon_dev, f->hdr, f->pdf, total, f->nodes_per_tree, f->D, f->C, f->CP, f->exact_flag_dev);
     RDF_LAUNCH_CHECK("rdf_pack_kernel");
@@ -187,7 +187,7 @@ extern "C" int rdf_selftest_fastdiv(unsigned cases_per_divisor, uint32_t seed, u
     unsigned long long* dev = nullptr;
     RDF_CUDA(cudaMalloc(&dev, 2 * sizeof(unsigned long long)));
     cudaMemset(dev, 0, 2 * sizeof(unsigned long long));
-    rdf_selftest_fastdiv_kernel<<<148 * 8, 256>>>(cases_per_divisor, seed, dev, dev + 1);
+    rdf_selftest_fastdiv_kernel<<<rdf_sm_count() * 8, 256>>>(cases_per_divisor, seed, dev, dev + 1);
     unsigned long long host[2] = {~0ull, ~0ull};
     cudaError_t e = cudaMemcpy(host, dev, sizeof(host), cudaMemcpyDeviceToHost);
     cudaFree(dev);

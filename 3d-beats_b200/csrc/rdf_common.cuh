@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/rdf_b200.h"
 
@@ -250,6 +251,22 @@ static inline int rdf_current_device() {
     if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= RDF_MAX_DEVICES) d = 0;
     return d;
 }
+// Number of SMs of the current device (148 on a B200), queried once per device: grid-stride kernels size their grids from it.
+static inline int rdf_sm_count() {
+    static int n__[RDF_MAX_DEVICES];
+    const int d = rdf_current_device();
+    if (n__[d] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || v <= 0) v = 148;
+        n__[d] = v;
+    }
+    return n__[d];
+}
+
+// Environment switches are experiment knobs: each one is read once per process (function-local static of a per-site lambda),
+// never on the per-frame launch path.
+#define RDF_GETENV_ONCE(name) ([]() -> const char* { static const char* v__ = getenv(name); return v__; }())
+
 #define RDF_ENSURE_DYN_SMEM(func, bytes)                                                                              \
     do {                                                                                                              \
         static size_t set__[RDF_MAX_DEVICES];                                                                         \

@@ -139,7 +139,7 @@ static int rdf_launch_canon(const rdf_eval_canon_params& p, cudaStream_t stream)
 static int rdf_warp_w() {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("RDF_WARP_W");
+        const char* e = RDF_GETENV_ONCE("RDF_WARP_W");
         v = e ? atoi(e) : 16;
         if (v != 8 && v != 16 && v != 32) v = 16;
     }
@@ -199,7 +199,7 @@ static int rdf_eval_packed(const rdf_forest_t* forest, const uint16_t* depth_dev
     {
         static int lv = -1;                                         // RDF_SMEM_LEVELS overrides (experiments)
         if (lv < 0) {
-            const char* e = getenv("RDF_SMEM_LEVELS");
+            const char* e = RDF_GETENV_ONCE("RDF_SMEM_LEVELS");
             lv = e ? atoi(e) : RDF_EVAL_SMEM_LEVELS;
             if (lv < 0 || lv > RDF_EVAL_SMEM_LEVELS) lv = RDF_EVAL_SMEM_LEVELS;
         }

@@ -176,7 +176,7 @@ extern "C" int rdf_condition_depth(const uint16_t* depth_in_dev, int dim_x, int 
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = getenv("RDF_NO_PDL") ? 0 : 1;
+    cfg.numAttrs = RDF_GETENV_ONCE("RDF_NO_PDL") ? 0 : 1;
     if (!gauss_dev) RDF_CUDA(cudaLaunchKernelEx(&cfg, rdf_condition_kernel<-1>, p));
     else if (k_size == 5) RDF_CUDA(cudaLaunchKernelEx(&cfg, rdf_condition_kernel<5>, p));
     else if (k_size == 3) RDF_CUDA(cudaLaunchKernelEx(&cfg, rdf_condition_kernel<3>, p));
@@ -295,7 +295,7 @@ extern "C" int rdf_stencil_hands(const uint16_t* depth_dev, int dim_x, int dim_y
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = getenv("RDF_NO_PDL") ? 0 : 1;
+    cfg.numAttrs = RDF_GETENV_ONCE("RDF_NO_PDL") ? 0 : 1;
     if (vec8) RDF_CUDA(cudaLaunchKernelEx(&cfg, rdf_stencil_hands_kernel<true>, p));
     else RDF_CUDA(cudaLaunchKernelEx(&cfg, rdf_stencil_hands_kernel<false>, p));
     return RDF_OK;
@@ -430,7 +430,7 @@ extern "C" int rdf_fingertip_z(const double* means_dev, int num_images, int num_
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = getenv("RDF_NO_PDL") ? 0 : 1;
+    cfg.numAttrs = RDF_GETENV_ONCE("RDF_NO_PDL") ? 0 : 1;
     RDF_CUDA(cudaLaunchKernelEx(&cfg, rdf_fingertip_z_kernel, p));
     return RDF_OK;
 }

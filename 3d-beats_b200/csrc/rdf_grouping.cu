@@ -284,9 +284,9 @@ extern "C" int rdf_group_hands(const uint16_t* img_dev, int dim_x, int dim_y, fl
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = getenv("RDF_NO_PDL") ? 0 : 1;
+    cfg.numAttrs = RDF_GETENV_ONCE("RDF_NO_PDL") ? 0 : 1;
     static long long* trace_dev = nullptr;                         // debug aid: RDF_GR_TRACE=1 prints clock64 deltas per phase (synchronises)
-    const bool tracing = getenv("RDF_GR_TRACE") != nullptr;
+    const bool tracing = RDF_GETENV_ONCE("RDF_GR_TRACE") != nullptr;
     if (tracing && !trace_dev) RDF_CUDA(cudaMalloc(&trace_dev, 16 * sizeof(long long)));
     long long* trace_arg = tracing ? trace_dev : nullptr;
     RDF_CUDA(cudaLaunchKernelEx(&cfg, rdf_group_hands_kernel, img_dev, dim_x, dim_y, pct_thresh, stencil_dev, g_info_dev, trace_arg));

@@ -336,13 +336,13 @@ static int rdf_layered_run_impl(const rdf_forest_t* const* forests, int num_laye
     // latency path: one warp per tree walk (see rdf_layered_walks_kernel)
     int num_walks = 0;
     for (int i = 0; i < num_layers; i++) num_walks += forests[i]->T;
-    if (num_walks <= RL2_MAX_WALKS && !getenv("RDF_LAYERED_V1")) {
+    if (num_walks <= RL2_MAX_WALKS && !RDF_GETENV_ONCE("RDF_LAYERED_V1")) {
         rdf_layered2_params q;
         q.base = p;
         // 8x4 patches per CTA (S x walks <= 32 warps).  Measured (RDF_LAYERED_SUB = 1 / 2 / 4): product frame 98.0 / 98.8 / 104.3 us, cfg2
         // frame 69.6 / 70.3 / 70.6 us - fewer, fatter CTAs save launches of empty tiles but wait for their slowest patch: one patch it is
         int S = 1;
-        if (const char* e = getenv("RDF_LAYERED_SUB")) { const int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && v * num_walks <= 32) S = v; }
+        if (const char* e = RDF_GETENV_ONCE("RDF_LAYERED_SUB")) { const int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && v * num_walks <= 32) S = v; }
         const int sub_w = S >= 2 ? 2 : 1, sub_h = S / sub_w;
         q.base.tiles_x = (p.w + 8 * sub_w - 1) / (8 * sub_w);
         q.num_walks = num_walks;
@@ -367,7 +367,7 @@ static int rdf_layered_run_impl(const rdf_forest_t* const* forests, int num_laye
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see griddepcontrol.wait in the kernel
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = getenv("RDF_NO_PDL") ? 0 : 1;
+        cfg.numAttrs = RDF_GETENV_ONCE("RDF_NO_PDL") ? 0 : 1;
         if (!fast)
             RDF_CUDA(cudaLaunchKernelEx(&cfg, rdf_layered_walks_kernel<false, true>, q));
         else if (scale == 1.f)
@@ -425,7 +425,7 @@ extern "C" int rdf_upload_frame(const void* host_pinned, void* dev, size_t bytes
     const size_t n16 = bytes / 16;
     const int tail = (int)(bytes - n16 * 16);
     size_t blocks = (n16 + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > rdf_sm_count() * 8) blocks = rdf_sm_count() * 8;
     if (blocks < 1) blocks = 1;
     rdf_upload_kernel<<<(unsigned)blocks, 256, 0, rdf_stream(stream)>>>(
         reinterpret_cast<const uint4*>(host_pinned), reinterpret_cast<uint4*>(dev), n16,

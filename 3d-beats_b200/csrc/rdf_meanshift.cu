@@ -22,7 +22,6 @@ namespace cg = cooperative_groups;
 #define MS_WARPS (MS_THREADS / 32)
 #define MS_MAX_ITEMS 1024
 #define MS_MAX_CLUSTER 8
-#define MS2_MAX_CLUSTER 16                // non-portable cluster size (opt-in attribute), latency path only
 
 struct rdf_ms_params {
     const uint16_t* labels;
@@ -205,34 +204,6 @@ __global__ void __launch_bounds__(MS_THREADS) rdf_mean_shift_kernel(const rdf_ms
     cluster.sync();   // no CTA may exit while peers can still address its shared memory
 }
 
-// =================================================================================================================
-// v2: latency path (the live product shape).  Same algorithm, but everything after the first read of the label image
-// lives in shared memory and the image is read with 128-bit loads issued up front:
-//   * each thread owns up to MS2_GROUPS groups of 8 consecutive pixels (one uint4 each), all loaded before first use;
-//   * the per-class coordinate lists are built with a stable counting sort: per-thread class counts packed four
-//     16-bit counters per 64-bit word, one block-wide exclusive scan per word (deterministic order = thread, then
-//     pixel), entries (x | y << 16) scattered into shared memory;
-//   * rounds run on the shared-memory lists exactly like v1 (items -> warp shuffles -> DSMEM exchange -> barrier).
-// Used when K <= MS2_MAX_K, the image fits MS_MAX_CLUSTER x MS2_CAP pixels and the label pointer is 16-byte aligned.
-// =================================================================================================================
-#define MS2_THREADS 1024
-#define MS2_WARPS 32
-#define MS2_GROUPS 7                      // 56 pixels per thread -> up to 57344 pixels per CTA
-#define MS2_CAP 50944                     // entries per CTA kept in shared memory (199 KB): 8 CTAs cover 848x480
-#define MS2_MAX_K 16
-#define MS2_NG (MS2_MAX_K / 4)
-#define MS2_ITEM 64
-#define MS2_MAX_ITEMS (MS2_CAP / MS2_ITEM + MS2_MAX_K)
-#define MS2_ITEM_CLASS_BYTES ((MS2_MAX_ITEMS + 15) / 16 * 16)
-
-struct rdf_ms2_params {
-    const uint16_t* labels;
-    const float* variances;
-    double* means_out;
-    int w, h, K, rounds;
-    int chunk;              // pixels per CTA, multiple of 8
-    unsigned long long* trace;   // optional: %globaltimer stamps of rank 0 (workspace head), phase by phase
-};
 
 __device__ __forceinline__ unsigned long long ms_now() {
     unsigned long long t;
@@ -271,246 +242,11 @@ __device__ __forceinline__ double ms_exp_nonpos(double x) {
     return (pl * __hiloint2double((k1 + 1023) << 20, 0)) * __hiloint2double((k2 + 1023) << 20, 0);
 }
 
-// Block-wide exclusive scan of MS2_NG 64-bit words per thread at once (each word = four 16-bit class counters): one
-// pass of warp shuffles per word, ONE shared-memory exchange and two barriers for all words together.
-// warp_tot: [MS2_NG][MS2_WARPS].  pre[c] <- exclusive prefix of v[c] over the block, tot[c] <- block total.
-__device__ __forceinline__ void ms2_block_exscan(const unsigned long long (&v)[MS2_NG], unsigned long long* warp_tot,
-                                                 unsigned long long (&pre)[MS2_NG], unsigned long long (&tot)[MS2_NG]) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long incl[MS2_NG];
-#pragma unroll
-    for (int c = 0; c < MS2_NG; c++) {
-        incl[c] = v[c];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl[c], o);
-            if (lane >= o) incl[c] += t;
-        }
-        if (lane == 31) warp_tot[c * MS2_WARPS + warp] = incl[c];
-    }
-    __syncthreads();
-    if (warp < MS2_NG) {                    // warp c scans the 32 warp totals of word c
-        unsigned long long t = warp_tot[warp * MS2_WARPS + lane];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long u = __shfl_up_sync(0xffffffffu, t, o);
-            if (lane >= o) t += u;
-        }
-        warp_tot[warp * MS2_WARPS + lane] = t;            // inclusive over warps
-    }
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < MS2_NG; c++) {
-        tot[c] = warp_tot[c * MS2_WARPS + MS2_WARPS - 1];
-        pre[c] = (warp ? warp_tot[c * MS2_WARPS + warp - 1] : 0ull) + incl[c] - v[c];
-    }
-}
-
-__global__ void __launch_bounds__(MS2_THREADS, 1) rdf_mean_shift_v2_kernel(const rdf_ms2_params p) {
-    cg::cluster_group cluster = cg::this_cluster();
-    const int rank = (int)cluster.block_rank();
-    const int NC = (int)cluster.num_blocks();
-    const int K = p.K;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    extern __shared__ __align__(16) unsigned char ms_smem[];
-    double* all_partial = reinterpret_cast<double*>(ms_smem);                 // [2][NC][K][3]
-    double* partial = all_partial + 2 * (size_t)NC * K * 3;                   // [MS2_MAX_ITEMS][3]
-    double* means_s = partial + MS2_MAX_ITEMS * 3;                            // [K][2]
-    double* ninv_s = means_s + 2 * K;                                         // [K]  -1 / (2 sigma^2)
-    unsigned long long* warp_tot = reinterpret_cast<unsigned long long*>(ninv_s + K);   // [MS2_NG][32]
-    int* seg_start = reinterpret_cast<int*>(warp_tot + MS2_NG * MS2_WARPS);   // [K+1]
-    int* item_start = seg_start + (MS2_MAX_K + 1);                            // [K+1]
-    unsigned char* item_class = reinterpret_cast<unsigned char*>(item_start + (MS2_MAX_K + 1) + 2);   // [MS2_MAX_ITEMS]
-    uint32_t* entries = reinterpret_cast<uint32_t*>(item_class + MS2_ITEM_CLASS_BYTES);   // [chunk]
-
-    const int npx = p.w * p.h;
-    // 8-pixel groups are dealt round-robin to the CTAs of the cluster (group G -> CTA G % NC), so every CTA sees a uniform
-    // sample of the image: a hand blob in the middle of the frame no longer lands on one or two CTAs (the per-round
-    // cluster barrier used to wait ~3 us for the most loaded CTA, profiles/r01_latency.md).
-    // Programmatic dependent launch: this grid may be scheduled while the kernel before it in the stream (the layered
-    // forest) is still running; nothing produced by that kernel is touched before this wait.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    MS_TRACE(0);
-    if (p.trace && rank == 0 && tid == 0) p.trace[16] = (unsigned long long)clock64();
-
-    // ---- issue every load of this thread before anything consumes them ----
-    uint4 px[MS2_GROUPS];
-#pragma unroll
-    for (int g = 0; g < MS2_GROUPS; g++) {
-        const int q = ((g * MS2_THREADS + tid) * NC + rank) * 8;
-        px[g] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);      // 65535 = no pixel
-        if (q + 8 <= npx) {
-            px[g] = __ldg(reinterpret_cast<const uint4*>(p.labels + q));
-        } else if (q < npx) {                                                      // ragged tail of the image
-            unsigned short tmp[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) tmp[j] = q + j < npx ? __ldg(p.labels + q + j) : (unsigned short)0xffff;
-            px[g] = make_uint4(tmp[0] | (tmp[1] << 16), tmp[2] | (tmp[3] << 16), tmp[4] | (tmp[5] << 16), tmp[6] | (tmp[7] << 16));
-        }
-    }
-    for (int k = tid; k < K; k += MS2_THREADS) {
-        means_s[2 * k] = 0.0;
-        means_s[2 * k + 1] = 0.0;
-        const float v = p.variances[k];
-        ninv_s[k] = -1.0 / (2.0 * (double)__fmul_rn(v, v));                   // sigma^2 = fp32 product, widened (mean_shift.cu:41)
-    }
-
-    auto label_of = [&](int g, int j) -> unsigned {
-        const unsigned wd = j < 2 ? px[g].x : j < 4 ? px[g].y : j < 6 ? px[g].z : px[g].w;
-        return (j & 1) ? wd >> 16 : wd & 0xffffu;
-    };
-
-    // ---- per-thread class counts, four 16-bit counters per word ----
-    unsigned long long cnt[MS2_NG];
-#pragma unroll
-    for (int c = 0; c < MS2_NG; c++) cnt[c] = 0ull;
-#pragma unroll
-    for (int g = 0; g < MS2_GROUPS; g++) {
-        if ((px[g].x & px[g].y & px[g].z & px[g].w) == 0xffffffffu) continue;       // all background
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const unsigned l = label_of(g, j);
-            if (l != 0u && l != RDF_NO_PIXEL && (int)l <= K) {                       // mean_shift.cu:23
-                const int k = (int)l - 1;
-                const unsigned long long inc = 1ull << (16 * (k & 3));
-#pragma unroll
-                for (int c = 0; c < MS2_NG; c++) cnt[c] += (k >> 2) == c ? inc : 0ull;
-            }
-        }
-    }
-    MS_TRACE(1);
-    // ---- block-wide exclusive scans -> stable positions; totals -> class segments ----
-    unsigned long long pre[MS2_NG], tot[MS2_NG];
-    ms2_block_exscan(cnt, warp_tot, pre, tot);
-    if (tid == 0) {
-        seg_start[0] = 0;
-        item_start[0] = 0;
-        for (int k = 0; k < K; k++) {
-            unsigned long long tw = 0ull;
-#pragma unroll
-            for (int c = 0; c < MS2_NG; c++) if ((k >> 2) == c) tw = tot[c];
-            const int len = (int)((tw >> (16 * (k & 3))) & 0xffffull);
-            seg_start[k + 1] = seg_start[k] + len;
-            item_start[k + 1] = item_start[k] + (len + MS2_ITEM - 1) / MS2_ITEM;
-        }
-    }
-    __syncthreads();
-    MS_TRACE(2);
-    // ---- scatter (x | y << 16) into the class-sorted shared-memory list ----
-#pragma unroll
-    for (int g = 0; g < MS2_GROUPS; g++) {
-        if ((px[g].x & px[g].y & px[g].z & px[g].w) == 0xffffffffu) continue;
-        const int q = ((g * MS2_THREADS + tid) * NC + rank) * 8;
-        int y = q / p.w, x = q - y * p.w;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const unsigned l = label_of(g, j);
-            if (l != 0u && l != RDF_NO_PIXEL && (int)l <= K) {
-                const int k = (int)l - 1;
-                unsigned long long pw = 0ull;
-#pragma unroll
-                for (int c = 0; c < MS2_NG; c++) if ((k >> 2) == c) pw = pre[c];
-                const int pos = seg_start[k] + (int)((pw >> (16 * (k & 3))) & 0xffffull);
-                entries[pos] = (uint32_t)x | ((uint32_t)y << 16);
-                const unsigned long long inc = 1ull << (16 * (k & 3));
-#pragma unroll
-                for (int c = 0; c < MS2_NG; c++) pre[c] += (k >> 2) == c ? inc : 0ull;
-            }
-            if (++x == p.w) { x = 0; y++; }
-        }
-    }
-    __syncthreads();
-
-    // ---- rounds ----
-    const int n_items = item_start[K];
-    for (int item = tid; item < n_items; item += MS2_THREADS) {              // class of each item, once
-        int lo = 0, hi = K - 1;                                              // last k with item_start[k] <= item
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (item_start[mid] <= item) lo = mid; else hi = mid - 1;
-        }
-        item_class[item] = (unsigned char)lo;
-    }
-    __syncthreads();
-    MS_TRACE(3);
-    for (int it = 0; it < p.rounds; it++) {
-        if (it < 10) MS_TRACE(4 + it);
-        for (int item = warp; item < n_items; item += MS2_WARPS) {
-            const int k = item_class[item];
-            const int e0 = seg_start[k] + (item - item_start[k]) * MS2_ITEM;
-            const int e1 = min(seg_start[k + 1], e0 + MS2_ITEM);
-            // MS2_ITEM == 64: two entries per lane, evaluated as two independent chains
-            const int ea = e0 + lane, eb = ea + 32;
-            const bool va = ea < e1, vb = eb < e1;
-            const uint32_t ca = va ? entries[ea] : 0u, cb = vb ? entries[eb] : 0u;
-            const double cxa = (double)(ca & 0xffffu), cya = (double)(ca >> 16);
-            const double cxb = (double)(cb & 0xffffu), cyb = (double)(cb >> 16);
-            double sx, sy, sp;
-            if (it == 0) {                                                   // mean_shift.cu:31-34
-                const double wa = va ? 1.0 : 0.0, wb = vb ? 1.0 : 0.0;
-                sx = cxa * wa + cxb * wb;
-                sy = cya * wa + cyb * wb;
-                sp = wa + wb;
-            } else {                                                         // mean_shift.cu:36-46
-                const double mx = means_s[2 * k], my = means_s[2 * k + 1];
-                // -1 / (2 sigma^2) once per class instead of one fp64 divide per pixel (a 1-ulp change of the exponent)
-                const double nis = ninv_s[k];
-                const double dxa = cxa - mx, dya = cya - my, dxb = cxb - mx, dyb = cyb - my;
-                double pa = ms_exp_nonpos((dxa * dxa + dya * dya) * nis);
-                double pb = ms_exp_nonpos((dxb * dxb + dyb * dyb) * nis);
-                pa = va ? pa : 0.0;
-                pb = vb ? pb : 0.0;
-                sx = dxa * pa + dxb * pb;
-                sy = dya * pa + dyb * pb;
-                sp = pa + pb;
-            }
-            if (it == 1) MS_TRACE(20);
-            sx = ms_warp_sum(sx);
-            sy = ms_warp_sum(sy);
-            sp = ms_warp_sum(sp);
-            if (it == 1) MS_TRACE(21);
-            if (lane == 0) {
-                partial[item * 3 + 0] = sx;
-                partial[item * 3 + 1] = sy;
-                partial[item * 3 + 2] = sp;
-            }
-        }
-        __syncthreads();
-        if (it == 1) MS_TRACE(22);
-        double* buf = all_partial + (size_t)(it & 1) * NC * K * 3;
-        for (int i = tid; i < 3 * K; i += MS2_THREADS) {
-            const int k = i / 3, comp = i - 3 * k;
-            double s = 0.0;
-            for (int item = item_start[k]; item < item_start[k + 1]; item++) s += partial[item * 3 + comp];
-            for (int r = 0; r < NC; r++) cluster.map_shared_rank(buf, r)[((size_t)rank * K + k) * 3 + comp] = s;
-        }
-        if (it == 1) MS_TRACE(23);
-        cluster.sync();
-        if (it == 1) MS_TRACE(24);
-        for (int i = tid; i < 2 * K; i += MS2_THREADS) {                     // thread (k, x|y): its own sum and the weight sum
-            const int k = i >> 1, comp = i & 1;
-            double sv = 0.0, sp = 0.0;
-            for (int r = 0; r < NC; r++) {
-                sv += buf[((size_t)r * K + k) * 3 + comp];
-                sp += buf[((size_t)r * K + k) * 3 + 2];
-            }
-            means_s[i] += sv / sp;                                           // mean_shift.py:53-55 (0/0 -> NaN)
-        }
-        if (it == 1) MS_TRACE(25);
-        __syncthreads();
-    }
-    MS_TRACE(14);
-    if (rank == 0)
-        for (int i = tid; i < 2 * K; i += MS2_THREADS) p.means_out[i] = means_s[i];
-    cluster.sync();   // no CTA may exit while peers can still address its shared memory
-    MS_TRACE(15);
-    if (p.trace && rank == 0 && tid == 0) p.trace[17] = (unsigned long long)clock64();
-}
-
 // =================================================================================================================
-// v3: class-parallel latency path.  The classes never interact (each has its own mean), so instead of spreading the PIXELS
-// over a cluster and meeting at a cluster barrier every round (v2: ~2.4 us per round, mostly synchronisation), every CLASS
+// v3: class-parallel latency path (THE DEFAULT; rdf_mean_shift_kernel above is the one documented fallback, taken only for
+// images above MS3_MAX_R x MS3_CAP = 407 552 pixels or a label pointer that is not 16-byte aligned).  The classes never
+// interact (each has its own mean), so instead of spreading the PIXELS over one cluster and meeting at a cluster barrier every
+// round (the retired pixel-parallel shared-memory version: ~2.4 us per round, mostly synchronisation), every CLASS
 // gets its own small cluster of R CTAs (R = 1 for images up to 50 880 pixels, 2 for the product's 424 x 240 label image,
 // 8 for 848 x 480).  Each CTA filters its share of the label image for its class (128-bit loads, the image is read once per
 // class out of L2), compacts the coordinates into shared memory (one 32-bit block scan), and then iterates: every thread owns
@@ -745,17 +481,6 @@ static size_t ms3_smem_bytes(int chunk) {
     return sizeof(double) * (2 * MS3_MAX_R * 3 + 2 * MS3_WARPS * 3) + sizeof(int) * MS3_WARPS + sizeof(uint32_t) * (size_t)chunk;
 }
 
-static size_t ms2_smem_bytes(int K, int NC, int chunk) {
-    size_t b = 0;
-    b += sizeof(double) * 2 * (size_t)NC * K * 3;
-    b += sizeof(double) * MS2_MAX_ITEMS * 3;
-    b += sizeof(double) * 3 * (size_t)K;
-    b += sizeof(unsigned long long) * MS2_NG * MS2_WARPS;
-    b += sizeof(int) * (2 * (MS2_MAX_K + 1) + 2);
-    b += MS2_ITEM_CLASS_BYTES;
-    b += sizeof(uint32_t) * (size_t)chunk;
-    return b;
-}
 
 static size_t ms_smem_bytes(int K, int NC) {
     size_t b = 0;
@@ -794,8 +519,8 @@ static int rdf_mean_shift_impl(const uint16_t* labels_dev, int num_images, int d
     RDF_REQUIRE((int64_t)dim_x * dim_y < (1LL << 30), "rdf_mean_shift: image too large");
 
     const int npx = dim_x * dim_y;
-    const bool v3_ok = npx <= MS3_MAX_R * MS3_CAP && (reinterpret_cast<uintptr_t>(labels_dev) & 15u) == 0 && !getenv("RDF_MS_V1") &&
-                       !getenv("RDF_MS_V2");
+    const bool v3_ok = npx <= MS3_MAX_R * MS3_CAP && (reinterpret_cast<uintptr_t>(labels_dev) & 15u) == 0 &&
+                       !RDF_GETENV_ONCE("RDF_MS_V1");            // RDF_MS_V1: force the fallback (tests / experiments)
     if (num_images > 1 && !(v3_ok && (npx & 7) == 0)) {
         // no batched form of the other paths: one launch per image (same results, the workspace is reused in stream order)
         for (int n = 0; n < num_images; n++) {
@@ -816,7 +541,7 @@ static int rdf_mean_shift_impl(const uint16_t* labels_dev, int num_images, int d
         {
             static int r_min = -1;
             if (r_min < 0) {
-                const char* e = getenv("RDF_MS3_R");
+                const char* e = RDF_GETENV_ONCE("RDF_MS3_R");
                 r_min = e ? atoi(e) : 0;
                 if (r_min < 0 || r_min > MS3_MAX_R) r_min = 0;
             }
@@ -831,19 +556,19 @@ static int rdf_mean_shift_impl(const uint16_t* labels_dev, int num_images, int d
         {
             const int r_cap = (npx + MS3_CAP - 1) / MS3_CAP;
             const long long clusters = (long long)num_images * num_labels;
-            if (clusters * R > 148) {                                   // any cluster size works (measured 3 / 4 / 5 / 6 CTAs: 100.8 / 99.1 /
-                int fit = (int)(148 / clusters);                        // 98.9 / 98.2 us per product frame)
+            if (clusters * R > rdf_sm_count()) {                                   // any cluster size works (measured 3 / 4 / 5 / 6 CTAs: 100.8 / 99.1 /
+                int fit = (int)(rdf_sm_count() / clusters);                        // 98.9 / 98.2 us per product frame)
                 if (fit < r_cap) fit = r_cap;
                 if (fit < 1) fit = 1;
                 if (fit < R) R = fit;
             }
-            const char* e = getenv("RDF_MS3_RFINAL");                   // experiments: any cluster size 1..8 that holds the image
+            const char* e = RDF_GETENV_ONCE("RDF_MS3_RFINAL");                   // experiments: any cluster size 1..8 that holds the image
             if (e && atoi(e) >= r_cap && atoi(e) >= 1 && atoi(e) <= MS3_MAX_R) R = atoi(e);
         }
         rdf_ms3_params q;
         q.labels = labels_dev; q.variances = variances_dev; q.means_out = means_dev;
         q.w = dim_x; q.h = dim_y; q.K = num_labels; q.rounds = rounds; q.R = R;
-        q.trace = getenv("RDF_MS_TRACE") ? reinterpret_cast<unsigned long long*>(workspace_dev) : nullptr;
+        q.trace = RDF_GETENV_ONCE("RDF_MS_TRACE") ? reinterpret_cast<unsigned long long*>(workspace_dev) : nullptr;
         q.with_fingertips = 0;
         if (ft) {
             q.with_fingertips = 1;
@@ -867,65 +592,8 @@ static int rdf_mean_shift_impl(const uint16_t* labels_dev, int num_images, int d
         attr3[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr3[1].val.programmaticStreamSerializationAllowed = 1;
         cfg3.attrs = attr3;
-        cfg3.numAttrs = getenv("RDF_NO_PDL") ? 1 : 2;
+        cfg3.numAttrs = RDF_GETENV_ONCE("RDF_NO_PDL") ? 1 : 2;
         RDF_CUDA(cudaLaunchKernelEx(&cfg3, rdf_mean_shift_v3_kernel, q));
-        return RDF_OK;
-    }
-    // pixel-parallel latency path: everything in shared memory (see v2 above)
-    if (num_labels <= MS2_MAX_K && npx <= MS_MAX_CLUSTER * MS2_CAP &&   /* capacity at the portable cluster size */ (reinterpret_cast<uintptr_t>(labels_dev) & 15u) == 0 &&
-        !getenv("RDF_MS_V1")) {
-        // cluster size: 16 CTAs (non-portable size, opt-in) when the device can co-schedule such a cluster with the kernel's
-        // full shared-memory footprint, else the portable 8.  RDF_MS_CLUSTER overrides (experiments).
-        static int nc_cap_dev[RDF_MAX_DEVICES];                       // per device: function attributes are per device
-        int& nc_cap = nc_cap_dev[rdf_current_device()];
-        if (!nc_cap) {
-            const char* e = getenv("RDF_MS_CLUSTER");
-            int want = e ? atoi(e) : MS2_MAX_CLUSTER;
-            if (want < 1 || want > MS2_MAX_CLUSTER) want = MS2_MAX_CLUSTER;
-            nc_cap = want < MS_MAX_CLUSTER ? want : MS_MAX_CLUSTER;
-            if (want > MS_MAX_CLUSTER) {
-                const int max_smem = (int)ms2_smem_bytes(MS2_MAX_K, MS2_MAX_CLUSTER, MS2_CAP / 2);   // largest image at 16 CTAs
-                cudaLaunchConfig_t probe = {};
-                probe.gridDim = dim3(want, 1, 1);
-                probe.blockDim = dim3(MS2_THREADS, 1, 1);
-                probe.dynamicSmemBytes = max_smem;
-                cudaLaunchAttribute pa[1];
-                pa[0].id = cudaLaunchAttributeClusterDimension;
-                pa[0].val.clusterDim.x = want; pa[0].val.clusterDim.y = 1; pa[0].val.clusterDim.z = 1;
-                probe.attrs = pa; probe.numAttrs = 1;
-                int n_clusters = 0;
-                if (cudaFuncSetAttribute(rdf_mean_shift_v2_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-                    cudaFuncSetAttribute(rdf_mean_shift_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) == cudaSuccess &&
-                    cudaOccupancyMaxActiveClusters(&n_clusters, rdf_mean_shift_v2_kernel, &probe) == cudaSuccess && n_clusters >= 1)
-                    nc_cap = want;
-                cudaGetLastError();                                     // a failed probe is not an error of this call
-            }
-        }
-        int NC = (npx + 4095) / 4096;                                  // >= 4096 pixels per CTA before adding CTAs
-        if (NC > nc_cap) NC = nc_cap;
-        rdf_ms2_params q;
-        q.labels = labels_dev; q.variances = variances_dev; q.means_out = means_dev;
-        q.w = dim_x; q.h = dim_y; q.K = num_labels; q.rounds = rounds;
-        const int ngroups = (npx + 7) / 8;
-        q.chunk = ((ngroups + NC - 1) / NC) * 8;                  // entries a CTA may hold (its share of 8-pixel groups)
-        q.trace = getenv("RDF_MS_TRACE") ? reinterpret_cast<unsigned long long*>(workspace_dev) : nullptr;
-        const size_t smem2 = ms2_smem_bytes(num_labels, NC, q.chunk);
-        RDF_ENSURE_DYN_SMEM(rdf_mean_shift_v2_kernel, smem2);
-        cudaLaunchConfig_t cfg2 = {};
-        cfg2.gridDim = dim3(NC, 1, 1);
-        cfg2.blockDim = dim3(MS2_THREADS, 1, 1);
-        cfg2.dynamicSmemBytes = smem2;
-        cfg2.stream = rdf_stream(stream);
-        cudaLaunchAttribute attr2[2];
-        attr2[0].id = cudaLaunchAttributeClusterDimension;
-        attr2[0].val.clusterDim.x = NC;
-        attr2[0].val.clusterDim.y = 1;
-        attr2[0].val.clusterDim.z = 1;
-        attr2[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see griddepcontrol.wait in the kernel
-        attr2[1].val.programmaticStreamSerializationAllowed = 1;
-        cfg2.attrs = attr2;
-        cfg2.numAttrs = getenv("RDF_NO_PDL") ? 1 : 2;
-        RDF_CUDA(cudaLaunchKernelEx(&cfg2, rdf_mean_shift_v2_kernel, q));
         return RDF_OK;
     }
     const int gran = 32 * MS_WARPS;

@@ -44,7 +44,7 @@ extern "C" int rdf_synth_depth(uint16_t* depth_dev, int kind, int num_images, in
     RDF_REQUIRE(depth_dev != nullptr && num_images >= 0 && dim_x > 0 && dim_y > 0 && kind >= 0 && kind <= 2,
                 "rdf_synth_depth: bad argument");
     if (num_images == 0) return RDF_OK;
-    rdf_synth_depth_kernel<<<148 * 16, 256, 0, rdf_stream(stream)>>>(depth_dev, kind, num_images, dim_x, dim_y, seed, first_frame);
+    rdf_synth_depth_kernel<<<rdf_sm_count() * 16, 256, 0, rdf_stream(stream)>>>(depth_dev, kind, num_images, dim_x, dim_y, seed, first_frame);
     RDF_LAUNCH_CHECK("rdf_synth_depth_kernel");
     return RDF_OK;
 }
@@ -80,7 +80,7 @@ extern "C" int rdf_synth_forest(float* canon_dev, int num_trees, int max_depth, 
     RDF_REQUIRE(canon_dev != nullptr && num_trees >= 1 && max_depth >= 1 && max_depth <= RDF_MAX_DEPTH && num_classes >= 1 &&
                     num_classes <= RDF_MAX_CLASSES,
                 "rdf_synth_forest: bad argument");
-    rdf_synth_forest_kernel<<<148 * 16, 256, 0, rdf_stream(stream)>>>(canon_dev, num_trees, max_depth, num_classes, seed);
+    rdf_synth_forest_kernel<<<rdf_sm_count() * 16, 256, 0, rdf_stream(stream)>>>(canon_dev, num_trees, max_depth, num_classes, seed);
     RDF_LAUNCH_CHECK("rdf_synth_forest_kernel");
     return RDF_OK;
 }

@@ -33,7 +33,7 @@ extern "C" int rdf_train_init(const uint16_t* labels_dev, int64_t num_pixels, in
     cudaStream_t st = rdf_stream(stream);
     RDF_CUDA(cudaMemsetAsync(root_counts_dev, 0, sizeof(uint64_t) * num_classes, st));
     if (num_pixels == 0) return RDF_OK;
-    rdf_train_init_kernel<<<148 * 8, 256, sizeof(unsigned) * num_classes, st>>>(
+    rdf_train_init_kernel<<<rdf_sm_count() * 8, 256, sizeof(unsigned) * num_classes, st>>>(
         labels_dev, num_pixels, num_classes, nodes_by_pixel_dev, reinterpret_cast<unsigned long long*>(root_counts_dev));
     RDF_LAUNCH_CHECK("rdf_train_init_kernel");
     return RDF_OK;
@@ -294,7 +294,7 @@ extern "C" int rdf_train_bucket(const int32_t* nodes_by_pixel_dev, int64_t num_p
     int* list = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(cursor) + tb_align16(sizeof(int) * (size_t)num_slots));
     RDF_CUDA(cudaMemsetAsync(starts, 0, sizeof(int) * ((size_t)num_slots + 1), st));
     int blocks = (int)((num_pixels + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > rdf_sm_count() * 16) blocks = rdf_sm_count() * 16;
     if (blocks < 1) blocks = 1;
     rdf_train_bucket_kernel<0><<<blocks, 256, 0, st>>>(nodes_by_pixel_dev, node_slot_dev, num_pixels, starts, nullptr);
     rdf_train_bucket_scan_kernel<<<1, 1024, 0, st>>>(starts, cursor, num_slots, total);

@@ -340,6 +340,11 @@ class DecisionTreeDatasetConfig():
         total_images = json.loads(open(dataset_dir + 'config.json').read())['num_images']
         num_images_to_fetch = sum([num_images for num_images, _, _ in images])
         assert num_images_to_fetch <= total_images
+        # same np.random draw as the reference (src/decision_tree.py:30-31) so that a seeded run consumes the identical random
+        # stream afterwards (per-dataset shuffles, proposals); like the reference, the result is not used: every dataset shuffles
+        # the whole index range itself, so train and test sets are drawn independently and may overlap
+        images_to_fetch = list(range(total_images))
+        np.random.shuffle(images_to_fetch)
         datasets = []
         for num_images, images_per_block, imgs_name in images:
             images_per_block = images_per_block or num_images
@@ -515,7 +520,7 @@ class DecisionTreeTrainer():
         self.node_slot_cu = GPUArray((self.MAX_LEAF_NODES,), dtype=np.int32)
         self.current_offsets = GPUArray((P, 4), dtype=np.float32)
         self.current_thresholds = GPUArray((P, NT), dtype=np.float32)
-        self.current_proposals_block_cpu = np.zeros((P, 5), dtype=np.float32)
+        self.current_proposals_block_cpu = None
 
         # whole dataset resident: nodes_by_pixel int32[N,H,W] (the reference keeps it nvcomp-compressed per block)
         self.nodes_by_pixel = GPUArray(dataset.images_shape(), dtype=np.int32)
@@ -562,12 +567,18 @@ class DecisionTreeTrainer():
 
     # -- proposal stream -------------------------------------------------------------------------------------
     def _next_proposals(self, level, block):
+        """Next proposal block as (offsets float32[P,4], thresholds float32[P,NT]).  Multi-GPU: rank 0's block is broadcast, so
+        every rank scores the same candidates whatever its own np.random state (or proposal_fn) would have produced.
+        Thresholds must be finite (ValueError otherwise); with NT > 1 each feature's thresholds are sorted ascending here - the
+        bucketed histogram searches them by bisection, and bin k then means "thresholds 0..k-1 are <= the feature"."""
         P, NT = self.NUM_PROPOSALS_PER_PROPOSAL_BLOCK, self.thresholds_per_feature
         if self.proposal_fn is not None:
             offsets, thresholds = self.proposal_fn(level, block)
             offsets = np.ascontiguousarray(offsets, dtype=np.float32).reshape(P, 4)
             thresholds = np.ascontiguousarray(thresholds, dtype=np.float32).reshape(P, NT)
         elif NT == 1:
+            if getattr(self, 'current_proposals_block_cpu', None) is None:
+                self.current_proposals_block_cpu = np.zeros((P, 5), dtype=np.float32)
             make_random_features(P, self.current_proposals_block_cpu)          # src/decision_tree.py:487
             offsets = np.ascontiguousarray(self.current_proposals_block_cpu[:, 0:4])
             thresholds = np.ascontiguousarray(self.current_proposals_block_cpu[:, 4:5])
@@ -577,7 +588,16 @@ class DecisionTreeTrainer():
             for i in range(P):
                 u, v = make_random_feature()
                 offsets[i] = (u[0], u[1], v[0], v[1])
-                thresholds[i] = np.sort(np.array([make_random_threshold() for _ in range(NT)], dtype=np.float32))
+                thresholds[i] = np.array([make_random_threshold() for _ in range(NT)], dtype=np.float32)
+        dist = self._dist()
+        if dist is not None:
+            from . import dist as rdist
+            offsets, thresholds = rdist.broadcast_proposals(offsets, thresholds, self.process_group)
+        if not np.isfinite(thresholds).all():
+            raise ValueError('split thresholds must be finite (a NaN threshold routes every pixel right in evaluation but cannot be '
+                             'placed in a sorted threshold table)')
+        if NT > 1:
+            thresholds = np.sort(thresholds, axis=1)
         return offsets, thresholds
 
     def _dist(self):

@@ -81,6 +81,24 @@ def sum_over_ranks(value, device=None):
     return float(t.item())
 
 
+def broadcast_proposals(offsets, thresholds, group=None, src=0):
+    """Rank `src`'s proposal block (offsets float32[P,4], thresholds float32[P,NT], NumPy) on every rank.  The trainer draws
+    proposals from the process-local np.random state; without this, ranks that were not seeded identically would sum histograms
+    of DIFFERENT features.  One small broadcast per proposal block (P x (4 + NT) floats), on the backend's own device."""
+    import numpy as np
+    import torch.distributed as dist
+    P = offsets.shape[0]
+    packed = np.concatenate([np.ascontiguousarray(offsets, dtype=np.float32).reshape(P, 4),
+                             np.ascontiguousarray(thresholds, dtype=np.float32).reshape(P, -1)], axis=1)
+    t = torch.from_numpy(packed)
+    on_gpu = dist.get_backend(group) == 'nccl'
+    if on_gpu:
+        t = t.cuda()
+    dist.broadcast(t, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
+    packed = t.cpu().numpy()
+    return np.ascontiguousarray(packed[:, :4]), np.ascontiguousarray(packed[:, 4:])
+
+
 def barrier():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:

@@ -255,7 +255,11 @@ RDF_API int rdf_selftest_fastdiv(unsigned cases_per_divisor, uint32_t seed, unsi
  * so the reference's left child for threshold k (f < t_k) is bins 0..k.
  *   nodes_by_pixel_dev int32[N,H,W] (-1 = inactive, else node index within the current level);
  *   node_slot_dev int32[2^level]: node index -> histogram slot, or -1 (node not in this block);
- *   offsets_dev float32[F,4] (ux,uy,vx,vy); thresholds_dev float32[F,NT] ascending;
+ *   offsets_dev float32[F,4] (ux,uy,vx,vy); thresholds_dev float32[F,NT];
+ *   PRECONDITION (rdf_train_hist, rdf_train_hist_bucketed, rdf_train_hist_bucketed_p2p): every feature's NT thresholds are
+ *   FINITE and sorted ASCENDING - the bin is found by bisection, and pick-best / advance-pixels read the same table.  The
+ *   library does not check this on the device; the host mirror (DecisionTreeTrainer._next_proposals) sorts each row and
+ *   raises on NaN / inf before uploading.
  *   hist_dev uint32[num_slots,F,NT+1,C], ACCUMULATED into (zero it first; multi-GPU: allreduce it afterwards).
  * rdf_train_pick_best replaces `pick_best_features` (src/cuda/tree_train.cu:99-236) incl. the Gini helpers (:66-97),
  *   reading hist_dev; candidate order is feature-major, threshold-minor; first strictly greatest gain wins.

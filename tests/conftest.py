@@ -25,6 +25,23 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+def _missing_reference_builds():
+    from oracle import ref_kernels as rk, ref_points as rp, grouping_oracle as go
+    return [name for name, ok in (('oracle/_ref/libref_kernels.so', rk.available()), ('oracle/_ref/libref_points.so', rp.available()),
+                                  ('oracle/_ref/libref_grouping.so', go.ref_available())) if not ok]
+
+
+@pytest.fixture(autouse=True)
+def _require_reference_builds(request):
+    """A `-m gpu` run must FAIL, not pass vacuously, when the strongest checker - the reference's own kernels and C++ compiled
+    unchanged (oracle/_ref, built by `make -C oracle ref` where /root/reference exists and shipped with the snapshot) - is absent."""
+    if 'gpu' in request.keywords:
+        missing = _missing_reference_builds()
+        if missing:
+            pytest.fail('reference builds missing: %s - run `python -c "import __graft_entry__ as g; g.build()"` where '
+                        '/root/reference exists; the GPU parity tests compare against them' % ', '.join(missing), pytrace=False)
+
+
 @pytest.fixture(scope='session')
 def dev():
     import torch

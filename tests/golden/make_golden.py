@@ -64,7 +64,8 @@ def main(out_dir):
         if filt is not None:
             out[f'{name}.filter'] = filt
         out[f'{name}.labels'] = to_np(labels)
-    np.savez_compressed(os.path.join(out_dir, 'eval_forest.npz'), names=np.array([c[0] for c in cases]), **out, **{'meta.' + k: np.array(v) for k, v in meta.items()})
+    metak = {'meta.' + k: np.array(v) for k, v in meta.items()}          # provenance travels inside every fixture
+    np.savez_compressed(os.path.join(out_dir, 'eval_forest.npz'), names=np.array([c[0] for c in cases]), **out, **metak)
 
     # ---- single tree: evaluate_image_using_tree (tree_eval.cu:140-212) ----
     out = {}
@@ -84,7 +85,7 @@ def main(out_dir):
         out[f'{name}.depth'] = depth
         out[f'{name}.tree'] = tree
         out[f'{name}.labels'] = to_np(labels)
-    np.savez_compressed(os.path.join(out_dir, 'eval_tree.npz'), names=np.array(names), **out)
+    np.savez_compressed(os.path.join(out_dir, 'eval_tree.npz'), names=np.array(names), **out, **metak)
 
     # ---- layered run + composite (decision_tree.py:233-264, tree_eval.cu:214-248) and mean shift ----
     out = {}
@@ -120,7 +121,7 @@ def main(out_dir):
     out['blobs.labels'] = lab
     out['blobs.variances'] = var
     out['blobs.means'] = rk.mean_shift(to_dev(lab).reshape(1, 60, 90), 4, var, 5)
-    np.savez_compressed(os.path.join(out_dir, 'layered_meanshift.npz'), names=np.array(names), **out)
+    np.savez_compressed(os.path.join(out_dir, 'layered_meanshift.npz'), names=np.array(names), **out, **metak)
 
     # ---- training: evaluate_random_features histograms of one level + whole-tree training (tree_train.cu) ----
     out = {}
@@ -160,7 +161,7 @@ def main(out_dir):
     out['train.labels'] = labels
     out['train.proposals'] = np.stack([np.stack(stream[lvl]) for lvl in range(D)])   # [D][blocks][P][5]
     out['train.tree'] = tree
-    np.savez_compressed(os.path.join(out_dir, 'train.npz'), **out)
+    np.savez_compressed(os.path.join(out_dir, 'train.npz'), **out, **metak)
     for f in sorted(os.listdir(out_dir)):
         print(f, os.path.getsize(os.path.join(out_dir, f)))
 

@@ -53,7 +53,10 @@ def main(out_dir):
                     pre + 'mm_rgba': rp.make_depth_rgba(grown, 0, 2), pre + 'depth_rgba': rp.make_depth_rgba(depth, 2000, 6000)})
         print(name, 'kept', int((depth > 0).sum()), 'groups', g_info[:, 0])
     np.savez_compressed(os.path.join(out_dir, 'frame.npz'), names=np.array([c[0] for c in CASES]),
-                        gpu=np.array(torch.cuda.get_device_name(0)), **out)
+                        **{'meta.gpu': np.array(torch.cuda.get_device_name(0)), 'meta.generator': np.array('tests/golden/make_golden_frame.py'),
+                           'meta.source': np.array('reference points_ops.cu / calibrated_plane.cu compiled unchanged for sm_100a '
+                                                   '(oracle/ref_kernels/ref_points.cu) + grouping.cpp compiled by g++ '
+                                                   '(oracle/ref_kernels/ref_grouping.cpp)')}, **out)
 
 
 if __name__ == '__main__':

@@ -89,6 +89,61 @@ def test_world_size_2_gloo(tmp_path):
     assert np.array_equal(h0, full), 'allreduced shard histograms differ from the single-rank histogram'
 
 
+def _proposal_worker(rank, world, port, out_dir):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, '3d-beats_b200')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from rdf_b200 import dist as rdist
+    from rdf_b200 import decision_tree as dt
+    rdist.init_from_env(backend='gloo')
+    np.random.seed(100 + rank)                              # the ranks are NOT seeded identically
+    out = {}
+    for name, nt in (('nt1', 1), ('nt4', 4)):
+        tr = dt.DecisionTreeTrainer(None, 6, thresholds_per_feature=nt)
+        blocks = [tr._next_proposals(0, b) for b in range(3)]
+        out[name + '.off'] = np.stack([b[0] for b in blocks])
+        out[name + '.thr'] = np.stack([b[1] for b in blocks])
+    # a proposal_fn that differs per rank is overridden by rank 0's as well; unsorted rows come back sorted
+    tr = dt.DecisionTreeTrainer(None, 2, thresholds_per_feature=3,
+                                proposal_fn=lambda lvl, blk: (np.full((2, 4), rank + 1.0), np.array([[3., 1., 2.], [9., -7., 8.]]) + rank))
+    out['fn.off'], out['fn.thr'] = tr._next_proposals(0, 0)
+    bad = dt.DecisionTreeTrainer(None, 1, thresholds_per_feature=2, proposal_fn=lambda lvl, blk: (np.zeros((1, 4)), np.array([[1., np.nan]])))
+    try:
+        bad._next_proposals(0, 0)
+        out['nan_rejected'] = np.array(False)
+    except ValueError:
+        out['nan_rejected'] = np.array(True)
+    np.savez(os.path.join(out_dir, f'prop_{rank}.npz'), **out)
+    rdist.barrier()
+    dist.destroy_process_group()
+
+
+def test_default_proposal_stream_is_rank0s_on_every_rank(tmp_path):
+    """ranks draw proposals from their own np.random state; rank 0's block must be what every rank scores."""
+    import torch.multiprocessing as mp
+    from rdf_b200 import decision_tree as dt
+    world, port = 2, _free_port()
+    mp.spawn(_proposal_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    z0, z1 = np.load(tmp_path / 'prop_0.npz'), np.load(tmp_path / 'prop_1.npz')
+    for k in z0.files:
+        assert np.array_equal(z0[k], z1[k]), f'ranks disagree on {k}'
+    assert bool(z0['nan_rejected'])
+    # ... and it IS rank 0's stream: replay seed 100 single-process
+    np.random.seed(100)
+    for name, nt in (('nt1', 1), ('nt4', 4)):
+        tr = dt.DecisionTreeTrainer(None, 6, thresholds_per_feature=nt, process_group=False)
+        blocks = [tr._next_proposals(0, b) for b in range(3)]
+        assert np.array_equal(z0[name + '.off'], np.stack([b[0] for b in blocks]))
+        assert np.array_equal(z0[name + '.thr'], np.stack([b[1] for b in blocks]))
+        assert (np.diff(z0[name + '.thr'], axis=-1) >= 0).all()
+    assert np.array_equal(z0['fn.off'], np.full((2, 4), 1.0, np.float32))
+    assert np.array_equal(z0['fn.thr'], np.array([[1., 2., 3.], [-7., 8., 9.]], np.float32))
+
+
 @pytest.mark.parametrize('total,world', [(4096, 1), (4096, 8), (5, 2), (7, 8), (0, 4), (42, 4)])
 def test_shard_range_partitions(total, world):
     from rdf_b200.dist import shard_range

@@ -170,7 +170,7 @@ def test_cfg1_full_size_vs_c_oracle_and_reference():
     assert np.array_equal(ours, exp)
     assert np.abs(probs - exp_p).max() <= 1e-5
     assert len(np.unique(ours)) == 4                        # non-degenerate label map
-    if rk.available():
+    if True:                       # the reference build is required under -m gpu (tests/conftest.py)
         ref = filled_u16((1, 480, 848))
         rk.eval_forest(to_dev(forest), to_dev(depth), ref)
         torch.cuda.synchronize()

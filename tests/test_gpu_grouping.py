@@ -29,7 +29,7 @@ def test_matches_reference_cpp_and_oracle(h, w, seed):
     st, g = _ours(img, thresh)
     st_o, g_o = go.make_groups(img, thresh)
     assert np.array_equal(st, st_o) and np.array_equal(g, g_o)
-    if go.ref_available():
+    if True:                       # the reference build is required under -m gpu (tests/conftest.py)
         coords, g_ref = go.ref_make_groups(img, thresh)
         assert np.array_equal(st, go.stencil_from_coords(coords, h, w))
         for side in (0, 1):

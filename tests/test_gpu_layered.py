@@ -53,8 +53,6 @@ def test_layered_matches_reference_kernels(tmp_path):
     from rdf_b200 import synth
     from rdf_b200.buffers import GpuBuffer
     from oracle import ref_kernels as rk
-    if not rk.available():
-        pytest.skip('oracle/_ref not built')
     H, W, r, scale = 480, 848, 2, 1.0
     depth = synth.depth_frames('live-mask', 1, H, W)
     ldf, forests, cfg, variances = _layered(tmp_path, (H, W), r, max_depth=16)

@@ -95,7 +95,7 @@ def test_trained_tree_matches_oracle_and_reference(D, P, blocks):
 
     exp = no.train_tree(depth, labels, C, D, lambda lvl: stream[lvl])
     _assert_same_tree(ours, exp, 'numpy oracle')
-    if rk.available():
+    if True:                       # the reference build is required under -m gpu (tests/conftest.py)
         ref = rk.train_tree(to_dev(depth), to_dev(labels), C, D, lambda lvl: stream[lvl])
         _assert_same_tree(ours, ref, 'reference kernels')
     # the trained tree classifies its own training pixels better than chance

@@ -1,7 +1,7 @@
 // Micro-benchmark: L1 data-pipe wavefronts per load instruction for the access shapes of the forest-eval kernel.
 // Run under ncu:  ncu --metrics l1tex__data_pipe_lsu_wavefronts.sum,l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum,
 //                     l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum,gpu__time_duration.sum  ./l1_wavefronts
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o l1_wavefronts l1_wavefronts.cu
+// Build on demand (the binary is a git-ignored artefact): nvcc --cudart shared -gencode arch=compute_100a,code=sm_100a -O3 -o l1_wavefronts l1_wavefronts.cu
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
