@@ -1,6 +1,7 @@
 """Drop-in shim for the reference's scripts (run_live.py, run_live_layered.py, test_on_saved_model.py, train_model.py; for the
-product loop src/3d_bz.py also `cuda.points_ops` -> rdf_b200.points_ops (PointsOps, gaussian_kernel) and `cpp_grouping` ->
-rdf_b200.grouping (CppGrouping)).
+live scripts and the product loop src/3d_bz.py also `cuda.points_ops` -> rdf_b200.points_ops (PointsOps with the reference's
+pycuda call forms, gaussian_kernel), `calibrated_plane` -> rdf_b200.calibrated_plane and `cpp_grouping` -> rdf_b200.grouping
+(CppGrouping)).
 
 `import rdf_dropin` BEFORE the scripts' own imports: it registers the B200 implementation under the top-level module
 names the reference uses (`decision_tree`, `cuda.mean_shift`, `cuda.py_nvcc_utils`, `engine.buffer`), so that
@@ -20,6 +21,7 @@ if _PKG not in sys.path:
     sys.path.insert(0, _PKG)
 
 import rdf_b200.buffers as _buffers  # noqa: E402
+import rdf_b200.calibrated_plane as _calibrated_plane  # noqa: E402
 import rdf_b200.decision_tree as _decision_tree  # noqa: E402
 import rdf_b200.grouping as _grouping  # noqa: E402
 import rdf_b200.mean_shift as _mean_shift  # noqa: E402
@@ -48,6 +50,7 @@ def install():
     cuda_pkg.points_ops = _points_ops                  # from cuda.points_ops import *  (src/3d_bz.py:7)
     sys.modules['cuda.points_ops'] = _points_ops
     sys.modules['cpp_grouping'] = _grouping            # from cpp_grouping import CppGrouping  (src/3d_bz.py:22)
+    sys.modules['calibrated_plane'] = _calibrated_plane   # from calibrated_plane import *  (src/run_live.py:8, src/run_live_layered.py:8)
     engine_pkg = _package('engine')
     engine_pkg.buffer = _buffers                       # GpuBuffer(shape, dtype).cu()  (src/engine/buffer.py:10-39)
     sys.modules['engine.buffer'] = _buffers

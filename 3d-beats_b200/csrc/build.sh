@@ -7,7 +7,7 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden"
 mkdir -p "$HERE/_obj"
 pids=()
-for f in rdf_capi rdf_eval rdf_layered rdf_meanshift rdf_synth rdf_train rdf_grouping rdf_tex rdf_frame; do
+for f in rdf_capi rdf_eval rdf_layered rdf_meanshift rdf_synth rdf_train rdf_grouping rdf_tex rdf_frame rdf_points; do
   [ -f "$HERE/$f.cu" ] || continue
   if [ ! -f "$HERE/_obj/$f.o" ] || [ "$HERE/$f.cu" -nt "$HERE/_obj/$f.o" ] || [ -n "$(find "$HERE" "$HERE/../../include" -maxdepth 1 \( -name '*.cuh' -o -name '*.h' \) -newer "$HERE/_obj/$f.o")" ]; then
     $NVCC $FLAGS ${RDF_NVCC_EXTRA} -c "$HERE/$f.cu" -o "$HERE/_obj/$f.o" &

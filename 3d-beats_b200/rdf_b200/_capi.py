@@ -48,6 +48,15 @@ SIGNATURES = {
     'rdf_group_hands': [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p],
     'rdf_condition_depth': [c_void_p, c_int, c_int, c_float, c_float, c_float, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p,
                             c_void_p, c_void_p],
+    'rdf_deproject_points': [c_void_p, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p],
+    'rdf_transform_points': [c_int, c_void_p, c_void_p, c_void_p],
+    'rdf_filter_points_by_plane': [c_int, c_float, c_void_p, c_void_p],
+    'rdf_remove_missing_points': [c_int, c_void_p, c_void_p, c_void_p],
+    'rdf_setup_depth_for_forest': [c_int, c_void_p, c_void_p, c_void_p],
+    'rdf_zeros_to_no_pixel': [c_int, c_void_p, c_void_p],
+    'rdf_shrink_image': [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    'rdf_stencil_by_group': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    'rdf_scatter_groups': [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
     'rdf_grow_groups': [c_void_p, c_int, c_int, c_void_p, c_void_p],
     'rdf_stencil_hands': [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int),
                           c_void_p, c_void_p],

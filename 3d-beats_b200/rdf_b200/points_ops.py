@@ -32,6 +32,10 @@ def _out_ptr(t):
 
 
 class PointsOps():
+    """Two call forms per kernel.  (1) This module's own: device arrays first, shapes taken from them.  (2) The reference's
+    pycuda form, with the argument order of the `extern "C"` kernel and `grid=` / `block=` accepted and ignored (the launch
+    geometry is the library's business), so that run_live.py:86-121, run_live_layered.py:87-135 and src/3d_bz.py:159-456 run
+    unchanged against the drop-in (compat/rdf_dropin.py)."""
     MAX_FILTER_SIZE = 41          # src/cuda/points_ops.py:34
 
     def __init__(self):
@@ -85,8 +89,12 @@ class PointsOps():
                                                   _capi.dptr(self._filter(sigma, k_size)), int(k_size), 0, _capi.dptr(d_out), None,
                                                   _capi.stream_ptr()))
 
-    def grow_groups(self, g_in, g_out):
+    def grow_groups(self, *args, grid=None, block=None):
+        """grow_groups(g_in, g_out)  |  pycuda form (IMG_DIM int32[2] = (x, y), g_in, g_out, grid=, block=), src/3d_bz.py:254-259"""
+        g_in, g_out = args[-2:]
         g_in, g_out = as_gpuarray(g_in), as_gpuarray(g_out)
+        if len(args) == 3:
+            g_in, g_out = g_in.reshape((int(args[0][1]), int(args[0][0]))), g_out.reshape((int(args[0][1]), int(args[0][0])))
         assert g_in.dtype == np.uint16 and g_out.dtype == np.uint16 and g_in.size == g_out.size
         h, w = g_in.shape[-2:]
         _capi.check(self._lib.rdf_grow_groups(_capi.dptr(g_in), w, h, _capi.dptr(g_out), _capi.stream_ptr()))
@@ -104,21 +112,38 @@ class PointsOps():
         _capi.check(self._lib.rdf_stencil_hands(_capi.dptr(depth), W, H, _capi.dptr(groups), int(mm_level), int(bool(grow)), n, ids, flips,
                                                 _capi.dptr(out), _capi.stream_ptr()))
 
-    def flip_x(self, img_in, img_out):
+    def flip_x(self, *args, grid=None, block=None):
+        """flip_x(img_in, img_out)  |  pycuda form (IMG_DIM int32[2] = (x, y), in, out, grid=, block=), src/3d_bz.py:407-411,441-446"""
+        img_in, img_out = args[-2:]
         img_in, img_out = as_gpuarray(img_in), as_gpuarray(img_out)
+        if len(args) == 3:
+            img_in, img_out = img_in.reshape((int(args[0][1]), int(args[0][0]))), img_out.reshape((int(args[0][1]), int(args[0][0])))
         assert img_in.dtype == np.uint16 and img_out.dtype == np.uint16 and img_in.size == img_out.size
         h, w = img_in.shape[-2:]
         _capi.check(self._lib.rdf_flip_x(_capi.dptr(img_in), w, h, _capi.dptr(img_out), _capi.stream_ptr()))
 
-    def make_rgba_from_labels(self, labels, colors, rgba):
-        labels, colors, rgba = as_gpuarray(labels), as_gpuarray(colors), as_gpuarray(rgba)
+    def make_rgba_from_labels(self, *args, grid=None, block=None):
+        """make_rgba_from_labels(labels, colors, rgba)  |  pycuda form (IMG_DIM_X, IMG_DIM_Y, NUM_COLORS, labels, colors, rgba,
+        grid=, block=), src/run_live_layered.py:126-135, src/3d_bz.py:448-456"""
+        labels, colors, rgba = (as_gpuarray(a) for a in args[-3:])
         assert labels.dtype == np.uint16 and colors.dtype == np.uint8 and rgba.dtype == np.uint8
-        h, w = labels.shape[-2:]
+        if len(args) == 6:
+            w, h, num_colors = int(args[0]), int(args[1]), int(args[2])
+            assert labels.size == w * h and colors.size >= 4 * num_colors
+        else:
+            (h, w), num_colors = labels.shape[-2:], colors.size // 4
         assert rgba.size == h * w * 4
-        _capi.check(self._lib.rdf_labels_to_rgba(_capi.dptr(labels), w, h, _capi.dptr(colors), colors.size // 4, _capi.dptr(rgba),
+        _capi.check(self._lib.rdf_labels_to_rgba(_capi.dptr(labels), w, h, _capi.dptr(colors), num_colors, _capi.dptr(rgba),
                                                  _capi.stream_ptr()))
 
-    def make_depth_rgba(self, depth, d_min, d_max, rgba):
+    def make_depth_rgba(self, *args, grid=None, block=None):
+        """make_depth_rgba(depth, d_min, d_max, rgba)  |  pycuda form (IMG_DIM int32[2] = (x, y), d_min, d_max, depth, rgba, grid=,
+        block=), src/3d_bz.py:266-274"""
+        if len(args) == 5:
+            dims, d_min, d_max, depth, rgba = args
+            depth = as_gpuarray(depth).reshape((int(dims[1]), int(dims[0])))
+        else:
+            depth, d_min, d_max, rgba = args
         depth, rgba = as_gpuarray(depth), as_gpuarray(rgba)
         assert depth.dtype == np.uint16 and rgba.dtype == np.uint8
         h, w = depth.shape[-2:]
@@ -141,3 +166,72 @@ class PointsOps():
         _capi.check(self._lib.rdf_fingertip_z(_capi.dptr(means), num_images, means.shape[-2], idx, n, int(labels_reduce), _out_ptr(raw_depth), W, H,
                                               float(pp[0]), float(pp[1]), float(fx), float(fy), _capi.dptr(plane), _out_ptr(z_out),
                                               None if means_copy is None else _out_ptr(means_copy), _capi.stream_ptr()))
+
+    # ---- the reference's remaining kernels, pycuda call form only (csrc/rdf_points.cu) --------------------------------------
+    @staticmethod
+    def _pts(pts, n):
+        pts = as_gpuarray(pts)
+        assert pts.dtype == np.float32 and pts.size >= 4 * n, 'points buffer: float32[n, 4]'
+        return pts
+
+    def deproject_points(self, imgs_dim, pp, f, imgs, pts, grid=None, block=None):
+        """src/cuda/points_ops.cu:5-36; imgs_dim = int32[4] (num_images, dim_x, dim_y, -)  (src/run_live_layered.py:87-94)"""
+        n, dim_x, dim_y = int(imgs_dim[0]), int(imgs_dim[1]), int(imgs_dim[2])
+        imgs = as_gpuarray(imgs)
+        assert imgs.dtype == np.uint16 and imgs.size == n * dim_x * dim_y
+        _capi.check(self._lib.rdf_deproject_points(_capi.dptr(imgs), n, dim_x, dim_y, float(pp[0]), float(pp[1]), float(f),
+                                                   _capi.dptr(self._pts(pts, n * dim_x * dim_y)), _capi.stream_ptr()))
+
+    def transform_points(self, num_pts, pts, t, grid=None, block=None):
+        """src/cuda/points_ops.cu:66-75; t = the row-major numpy float32[4,4] CalibratedPlane.get_mat() returns"""
+        t = np.ascontiguousarray(t, dtype=np.float32)
+        assert t.size == 16
+        _capi.check(self._lib.rdf_transform_points(int(num_pts), _capi.dptr(self._pts(pts, int(num_pts))),
+                                                   t.ctypes.data_as(ctypes.c_void_p), _capi.stream_ptr()))
+
+    def filter_points_by_plane(self, num_pts, plane_z_threshold, pts, grid=None, block=None):
+        """src/cuda/calibrated_plane.cu:30-45 (the reference fetches it on CalibratedPlane; see rdf_b200/calibrated_plane.py)"""
+        _capi.check(self._lib.rdf_filter_points_by_plane(int(num_pts), float(plane_z_threshold), _capi.dptr(self._pts(pts, int(num_pts))),
+                                                         _capi.stream_ptr()))
+
+    def _depth_n(self, depth, n):
+        depth = as_gpuarray(depth)
+        assert depth.dtype == np.uint16 and depth.size >= n
+        return depth
+
+    def remove_missing_3d_points_from_depth_image(self, num_pixels, pts, depth, grid=None, block=None):
+        """src/cuda/points_ops.cu:131-146"""
+        n = int(num_pixels)
+        _capi.check(self._lib.rdf_remove_missing_points(n, _capi.dptr(self._pts(pts, n)), _capi.dptr(self._depth_n(depth, n)), _capi.stream_ptr()))
+
+    def setup_depth_image_for_forest(self, num_pixels, pts, depth, grid=None, block=None):
+        """src/cuda/points_ops.cu:149-165  (src/run_live.py:116-121, src/run_live_layered.py:117-122)"""
+        n = int(num_pixels)
+        _capi.check(self._lib.rdf_setup_depth_for_forest(n, _capi.dptr(self._pts(pts, n)), _capi.dptr(self._depth_n(depth, n)), _capi.stream_ptr()))
+
+    def convert_0s_to_maxuint(self, num_pixels, depth, grid=None, block=None):
+        """src/cuda/points_ops.cu:118-127"""
+        n = int(num_pixels)
+        _capi.check(self._lib.rdf_zeros_to_no_pixel(n, _capi.dptr(self._depth_n(depth, n)), _capi.stream_ptr()))
+
+    def shrink_image(self, img_dim_in, mipmap_level, d_in, d_out, grid=None, block=None):
+        """src/cuda/points_ops.cu:375-404; img_dim_in = int32[2] (x, y)"""
+        dim_x, dim_y, level = int(img_dim_in[0]), int(img_dim_in[1]), int(mipmap_level)
+        d_in, d_out = self._depth_n(d_in, dim_x * dim_y), self._depth_n(d_out, (dim_x >> level) * (dim_y >> level))
+        _capi.check(self._lib.rdf_shrink_image(_capi.dptr(d_in), dim_x, dim_y, level, _capi.dptr(d_out), _capi.stream_ptr()))
+
+    def stencil_depth_image_by_group(self, img_dim, mipmap_level, group, g_in, d_in, d_out, grid=None, block=None):
+        """src/cuda/points_ops.cu:441-463; img_dim = int32[2] (x, y)"""
+        dim_x, dim_y, level = int(img_dim[0]), int(img_dim[1]), int(mipmap_level)
+        g_in = self._depth_n(g_in, (dim_x >> level) * (dim_y >> level))
+        d_in, d_out = self._depth_n(d_in, dim_x * dim_y), self._depth_n(d_out, dim_x * dim_y)
+        _capi.check(self._lib.rdf_stencil_by_group(_capi.dptr(g_in), _capi.dptr(d_in), dim_x, dim_y, level, int(group), _capi.dptr(d_out),
+                                                   _capi.stream_ptr()))
+
+    def write_pixel_groups_to_stencil_image(self, coords, num_coords, stencil, stencil_dims, grid=None, block=None):
+        """src/cuda/points_ops.cu:486-503; coords int32[>= num_coords, 3] = (row, col, group), stencil_dims = (rows, cols)"""
+        coords, n = as_gpuarray(coords), int(num_coords)
+        rows, cols = int(stencil_dims[0]), int(stencil_dims[1])
+        assert coords.dtype == np.int32 and coords.size >= 3 * n
+        _capi.check(self._lib.rdf_scatter_groups(_capi.dptr(coords), n, _capi.dptr(self._depth_n(stencil, rows * cols)), rows, cols,
+                                                 _capi.stream_ptr()))

@@ -189,6 +189,35 @@ RDF_API int rdf_condition_depth(const uint16_t* depth_in_dev, int dim_x, int dim
                         const float* plane_dev, float plane_z_threshold, const float* gauss_dev, int k_size, int mipmap_level,
                         uint16_t* depth_out_dev, uint16_t* depth_mm_dev, void* stream);
 
+/* The reference's pre-forest point kernels one by one (csrc/rdf_points.cu), for callers that drive them individually with a
+ * user-visible point image pts_dev float32[N*H*W][4] (16-byte aligned) - src/run_live.py:86-121, src/run_live_layered.py:87-122,
+ * src/3d_bz.py:159-259,390-420.  Same results as the reference's kernels bit for bit (fp32 operation order of its compiled code);
+ * the fused product path is rdf_condition_depth / rdf_stencil_hands below.
+ *   rdf_deproject_points        deproject_points (src/cuda/points_ops.cu:5-36): d > 0 -> (d*(x-ppx)/f, d*(y-ppy)/f, d, 1); d == 0
+ *                               leaves the point as it was.
+ *   rdf_transform_points        transform_points (:66-75): p <- M p for points with w == 1; mat_host = 16 floats, row-major (numpy),
+ *                               read at call time (passed to the kernel by value like the reference's glm::mat4 argument).
+ *   rdf_filter_points_by_plane  filter_points_by_plane (src/cuda/calibrated_plane.cu:30-45): w == 1 and z > -threshold -> (0,0,0,0).
+ *   rdf_remove_missing_points   remove_missing_3d_points_from_depth_image (points_ops.cu:131-146): w == 0 -> depth 0.
+ *   rdf_setup_depth_for_forest  setup_depth_image_for_forest (:149-165): depth 0 or w == 0 -> depth 65535.
+ *   rdf_zeros_to_no_pixel       convert_0s_to_maxuint (:118-127).
+ *   rdf_shrink_image            shrink_image (:375-404): out[y][x] = in[y << level][x << level], out is (dim_y >> level) x (dim_x >> level).
+ *   rdf_stencil_by_group        stencil_depth_image_by_group (:441-463): out = depth where groups[y >> level][x >> level] == group,
+ *                               other pixels of out are left untouched.
+ *   rdf_scatter_groups          write_pixel_groups_to_stencil_image (:486-503): stencil[coords[i][0]][coords[i][1]] = coords[i][2],
+ *                               coords_dev int32[num_coords][3], stencil uint16[rows][cols]. */
+RDF_API int rdf_deproject_points(const uint16_t* depth_dev, int num_images, int dim_x, int dim_y, float ppx, float ppy, float focal,
+                         float* pts_dev, void* stream);
+RDF_API int rdf_transform_points(int num_pts, float* pts_dev, const float* mat_host, void* stream);
+RDF_API int rdf_filter_points_by_plane(int num_pts, float plane_z_threshold, float* pts_dev, void* stream);
+RDF_API int rdf_remove_missing_points(int num_pts, const float* pts_dev, uint16_t* depth_dev, void* stream);
+RDF_API int rdf_setup_depth_for_forest(int num_pts, const float* pts_dev, uint16_t* depth_dev, void* stream);
+RDF_API int rdf_zeros_to_no_pixel(int num_pixels, uint16_t* depth_dev, void* stream);
+RDF_API int rdf_shrink_image(const uint16_t* in_dev, int dim_x, int dim_y, int mipmap_level, uint16_t* out_dev, void* stream);
+RDF_API int rdf_stencil_by_group(const uint16_t* groups_dev, const uint16_t* depth_dev, int dim_x, int dim_y, int mipmap_level, int group,
+                         uint16_t* out_dev, void* stream);
+RDF_API int rdf_scatter_groups(const int32_t* coords_dev, int num_coords, uint16_t* stencil_dev, int rows, int cols, void* stream);
+
 /* rdf_grow_groups: grow_groups (src/cuda/points_ops.cu:407-438, call site src/3d_bz.py:252-259): a zero pixel takes the first
  * non-zero value among its left, right, upper, lower neighbour. */
 RDF_API int rdf_grow_groups(const uint16_t* groups_in_dev, int dim_x, int dim_y, uint16_t* groups_out_dev, void* stream);

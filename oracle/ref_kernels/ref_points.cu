@@ -37,6 +37,11 @@ REF_EXPORT int ref_remove_missing(int num_pts, float* pts, uint16_t* depth, void
     remove_missing_3d_points_from_depth_image<<<cdiv(num_pts, 1024), 1024, 0, (cudaStream_t)stream>>>(num_pts, (glm::vec4*)pts, depth);
     return ref_check();
 }
+// src/run_live.py:116-121, src/run_live_layered.py:117-122
+REF_EXPORT int ref_setup_depth_image_for_forest(int num_pts, float* pts, uint16_t* depth, void* stream) {
+    setup_depth_image_for_forest<<<num_pts / 1024 + 1, 1024, 0, (cudaStream_t)stream>>>(num_pts, (glm::vec4*)pts, depth);
+    return ref_check();
+}
 // src/cuda/points_ops.py:62-98
 REF_EXPORT int ref_gaussian_depth_filter(int dim_x, int dim_y, int k_size, float* k, uint16_t* d_in, uint16_t* d_out, void* stream) {
     dim3 block(32, 32, 1), grid(cdiv(dim_x, 32), cdiv(dim_y, 32), 1);

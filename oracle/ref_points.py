@@ -71,6 +71,22 @@ def condition_frame(depth_raw, pp, focal, plane, plane_z_threshold, gauss_kernel
     return _host_u16(depth), _host_u16(mm)
 
 
+def live_frame_for_forest(depth_raw, pp, focal, plane, plane_z_threshold):
+    """src/run_live.py:86-121 / src/run_live_layered.py:87-122 with the reference's kernels: deproject -> transform -> plane filter ->
+    setup_depth_image_for_forest.  Returns (pts float32[H,W,4], depth uint16[H,W]) as numpy."""
+    H, W = depth_raw.shape
+    depth = _dev_u16(depth_raw)
+    pts = torch.zeros((H, W, 4), dtype=torch.float32, device='cuda')
+    plane_h = np.ascontiguousarray(plane, dtype=np.float32)
+    L = lib()
+    _ok(L.ref_deproject_points(W, H, _f(pp[0]), _f(pp[1]), _f(focal), _p(depth), _p(pts), _st()))
+    _ok(L.ref_transform_points(W * H, _p(pts), plane_h.ctypes.data_as(ctypes.c_void_p), _st()))
+    _ok(L.ref_filter_points_by_plane(W * H, _f(plane_z_threshold), _p(pts), _st()))
+    _ok(L.ref_setup_depth_image_for_forest(W * H, _p(pts), _p(depth), _st()))
+    torch.cuda.synchronize()
+    return pts.cpu().numpy(), _host_u16(depth)
+
+
 def grow_groups(g_in):
     h, w = g_in.shape
     a = _dev_u16(g_in)

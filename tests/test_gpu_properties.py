@@ -112,6 +112,37 @@ def test_cfg5_shape_deep_forest_matches_c_oracle_on_a_band():
     assert np.array_equal(out.get()[0, 300:308], exp[0, 300:308])
 
 
+@pytest.mark.parametrize('kind', ['dense-smooth', 'dense-noise'])
+def test_cfg5_at_depth_24_matches_the_reference_kernel(kind):
+    """BASELINE configs[4] at its stated size: 8 trees of depth 24 (134 M nodes: 8.05 GB canonical, 8.6 GB packed; leaf ids up
+    to 2.7e8, header byte offsets up to 4.3e9) on a whole 1280x720 frame, against the reference's own
+    evaluate_image_using_forest (src/cuda/tree_eval.cu:24-137, compiled unchanged) run on the same device - no host copy of the
+    forest is needed.  This is where an overflow in the packed ids (csrc/rdf_capi.cu pack, mad.wide.u32 header addressing in
+    csrc/rdf_traverse.cuh) would show."""
+    import torch
+    from rdf_b200 import decision_tree as dt
+    from oracle import ref_kernels as rk
+    H, W = 720, 1280
+    forest = _forest(8, 24, 4, seed=77)
+    depth = _depth(kind, 1, H, W, seed=77)
+    out = dt.cu_array.GPUArray((1, H, W), dtype=np.uint16).fill(65535)
+    dt.DecisionTreeEvaluator().get_labels_forest(forest, depth, out)
+    ref = filled_u16((1, H, W), 65535)
+    rk.eval_forest(forest.forest_cu.tensor, depth.tensor, ref)
+    torch.cuda.synchronize()
+    got, want = to_np(out.tensor), to_np(ref)
+    assert (want != 65535).all()                                   # dense frames: every pixel is evaluated
+    assert len(np.unique(want)) >= 3                               # not a degenerate label map
+    assert np.array_equal(got, want), f'{(got != want).sum()} of {got.size} labels differ from the reference kernel at D=24'
+    # the deepest level is really reached through the packed ids: the last tree's last-level rows are far above 2^31 bytes
+    info = [ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_size_t()]
+    from rdf_b200 import _capi
+    _capi.check(_capi.load().rdf_forest_info(forest.handle(), *[ctypes.byref(i) for i in info]))
+    assert info[1].value == 24 and info[3].value == 8 * ((1 << 24) - 1) * (32 + 2 * 4 * 4)      # 8.59e9 packed bytes
+    del forest, depth, out, ref
+    torch.cuda.empty_cache()
+
+
 def test_histogram_linearity_and_conservation_at_cfg4_width():
     """hist(images A + B) == hist(A) + hist(B) (what the multi-GPU allreduce relies on) and every feature row counts every
     active pixel exactly once, at 848x480 with 200 features x 64 thresholds."""
