@@ -190,10 +190,20 @@ extern "C" int rdf_train_hist(const uint16_t* depth_dev, const uint16_t* labels_
 // same feature: probes of neighbouring pixels share sectors, thresholds are shared-memory broadcasts, and updates are
 // warp-aggregated (match.all when every lane hits the same counter, else match.any), so no shared-memory atomic ever
 // collides within a warp.
+// Tunables (overridable with -D for variant builds, tools/build_variant.sh): threads per CTA, CTAs per SM the shared-memory
+// budget is split over, features evaluated together by one thread.
+#ifndef TB_THREADS
 #define TB_THREADS 1024
+#endif
+#ifndef TB_CTAS_PER_SM
+#define TB_CTAS_PER_SM 1
+#endif
+#ifndef TB_U
+#define TB_U 4                  // features evaluated together by one thread (independent load chains)
+#endif
 #define TB_TILE 8192            // sorted pixels per CTA
 #define TB_MAX_FC 256
-#define TB_U 4                  // features evaluated together by one thread (independent load chains)
+#define TB_SMEM_BUDGET ((size_t)(TB_CTAS_PER_SM == 1 ? 220 : TB_CTAS_PER_SM == 2 ? 110 : 72) * 1024)
 
 struct rdf_bucket_ws {           // layout of the caller-provided workspace
     int total;                   // number of bucketed pixels (device-side value, never read by the host)
@@ -331,6 +341,28 @@ __device__ __forceinline__ int tb_int_thresh(float t) {
 __device__ __forceinline__ void tb_red_shared(unsigned smem_addr, unsigned v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_addr), "r"(v) : "memory");
 }
+// if (leader) red.shared.add.u32 [addr], v  as one predicated instruction
+__device__ __forceinline__ void tb_red_shared_if(bool leader, unsigned smem_addr, unsigned v) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" ::"r"(smem_addr), "r"(v), "r"((unsigned)leader)
+                 : "memory");
+}
+// One step of the threshold search on a running shared address: if (*(int*)(addr + OFF) <= f) addr += INC.
+// (Not volatile: the threshold table is read-only after the CTA's first barrier, and the TB_U chains should interleave freely.)
+template <int OFF, int INC>
+__device__ __forceinline__ void tb_step(unsigned& addr, int f) {
+    asm("{\n\t.reg .pred p;\n\t.reg .s32 t;\n\tld.shared.s32 t, [%0+%1];\n\tsetp.le.s32 p, t, %3;\n\t@p add.u32 %0, %0, %2;\n\t}"
+        : "+r"(addr)
+        : "n"(OFF), "n"(INC), "r"(f));
+}
+// steps LG, LG-1, ..., 0 (thresholds[pos + 2^LG - 1] <= f ? pos += 2^LG) for TB_U interleaved searches, in lock step
+template <int LG, int U>
+__device__ __forceinline__ void tb_search_steps(unsigned (&pa)[U], const int (&f)[U]) {
+    if constexpr (LG >= 0) {
+#pragma unroll
+        for (int u = 0; u < U; u++) tb_step<(4 << LG) - 4, (4 << LG)>(pa[u], f[u]);
+        tb_search_steps<LG - 1, U>(pa, f);
+    }
+}
 __device__ __forceinline__ int tb_lds(unsigned smem_addr) {
     int v;
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_addr));
@@ -340,7 +372,7 @@ __device__ __forceinline__ int tb_lds(unsigned smem_addr) {
 // LOG2NTP: thresholds of a feature are padded in shared memory to NTP = 2^LOG2NTP entries with INT_MAX, so the search is a
 // fixed, fully unrolled sequence of LOG2NTP + 1 loads without bound checks.
 template <int LOG2NTP>
-__global__ void __launch_bounds__(TB_THREADS, 1) rdf_train_hist_bucketed_kernel(const rdf_histb_params p) {
+__global__ void __launch_bounds__(TB_THREADS, TB_CTAS_PER_SM) rdf_train_hist_bucketed_kernel(const rdf_histb_params p) {
     constexpr int NTP = 1 << LOG2NTP;
     extern __shared__ __align__(16) unsigned char tb_smem[];
     float4* off_s = reinterpret_cast<float4*>(tb_smem);                          // [FC]
@@ -435,30 +467,24 @@ __global__ void __launch_bounds__(TB_THREADS, 1) rdf_train_hist_bucketed_kernel(
                     else f[u] = rdf_feature_i<false>(img, p.W, p.H, X, Y, df, rcp, xm, ym, o.x, o.y, o.z, o.w);
                     f[u] = d != 0u ? f[u] : 0;
                 }
-                // bin = #{k : t_k <= f}: binary search by halving steps on byte offsets, then one last compare
-                unsigned pos[TB_U];
+                // bin = #{k : t_k <= f}: binary search by halving steps, then one last compare.  The running value is the shared
+                // ADDRESS of thresholds[pos] (one predicated add per step: load, compare, add), not an index that would need a
+                // select and a second add to become an address (those were 14 of 79 instructions per evaluation,
+                // profiles/r02_ncu_train_hist.md).
+                unsigned pa[TB_U];
 #pragma unroll
-                for (int u = 0; u < TB_U; u++) pos[u] = 0u;
+                for (int u = 0; u < TB_U; u++) pa[u] = tha[u];
+                tb_search_steps<LOG2NTP - 1, TB_U>(pa, f);                               // thresholds[pos + step - 1] <= f ?
 #pragma unroll
-                for (int lg = LOG2NTP - 1; lg >= 0; lg--) {
-#pragma unroll
-                    for (int u = 0; u < TB_U; u++) {
-                        const int t = tb_lds(tha[u] + pos[u] + ((4u << lg) - 4u));      // thresholds[pos + step - 1]
-                        pos[u] += t <= f[u] ? (4u << lg) : 0u;
-                    }
-                }
+                for (int u = 0; u < TB_U; u++) tb_step<0, 4>(pa[u], f[u]);               // pos <= NTP - 1; then pos = bin in 0..NT
 #pragma unroll
                 for (int u = 0; u < TB_U; u++) {
-                    const int t = tb_lds(tha[u] + pos[u]);                              // pos <= NTP - 1
-                    pos[u] += t <= f[u] ? 4u : 0u;                                      // pos = 4 * bin, bin in 0..NT
-                }
-#pragma unroll
-                for (int u = 0; u < TB_U; u++) {
-                    const unsigned key = pos[u] * (unsigned)p.C + label4;               // byte offset of [bin][label]
+                    const unsigned key = (pa[u] - tha[u]) * (unsigned)p.C + label4;     // byte offset of [bin][label]
                     const unsigned dst = hist_base + (unsigned)(j0 + u) * row_bytes + key;
-                    // one shared-memory reduction per distinct counter of the warp (lowest lane of each group)
+                    // one shared-memory reduction per distinct counter of the warp, issued by the lowest lane of each group as a
+                    // PREDICATED instruction (a branch around it cost three more instructions per evaluation)
                     const unsigned grp = __match_any_sync(am, key);
-                    if ((grp & lanemask_lt) == 0u) tb_red_shared(dst, (unsigned)__popc(grp));
+                    tb_red_shared_if((grp & lanemask_lt) == 0u, dst, (unsigned)__popc(grp));
                 }
             }
         }
@@ -521,7 +547,7 @@ static int rdf_hist_bucketed_launch(const uint16_t* depth_dev, const uint16_t* l
     int log2ntp = 0;
     while ((1 << log2ntp) < p.NT) log2ntp++;
     RDF_REQUIRE(log2ntp <= 10, "rdf_train_hist_bucketed: at most 1024 thresholds per feature (got %d)", p.NT);
-    const size_t smem_budget = 220 * 1024;
+    const size_t smem_budget = TB_SMEM_BUDGET;
     const size_t per_feature = sizeof(float4) + sizeof(int) * ((size_t)1 << log2ntp) + sizeof(uint32_t) * (size_t)p.NB * p.C + 1;
     // features per CTA: a multiple of TB_U (the loop evaluates TB_U at a time, the chunk is padded to it) that fits shared memory
     int fc_max = (int)((smem_budget - 64) / per_feature);
@@ -675,6 +701,103 @@ __device__ __forceinline__ unsigned pb_warp_incl_scan(unsigned v, int lane) {
     return v;
 }
 
+// ---- candidate screening -------------------------------------------------------------------------------------------------
+// The exact gain costs two div.rn.f32 per (class, threshold) and was 10 % of HBM peak (profiles/r01_train_cfg4.md).  Almost all
+// candidates lose by far, so each feature is first scored in cheap arithmetic and only features that could hold the winner run
+// the exact sequence.  With ls, rs the side totals, lc / rc the per-class side counts, T = ls + rs and P the parent total,
+//     gain = gini(parent) - (ls/P) (1 - sum (lc/ls)^2) - (rs/P) (1 - sum (rc/rs)^2) = gini(parent) - (T - Q) / P,
+//     Q = sum lc^2 / ls + sum rc^2 / rs,
+// i.e. for one node the gain is an increasing function of Q alone (an empty side contributes 0 to Q and the reference then
+// defines gain = 0, which is the formula's value too when T == P; rows with T != P skip the screen).  Q~ is Q in fp32 with
+// MUFU reciprocals: |Q~ - Q| <= d2 P with d2 < 1e-6 (a dozen roundings of 6e-8 on terms <= P; counts above 2^24 convert with
+// an error of <= 2 counts out of P >= 2^24).  The exact fp32 gain g differs from the real one by d1 < 1e-6 (same count of
+// roundings on values <= 1).  If candidate x has the greatest exact gain and y the greatest Q~ seen anywhere, then
+// g(x) >= g(y) => Q(x) >= Q(y) - 2 d1 P => Q~(x) >= Q~(y) - 2 (d1 + d2) P.  A feature is therefore skipped only when all its
+// candidates have Q~ < (greatest Q~ seen so far) - PB_SCREEN_MARGIN * P with PB_SCREEN_MARGIN = 2e-5 >= 5 x 2 (d1 + d2): no
+// candidate that attains the greatest exact gain is ever skipped, every surviving feature is scored exactly as before, and the
+// winner (greatest gain, ties -> smallest index) is the same candidate.  Tie-heavy nodes simply screen nothing out.
+#define PB_SCREEN_MARGIN 2e-5f
+
+__device__ __forceinline__ uint4 pb_ld4(const uint32_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+__device__ __forceinline__ float pb_q_side(float s0, float s1, float s2, float s3, float n) {
+    // sum c^2 / n, 0 for an empty side
+    const float sq = __fmaf_rn(s3, s3, __fmaf_rn(s2, s2, __fmaf_rn(s1, s1, __fmul_rn(s0, s0))));
+    return n > 0.f ? __fdividef(sq, n) : 0.f;
+}
+
+// Greatest Q~ over the two candidates this lane owns (k = 2 lane, 2 lane + 1) of a feature with NT <= 64 thresholds, -1 if it
+// owns none.  *row_total receives T.  CT == 4: four classes, one 128-bit load per bin; CT == 0: any C, one class at a time.
+struct pb_row4 {                                                   // the bins a lane owns of a 4-class row: 2 lane, 2 lane + 1, and bin 64
+    uint4 a, b, last;
+};
+
+__device__ __forceinline__ pb_row4 pb_load_row4(const uint32_t* __restrict__ h, int NB, int lane) {
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    pb_row4 r;
+    r.a = 2 * lane < NB ? pb_ld4(h + 8 * lane) : z;
+    r.b = 2 * lane + 1 < NB ? pb_ld4(h + 8 * lane + 4) : z;
+    r.last = NB > 64 ? pb_ld4(h + 4 * 64) : z;                     // bin 64 exists only for NT == 64
+    return r;
+}
+
+template <int CT>
+__device__ __forceinline__ float pb_screen_feature(const uint32_t* __restrict__ h, const pb_row4& row, int NT, int C, int lane,
+                                                   unsigned* row_total) {
+    const int NB = NT + 1, k0 = 2 * lane, k1 = k0 + 1;
+    float q0, q1;
+    unsigned T;
+    if (CT == 4) {
+        const uint4 a = row.a, b = row.b, last = row.last;
+        uint4 in = make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);    // inclusive scan over lanes of the pair sums
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned tx = __shfl_up_sync(0xffffffffu, in.x, o), ty = __shfl_up_sync(0xffffffffu, in.y, o);
+            const unsigned tz = __shfl_up_sync(0xffffffffu, in.z, o), tw = __shfl_up_sync(0xffffffffu, in.w, o);
+            if (lane >= o) { in.x += tx; in.y += ty; in.z += tz; in.w += tw; }
+        }
+        const unsigned t0 = __shfl_sync(0xffffffffu, in.x, 31) + last.x, t1 = __shfl_sync(0xffffffffu, in.y, 31) + last.y;
+        const unsigned t2 = __shfl_sync(0xffffffffu, in.z, 31) + last.z, t3 = __shfl_sync(0xffffffffu, in.w, 31) + last.w;
+        T = t0 + t1 + t2 + t3;
+        const float f0 = __uint2float_rn(t0), f1 = __uint2float_rn(t1), f2 = __uint2float_rn(t2), f3 = __uint2float_rn(t3);
+        const float Tf = (f0 + f1) + (f2 + f3);
+        // candidate k1: left = bins 0..k1 = the inclusive scan; candidate k0: that minus bin k1
+        const float l10 = __uint2float_rn(in.x), l11 = __uint2float_rn(in.y), l12 = __uint2float_rn(in.z), l13 = __uint2float_rn(in.w);
+        const float l00 = __uint2float_rn(in.x - b.x), l01 = __uint2float_rn(in.y - b.y), l02 = __uint2float_rn(in.z - b.z),
+                    l03 = __uint2float_rn(in.w - b.w);
+        const float ls1 = (l10 + l11) + (l12 + l13), ls0 = (l00 + l01) + (l02 + l03);
+        q1 = pb_q_side(l10, l11, l12, l13, ls1) + pb_q_side(f0 - l10, f1 - l11, f2 - l12, f3 - l13, Tf - ls1);
+        q0 = pb_q_side(l00, l01, l02, l03, ls0) + pb_q_side(f0 - l00, f1 - l01, f2 - l02, f3 - l03, Tf - ls0);
+    } else {
+        float sl0 = 0.f, sl1 = 0.f, sr0 = 0.f, sr1 = 0.f, ls0 = 0.f, ls1 = 0.f, Tf = 0.f;
+        T = 0u;
+        for (int c = 0; c < C; c++) {
+            const unsigned a = k0 < NB ? __ldg(h + k0 * C + c) : 0u;
+            const unsigned b = k1 < NB ? __ldg(h + k1 * C + c) : 0u;
+            const unsigned last = NB > 64 ? __ldg(h + 64 * C + c) : 0u;
+            unsigned in = a + b;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, in, o);
+                if (lane >= o) in += t;
+            }
+            const unsigned tc = __shfl_sync(0xffffffffu, in, 31) + last;
+            T += tc;
+            const float tf = __uint2float_rn(tc), l1 = __uint2float_rn(in), l0 = __uint2float_rn(in - b);
+            Tf += tf;
+            ls0 += l0; ls1 += l1;
+            sl0 = __fmaf_rn(l0, l0, sl0); sl1 = __fmaf_rn(l1, l1, sl1);
+            sr0 = __fmaf_rn(tf - l0, tf - l0, sr0); sr1 = __fmaf_rn(tf - l1, tf - l1, sr1);
+        }
+        q0 = (ls0 > 0.f ? __fdividef(sl0, ls0) : 0.f) + (Tf - ls0 > 0.f ? __fdividef(sr0, Tf - ls0) : 0.f);
+        q1 = (ls1 > 0.f ? __fdividef(sl1, ls1) : 0.f) + (Tf - ls1 > 0.f ? __fdividef(sr1, Tf - ls1) : 0.f);
+    }
+    *row_total = T;
+    q0 = k0 < NT ? q0 : -1.f;
+    q1 = k1 < NT ? q1 : -1.f;
+    return fmaxf(q0, q1);
+}
+
 // One CTA per active node; each WARP takes whole features (f = warp, warp + PB_WARPS, ...) with lanes across the threshold
 // bins, so a feature's [NT+1][C] histogram (1040 B at NT=64, C=4) is read with coalesced loads; left counts per threshold come
 // from warp prefix sums over the bins.  (The first version gave each thread a feature and walked its 1040 bytes serially:
@@ -682,6 +805,8 @@ __device__ __forceinline__ unsigned pb_warp_incl_scan(unsigned v, int lane) {
 // Per class the Gini terms are accumulated in class order exactly as the reference's compiled helpers do
 // (cvt.rn.f32.u64, div.rn, fma; tree_train.cu:72-89).  Winner = greatest gain, ties -> smallest candidate index
 // (= first in proposal order: feature-major, threshold-minor).
+// SCREEN: -1 = score every feature exactly; 4 / 0 = screen first (pb_screen_feature<4> for C == 4, <0> for any C; NT <= 64).
+template <int SCREEN>
 __global__ void __launch_bounds__(PB_THREADS) rdf_train_pick_best_kernel(const rdf_pick_params p) {
     const int a = blockIdx.x;
     if (a >= p.num_active) return;
@@ -701,6 +826,7 @@ __global__ void __launch_bounds__(PB_THREADS) rdf_train_pick_best_kernel(const r
     __shared__ int red_i[PB_WARPS];
     __shared__ float s_gini_parent;
     __shared__ unsigned long long s_parent_sum;
+    __shared__ unsigned s_qmax;                                    // greatest Q~ any warp of the CTA has seen (float bits, Q~ >= 0)
 
     for (int c = threadIdx.x; c < C; c += PB_THREADS) par[c] = p.parent_counts[(size_t)node * C + c];
     __syncthreads();
@@ -709,6 +835,7 @@ __global__ void __launch_bounds__(PB_THREADS) rdf_train_pick_best_kernel(const r
         for (int c = 0; c < C; c++) s += par[c];
         s_parent_sum = s;
         s_gini_parent = rdf_gini(par, C, s);
+        s_qmax = 0u;
     }
     __syncthreads();
     const unsigned long long parent_sum = s_parent_sum;
@@ -717,8 +844,31 @@ __global__ void __launch_bounds__(PB_THREADS) rdf_train_pick_best_kernel(const r
 
     float best_g = -1.f;
     int best_i = 0x7fffffff;
+    float q_run = 0.f;                                             // greatest Q~ this warp has seen (warp-uniform)
+    const float q_margin = PB_SCREEN_MARGIN * fmaxf(p_sum_f, 1.f);
+    // SCREEN == 4: the next feature's row is loaded before the current one is scored (one row per warp in flight is ~33 KB per
+    // SM, about what HBM latency x bandwidth needs; two rows leave slack)
+    const uint32_t* hist_node = p.hist + (size_t)slot * p.f_stride * p.NB * C;
+    pb_row4 row_next;
+    if (SCREEN == 4 && warp < p.F) row_next = pb_load_row4(hist_node + (size_t)warp * p.NB * C, p.NB, lane);
     for (int f = warp; f < p.F; f += PB_WARPS) {
-        const uint32_t* h = p.hist + ((size_t)slot * p.f_stride + f) * p.NB * C;
+        const uint32_t* h = hist_node + (size_t)f * p.NB * C;
+        if (SCREEN >= 0) {
+            pb_row4 row;
+            if (SCREEN == 4) {
+                row = row_next;
+                if (f + PB_WARPS < p.F) row_next = pb_load_row4(h + (size_t)PB_WARPS * p.NB * C, p.NB, lane);
+            }
+            unsigned row_total;
+            const float qm = pb_screen_feature<SCREEN>(h, row, p.NT, C, lane, &row_total);
+            const float q_seen = fmaxf(q_run, __uint_as_float(*reinterpret_cast<volatile unsigned*>(&s_qmax)));
+            const float q_feat = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(qm, 0.f))));
+            if (q_feat > q_seen && lane == 0) atomicMax(&s_qmax, __float_as_uint(q_feat));
+            q_run = fmaxf(q_seen, q_feat);
+            // skip when no candidate of this feature can attain the greatest exact gain (see PB_SCREEN_MARGIN); a row whose
+            // total differs from the parent's count (never with this library's own histograms) is always scored exactly
+            if (q_feat < q_run - q_margin && (unsigned long long)row_total == parent_sum) continue;
+        }
         // class totals over all NT + 1 bins
         unsigned T = 0;
         for (int c = 0; c < C; c++) {
@@ -855,6 +1005,14 @@ __global__ void __launch_bounds__(128) rdf_train_pick_finalize_kernel(const rdf_
     pb_finalize(p, a, node, best_g, best_i, cc, cc + p.C, p.parent_counts + (size_t)node * p.C);
 }
 
+// RDF_PICK_NO_SCREEN=1 scores every candidate exactly (experiments / A-B tests of the screen)
+static void pb_launch(const rdf_pick_params& p, size_t smem, cudaStream_t st) {
+    const bool screen = p.NT <= 64 && RDF_GETENV_ONCE("RDF_PICK_NO_SCREEN") == nullptr;
+    if (!screen) rdf_train_pick_best_kernel<-1><<<p.num_active, PB_THREADS, smem, st>>>(p);
+    else if (p.C == 4) rdf_train_pick_best_kernel<4><<<p.num_active, PB_THREADS, smem, st>>>(p);
+    else rdf_train_pick_best_kernel<0><<<p.num_active, PB_THREADS, smem, st>>>(p);
+}
+
 extern "C" int rdf_train_pick_best(int num_active, const int32_t* active_nodes_dev, const int32_t* node_slot_dev,
                                    const uint64_t* parent_counts_dev, const uint32_t* hist_dev, int num_slots,
                                    const float* offsets_dev, const float* thresholds_dev, int num_features,
@@ -877,9 +1035,8 @@ extern "C" int rdf_train_pick_best(int num_active, const int32_t* active_nodes_d
     p.C = num_classes; p.level = level; p.D = max_depth;
     p.cand_gain = nullptr; p.cand_idx = nullptr; p.cand_counts = nullptr; p.f_offset = 0; p.f_stride = num_features;
     const size_t smem = sizeof(unsigned long long) * 3 * (size_t)num_classes + sizeof(unsigned) * (size_t)PB_WARPS * 2 * num_classes;
-    if (smem > 48 * 1024) RDF_ENSURE_DYN_SMEM(rdf_train_pick_best_kernel, smem);
-    RDF_REQUIRE(smem <= 220 * 1024, "rdf_train_pick_best: %d classes exceed the shared-memory scratch", num_classes);
-    rdf_train_pick_best_kernel<<<num_active, PB_THREADS, smem, rdf_stream(stream)>>>(p);
+    RDF_REQUIRE(smem <= 48 * 1024, "rdf_train_pick_best: %d classes exceed the shared-memory scratch", num_classes);
+    pb_launch(p, smem, rdf_stream(stream));
     RDF_LAUNCH_CHECK("rdf_train_pick_best_kernel");
     return RDF_OK;
 }
@@ -907,7 +1064,7 @@ extern "C" int rdf_train_pick_candidates(int num_active, const int32_t* active_n
     p.f_offset = feature_offset;
     p.f_stride = feature_stride;
     const size_t smem = sizeof(unsigned long long) * 3 * (size_t)num_classes + sizeof(unsigned) * (size_t)PB_WARPS * 2 * num_classes;
-    rdf_train_pick_best_kernel<<<num_active, PB_THREADS, smem, rdf_stream(stream)>>>(p);
+    pb_launch(p, smem, rdf_stream(stream));
     RDF_LAUNCH_CHECK("rdf_train_pick_best_kernel (candidates)");
     return RDF_OK;
 }

@@ -3,6 +3,7 @@
 bucket (counting sort by node) | histogram | pick-best | next-active | advance-pixels.  One JSON line per level."""
 import argparse
 import ctypes
+import hashlib
 import json
 import os
 import sys
@@ -85,7 +86,11 @@ def main():
             t = {'bucket': ev[0].elapsed_time(ev[1]), 'zero': tz, 'hist': th, 'pick_best': tp,
                  'next_active': ev[2].elapsed_time(ev[3]), 'advance': ev[3].elapsed_time(ev[4])}
         print(json.dumps({'level': level, 'active_nodes': S, 'features': F, 'ms': {k: round(v, 3) for k, v in t.items()},
-                          'next_active_nodes': int(num_next.item()), 'hist_GB': S * F * (NT + 1) * C * 4 / 1e9}), flush=True)
+                          'next_active_nodes': int(num_next.item()), 'hist_GB': S * F * (NT + 1) * C * 4 / 1e9,
+                          'pick_best_GBps': S * F * (NT + 1) * C * 4 / 1e6 / max(t['pick_best'], 1e-9),
+                          'pick_screen': not os.environ.get('RDF_PICK_NO_SCREEN'),
+                          # identical split records whatever the kernel variant: digest of the level's node records + child counts
+                          'records_md5': hashlib.md5(tree.cpu().numpy().tobytes() + next_counts.cpu().numpy().tobytes()).hexdigest()}), flush=True)
         del hist, ws, nodes
 
 
