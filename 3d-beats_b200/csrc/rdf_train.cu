@@ -192,15 +192,19 @@ extern "C" int rdf_train_hist(const uint16_t* depth_dev, const uint16_t* labels_
 // collides within a warp.
 // Tunables (overridable with -D for variant builds, tools/build_variant.sh): threads per CTA, CTAs per SM the shared-memory
 // budget is split over, features evaluated together by one thread.
+// Measured on cfg4 (profiles/r02_train_cfg4.md): the kernel is latency-bound (1.65 eligible warps per scheduler of 8 resident), so
+// eight interleaved feature chains per thread and two half-size CTAs per SM (one keeps issuing while the other sits at its
+// per-node flush barrier) beat 1 x 1024 threads x 4 chains by 9-10 %.
 #ifndef TB_THREADS
-#define TB_THREADS 1024
+#define TB_THREADS 512
 #endif
 #ifndef TB_CTAS_PER_SM
-#define TB_CTAS_PER_SM 1
+#define TB_CTAS_PER_SM 2
 #endif
 #ifndef TB_U
-#define TB_U 4                  // features evaluated together by one thread (independent load chains)
+#define TB_U 8                  // features evaluated together by one thread (independent load chains)
 #endif
+static_assert((TB_U & (TB_U - 1)) == 0 && TB_U >= 1, "TB_U must be a power of two: feature chunks are rounded with bit masks");
 #define TB_TILE 8192            // sorted pixels per CTA
 #define TB_MAX_FC 256
 #define TB_SMEM_BUDGET ((size_t)(TB_CTAS_PER_SM == 1 ? 220 : TB_CTAS_PER_SM == 2 ? 110 : 72) * 1024)

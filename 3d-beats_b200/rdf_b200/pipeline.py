@@ -25,33 +25,39 @@ def pinned_like(shape, np_dtype):
 
 
 class HostBatchEvaluator:
-    def __init__(self, evaluator, forest, frame_shape, chunk_frames=64, labels_reduce=1, scale_factor=1.):
+    def __init__(self, evaluator, forest, frame_shape, chunk_frames=64, labels_reduce=1, scale_factor=1., buffers=3):
+        """buffers: device chunk buffers in rotation (3: the H2D of chunk i+1, the evaluation of chunk i and the D2H of chunk i-1
+        each own one, so neither copy direction ever waits for the other's buffer)."""
         self.ev = evaluator
         self.forest = forest
         self.H, self.W = frame_shape
         self.r = labels_reduce
         self.scale = scale_factor
         self.chunk = int(chunk_frames)
+        self.nbuf = max(2, int(buffers))
         h, w = self.H // self.r, self.W // self.r
-        self.depth_dev = [GPUArray((self.chunk, self.H, self.W), dtype=np.uint16) for _ in range(2)]
-        self.labels_dev = [GPUArray((self.chunk, h, w), dtype=np.uint16) for _ in range(2)]
+        self.depth_dev = [GPUArray((self.chunk, self.H, self.W), dtype=np.uint16) for _ in range(self.nbuf)]
+        self.labels_dev = [GPUArray((self.chunk, h, w), dtype=np.uint16) for _ in range(self.nbuf)]
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream() for _ in range(3))
         self.bytes_h2d = 0
         self.bytes_d2h = 0
 
-    def run(self, depth_host, labels_host, prefill=65535):
+    def run(self, depth_host, labels_host, prefill=65535, copy_only=False):
         """depth_host: pinned torch uint16[N,H,W]; labels_host: pinned torch uint16[N,h,w] (fully overwritten:
-        skipped pixels hold `prefill`, as after the reference's labels.fill(65535) + get_labels_forest + .get())."""
+        skipped pixels hold `prefill`, as after the reference's labels.fill(65535) + get_labels_forest + .get()).
+        copy_only: the same chunked H2D / D2H traffic with NO kernel in between - the control experiment that separates what the
+        host <-> device copies cost from what the evaluation costs (labels_host then receives whatever the buffers held)."""
         N = depth_host.shape[0]
         cur = torch.cuda.current_stream()
         for s in (self.s_in, self.s_run, self.s_out):
             s.wait_stream(cur)
-        ev_in = [None, None]      # H2D of buffer b finished
-        ev_run = [None, None]     # eval on buffer b finished
-        ev_out = [None, None]     # D2H of buffer b finished (buffer reusable)
+        nbuf = self.nbuf
+        ev_in = [None] * nbuf     # H2D of buffer b finished
+        ev_run = [None] * nbuf    # eval on buffer b finished
+        ev_out = [None] * nbuf    # D2H of buffer b finished (buffer reusable)
         self.bytes_h2d = self.bytes_d2h = 0
         for ci, n0 in enumerate(range(0, N, self.chunk)):
-            b = ci & 1
+            b = ci % nbuf
             nb = min(self.chunk, N - n0)
             d_dev = self.depth_dev[b][:nb] if nb < self.chunk else self.depth_dev[b]
             l_dev = self.labels_dev[b][:nb] if nb < self.chunk else self.labels_dev[b]
@@ -64,8 +70,9 @@ class HostBatchEvaluator:
                 self.s_run.wait_event(ev_in[b])
                 if ev_out[b] is not None:
                     self.s_run.wait_event(ev_out[b])              # previous D2H of this labels buffer finished
-                l_dev.fill(prefill)
-                self.ev.get_labels_forest(self.forest, d_dev, l_dev, labels_reduce=self.r, scale_factor=self.scale)
+                if not copy_only:
+                    l_dev.fill(prefill)
+                    self.ev.get_labels_forest(self.forest, d_dev, l_dev, labels_reduce=self.r, scale_factor=self.scale)
                 ev_run[b] = torch.cuda.Event(); ev_run[b].record(self.s_run)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(ev_run[b])

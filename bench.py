@@ -7,14 +7,24 @@
 Workload (default `cfg3`, BASELINE.json configs[2], the configuration the Mpixels/s metric is quoted on):
 4096 synthetic 848x480 uint16 depth frames (dense-smooth), random-init 4-tree depth-20 forest, 4 classes,
 sharded by frame over the ranks with no data-path collective (strong scaling: the 4096 frames are split).
-A step = one pass of get_labels_forest over the rank's frames, inputs resident in HBM.  Extra objects on the line:
-  e2e          same metric through the host-buffer API (pinned host frames -> label maps in pinned host memory),
-               H2D and D2H inside the timed region
-  roofline     algorithmic bytes (4 + T*(32*D + 4*C) B per pixel) / kernel time vs the measured HBM peak
-  latency      BASELINE.json configs[1]: one 848x480 frame -> 2-layer stacked forest + 6-round mean shift, p50/p95/p99
+A step = one pass of get_labels_forest over the rank's frames, inputs resident in HBM.  Objects on the (compact) line, in
+this order so that a truncated tail keeps the headline facts:
+  latency      BASELINE.json configs[1]: one 848x480 frame -> 2-layer stacked forest + 6-round mean shift, p50/p99 (N=1)
+  configs      the other BASELINE configs, each with mpix_s + parity: cfg1, cfg3_noise, cfg3_survey_forest (the SURVEY 8d
+               generator uploaded from NumPy instead of the on-device hash forest), cfg5, cfg5_noise (N=1)
+  e2e          same metric through the host-buffer API (pinned host frames -> label maps in pinned host memory), H2D and D2H
+               inside the timed region; copy_only_* = the same chunked copies with no kernel (the host-copy ceiling)
+  roofline     algorithmic bytes (4 + T*(32*D + 4*C) B per pixel) / kernel time vs the measured HBM peak, plus
+               `binding` = the physically bounded fraction (L1 data-pipe wavefronts, from the ncu capture in profiles/)
   ref_gpu      the reference's own kernels (compiled unchanged for sm_100a) on the same GPU, same inputs (sub-batch)
-  cpu_baseline the C oracle on the host cores over a bounded sample (rank 0, N=1 only)
-  train_cfg4   BASELINE.json configs[3]: one level of the training split search (bucket + histogram + pick-best)
+  cpu_baseline the C oracle on the host cores over a bounded sample; cpu_baseline_numpy = the NumPy oracle, one process and a
+               pool of all host cores (N=1)
+  train_cfg4   BASELINE.json configs[3]: the training split search at levels 0/4/8/12 (bucket + histogram + pick-best); under
+               torchrun (N>1) images are sharded and both exchange modes are timed (NVLink reduce-scatter fused into the
+               histogram kernel, NCCL allreduce), with a single-GPU run of the same level beside them and a parity check of a
+               whole sharded training
+  hands_frame  one whole product frame (N=1)
+Verbose per-leg details go to stderr as `# details: {...}`.
 """
 import argparse
 import json
@@ -283,11 +293,12 @@ def latency_cfg2(iters=1000, warm=100):
     }
 
 
-def train_cfg4(level=8, iters=2):
+def train_cfg4(level=8, iters=2, check=True):
     """BASELINE configs[3] on this rank's GPU: one level of the split search over 42 dense-smooth 848x480 frames (17.1 M labelled
-    pixels), 2000 features x 64 thresholds, C = 4, 2^level active nodes: bucket the pixels by node + histogram + pick-best.
-    A feature sub-block is checked against the C oracle on two frames."""
+    pixels, ~13 M of them still active at the deeper levels), 2000 features x 64 thresholds, C = 4, 2^level active nodes: bucket
+    the pixels by node + histogram + pick-best.  A feature sub-block is checked against the C oracle on two frames."""
     import ctypes
+    import hashlib
     import torch
     from rdf_b200 import _capi, synth
     from oracle import c_oracle as co
@@ -313,15 +324,23 @@ def train_cfg4(level=8, iters=2):
     _capi.check(lib.rdf_train_bucket_workspace_bytes(N * H * W, S, ctypes.byref(need)))
     ws = torch.zeros(((need.value + 3) // 4,), dtype=torch.int32, device='cuda')
     st = _capi.stream_ptr
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 
-    def one_level():
+    def one_level(timed=False):
+        best_gain.fill_(-1.0)
         _capi.check(lib.rdf_train_bucket(_capi.dptr(nodes), N * H * W, _capi.dptr(slot), S, _capi.dptr(ws), need.value, st()))
         hist.zero_()
+        if timed:
+            ev[0].record()
         _capi.check(lib.rdf_train_hist_bucketed(_capi.dptr(depth), _capi.dptr(labels), N, W, H, _capi.dptr(ws), S, _capi.dptr(offsets),
                                                 _capi.dptr(thresholds), F, NT, C, _capi.dptr(hist), st()))
+        if timed:
+            ev[1].record()
         _capi.check(lib.rdf_train_pick_best(S, _capi.dptr(slot), _capi.dptr(slot), _capi.dptr(parent), _capi.dptr(hist), S,
                                             _capi.dptr(offsets), _capi.dptr(thresholds), F, NT, C, level, D, _capi.dptr(tree),
                                             _capi.dptr(next_counts), _capi.dptr(best_gain), st()))
+        if timed:
+            ev[2].record()
     one_level()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -331,19 +350,75 @@ def train_cfg4(level=8, iters=2):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-    nf = 6                                                       # parity: 6 features x 64 thresholds on 2 frames vs the C oracle
-    h2 = torch.zeros((S, nf, NT + 1, C), dtype=torch.int32, device='cuda')
-    nodes2 = nodes[:2].contiguous()
-    _capi.check(lib.rdf_train_bucket(_capi.dptr(nodes2), 2 * H * W, _capi.dptr(slot), S, _capi.dptr(ws), need.value, st()))
-    _capi.check(lib.rdf_train_hist_bucketed(_capi.dptr(depth[:2]), _capi.dptr(labels[:2]), 2, W, H, _capi.dptr(ws), S, _capi.dptr(offsets[:nf]),
-                                            _capi.dptr(thresholds[:nf]), nf, NT, C, _capi.dptr(h2), st()))
+    one_level(timed=True)                                        # per-kernel split of one more level
     torch.cuda.synchronize()
-    exp = co.train_hist(depth_np[:2], labels_np[:2], nodes_np[:2], np.arange(S, dtype=np.int32), S, off_np[:nf], th_np[:nf], C)
-    px = N * H * W
-    return {'workload': f'cfg4: {px} labelled pixels (42 frames 848x480), {F} features x {NT} thresholds, C={C}, level {level} ({S} nodes)',
-            'ms_per_level': ms, 'g_feature_evals_per_s': px * F / ms / 1e6, 'algorithmic_GBps': (px * 8 + px * F * 8) / ms / 1e6,
-            'histogram_bit_exact_vs_c_oracle': bool(np.array_equal(h2.cpu().numpy().view(np.uint32), exp)),
-            'what': 'rdf_train_bucket + rdf_train_hist_bucketed + rdf_train_pick_best, inputs resident'}
+    hist_ms, pick_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+    digest = hashlib.md5(tree.cpu().numpy().tobytes() + next_counts.cpu().numpy().tobytes()).hexdigest()
+    active_px = int((nodes_np >= 0).sum())
+    out = {'level': level, 'nodes': S, 'ms_per_level': ms, 'hist_ms': hist_ms, 'pick_best_ms': pick_ms,
+           'pick_best_GBps': S * F * (NT + 1) * C * 4 / 1e6 / pick_ms, 'active_px': active_px,
+           'g_feature_evals_per_s': active_px * F / ms / 1e6, 'algorithmic_GBps': (active_px * 8 + active_px * F * 8) / ms / 1e6,
+           'records_md5': digest}
+    if check:
+        nf = 6                                                   # parity: 6 features x 64 thresholds on 2 frames vs the C oracle
+        h2 = torch.zeros((S, nf, NT + 1, C), dtype=torch.int32, device='cuda')
+        nodes2 = nodes[:2].contiguous()
+        _capi.check(lib.rdf_train_bucket(_capi.dptr(nodes2), 2 * H * W, _capi.dptr(slot), S, _capi.dptr(ws), need.value, st()))
+        _capi.check(lib.rdf_train_hist_bucketed(_capi.dptr(depth[:2]), _capi.dptr(labels[:2]), 2, W, H, _capi.dptr(ws), S, _capi.dptr(offsets[:nf]),
+                                                _capi.dptr(thresholds[:nf]), nf, NT, C, _capi.dptr(h2), st()))
+        torch.cuda.synchronize()
+        exp = co.train_hist(depth_np[:2], labels_np[:2], nodes_np[:2], np.arange(S, dtype=np.int32), S, off_np[:nf], th_np[:nf], C)
+        out['histogram_bit_exact_vs_c_oracle'] = bool(np.array_equal(h2.cpu().numpy().view(np.uint32), exp))
+    del hist, ws, depth, labels, nodes
+    torch.cuda.empty_cache()
+    return out
+
+
+def train_cfg4_sweep(levels=(0, 4, 8, 12)):
+    """one full level sweep at 1 / 16 / 256 / 4096 active nodes."""
+    res = {'workload': 'cfg4: 42 frames 848x480 (17.1 M labelled px), 2000 features x 64 thresholds, C=4; rdf_train_bucket + '
+                       'rdf_train_hist_bucketed + rdf_train_pick_best, inputs resident', 'levels': {}}
+    for lv in levels:
+        r = train_cfg4(lv, check=(lv == 8))
+        res['levels'][str(lv)] = {k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items() if k not in ('level',)}
+    return res
+
+
+def train_cfg4_multi_gpu(levels=(0, 8, 12)):
+    """The path's one collective, under torchrun (every rank calls this): images sharded over the ranks, both exchange modes
+    (tools/bench_train_mgpu.py), a whole sharded training checked against single-GPU training (tools/mgpu_check.py), and - on rank 0
+    alone, afterwards - the same levels on one GPU for the efficiency."""
+    import importlib.util
+    import torch
+    from rdf_b200 import dist as rdist
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, 'tools', name + '.py'))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    rank, world, _ = rdist.env_rank_world()
+    per_level = load('bench_train_mgpu').run(levels=list(levels), iters=3)
+    parity = load('mgpu_check').run()
+    out = None
+    if rank == 0:
+        out = {'n_gpus': world, 'exchange': 'p2p = reduce-scatter fused into the histogram kernel over NVLink + all-gather of per-node '
+                                            'winners; allreduce = NCCL sum-allreduce of the whole histogram',
+               'levels': {}, 'sharded_training_matches_single_gpu': parity['sharded_training_matches_single_gpu'],
+               'eval_shards_match_single_gpu': parity['eval_shards_match_single_gpu'],
+               'exchange_modes_tested': parity['exchange_modes_tested']}
+        for rec in per_level:
+            one = train_cfg4(rec['cfg4_level'], check=False)
+            t1 = one['ms_per_level']
+            out['levels'][str(rec['cfg4_level'])] = {
+                'nodes': rec['active_nodes'], 'ms_per_level_p2p': round(rec['ms_per_level_p2p'], 3),
+                'ms_per_level_allreduce': round(rec['ms_per_level_allreduce'], 3), 'ms_per_level_1gpu': round(t1, 3),
+                'efficiency_p2p': round(t1 / (world * rec['ms_per_level_p2p']), 3),
+                'efficiency_allreduce': round(t1 / (world * rec['ms_per_level_allreduce']), 3),
+                'node_records_identical': bool(rec['node_records_identical'] and rec['records_md5'] == one['records_md5']),
+                'records_md5': rec['records_md5']}
+    rdist.barrier()
+    return out
 
 
 def hands_frame(iters=500):
@@ -380,6 +455,195 @@ def ref_gpu_rate(forest_canon, depth_dev, frames, H, W, steps=2):
                     'geometry (block (1024//T, T)), same frames and forest, inputs resident', 'labels': labels}
 
 
+def make_forest(T, D, C, seed, kind='hash'):
+    """kind 'hash': rdf_synth_forest on the device (csrc/rdf_synth.cu: every node from a hash of its index, each of ux, uy, vx, vy
+    independently log2-uniform in magnitude - a 7.5 GiB forest is generated in place); 'survey': the SURVEY 8d generator
+    (synth.random_forest: direction U(0, 2 pi), magnitude e^U(0,14)) drawn with NumPy and uploaded."""
+    from rdf_b200 import _capi, synth
+    from rdf_b200 import decision_tree as dt
+    forest = dt.DecisionForest(T, D, C)
+    if kind == 'survey':
+        forest.forest_cu.set(synth.random_forest(T, D, C, seed=seed))
+    else:
+        _capi.check(_capi.load().rdf_synth_forest(_capi.dptr(forest.forest_cu), T, D, C, seed, _capi.stream_ptr()))
+    return forest
+
+
+FOREST_DESC = {'hash': 'hash_forest (on-device, per-component log2-uniform offsets)', 'survey': 'SURVEY 8d generator (NumPy, uploaded)'}
+
+
+def time_eval(forest, kind, frames, W, H, steps, warmup, seed, first_frame=0, single=None):
+    """Device time of `steps` passes of get_labels_forest, inputs resident.  single (one-frame workloads): a different frame every
+    step and a 256 MB write to flush L2 before it, per-step events.  Returns (ms_per_step, depth, labels) - the device arrays of the
+    LAST step stay available for parity checks."""
+    import torch
+    from rdf_b200 import _capi
+    from rdf_b200 import decision_tree as dt
+    lib = _capi.load()
+    single = (frames == 1) if single is None else single
+    ring = (steps + warmup) if single else frames
+    depth = dt.cu_array.GPUArray((ring, H, W), dtype=np.uint16)
+    _capi.check(lib.rdf_synth_depth(_capi.dptr(depth), KIND_ID[kind], ring, W, H, seed, first_frame, _capi.stream_ptr()))
+    labels = dt.cu_array.GPUArray((ring, H, W), dtype=np.uint16).fill(65535)
+    ev = dt.DecisionTreeEvaluator()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if single:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+        for k in range(warmup):
+            ev.get_labels_forest(forest, depth[k:k + 1], labels[k:k + 1])
+        torch.cuda.synchronize()
+        elapsed = 0.0
+        for k in range(steps):
+            flush.zero_()
+            e0.record()
+            ev.get_labels_forest(forest, depth[warmup + k:warmup + k + 1], labels[warmup + k:warmup + k + 1])
+            e1.record()
+            torch.cuda.synchronize()
+            elapsed += e0.elapsed_time(e1)
+        del flush
+    else:
+        for _ in range(warmup):
+            ev.get_labels_forest(forest, depth, labels)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            ev.get_labels_forest(forest, depth, labels)
+        e1.record()
+        torch.cuda.synchronize()
+        elapsed = e0.elapsed_time(e1)
+    return elapsed / steps, depth, labels
+
+
+def parity_vs_c_oracle(forest, kind, W, H, seed, frame_index, labels_frame):
+    """One frame of what was timed against the C oracle (host threads)."""
+    from rdf_b200 import synth
+    from oracle import c_oracle as co
+    d0 = synth.depth_frames(kind, 1, H, W, seed=seed, first_frame=frame_index)
+    exp = np.full((1, H, W), 65535, np.uint16)
+    co.eval_forest(forest.forest_cu.get(), d0, exp, nthreads=host_cores())
+    return bool(np.array_equal(labels_frame.get(), exp))
+
+
+def parity_vs_reference_kernel(forest, depth_frame, labels_frame):
+    """One frame of what was timed against the reference's own kernel on the device (no host copy of the forest: cfg5's is 8 GB)."""
+    import torch
+    from oracle import ref_kernels as rk
+    if not rk.available():
+        return None
+    ref = torch.full(tuple(labels_frame.shape), -1, dtype=torch.int16, device='cuda').view(torch.uint16)
+    rk.eval_forest(forest.forest_cu.tensor, depth_frame.tensor, ref)
+    torch.cuda.synchronize()
+    return bool(torch.equal(ref.view(torch.int16), labels_frame.tensor.view(torch.int16)))
+
+
+def other_configs(seed):
+    """BASELINE.json's remaining configurations as compact {mpix_s, parity} entries (N = 1, rank 0)."""
+    import torch
+    out = {}
+
+    def entry(name, T, D, C, W, H, kind, frames, steps, warmup, forest, checker, note=None):
+        ms, depth, labels = time_eval(forest, kind, frames, W, H, steps, warmup, seed)
+        last = (steps + warmup - 1) if frames == 1 else 0
+        if checker == 'ref_kernel':
+            par = parity_vs_reference_kernel(forest, depth[last:last + 1], labels[last:last + 1])
+        else:
+            par = parity_vs_c_oracle(forest, kind, W, H, seed, last, labels[last:last + 1])
+        e = {'mpix_s': round(frames * H * W / ms / 1e3, 1), 'ms_per_step': round(ms, 4), 'parity': par,
+             'parity_vs': 'reference kernel on the device, whole frame' if checker == 'ref_kernel' else 'C oracle, one frame',
+             'frac_logical_roofline': round(b_alg_per_pixel(T, D, C) * frames * H * W / (ms * 1e-3) / 1e9 / measured_peaks()[0], 3)}
+        if note:
+            e['note'] = note
+        out[name] = e
+        del depth, labels
+        torch.cuda.empty_cache()
+
+    f1 = make_forest(3, 16, 4, seed)
+    entry('cfg1', 3, 16, 4, 848, 480, 'dense-smooth', 1, 20, 5, f1, 'c_oracle', 'one frame per step, new frame + L2 flush each step')
+    del f1
+    f3 = make_forest(4, 20, 4, seed)
+    entry('cfg3_noise', 4, 20, 4, 848, 480, 'dense-noise', 512, 3, 3, f3, 'c_oracle', '512 of the 4096 frames per step')
+    del f3
+    f3s = make_forest(4, 20, 4, seed, 'survey')
+    entry('cfg3_survey_forest', 4, 20, 4, 848, 480, 'dense-smooth', 512, 3, 3, f3s, 'c_oracle',
+          '512 frames per step, forest = ' + FOREST_DESC['survey'])
+    del f3s
+    torch.cuda.empty_cache()
+    f5 = make_forest(8, 24, 4, seed)
+    entry('cfg5', 8, 24, 4, 1280, 720, 'dense-smooth', 1, 10, 3, f5, 'ref_kernel', 'one frame per step, new frame + L2 flush each step')
+    entry('cfg5_noise', 8, 24, 4, 1280, 720, 'dense-noise', 1, 10, 3, f5, 'ref_kernel', 'one frame per step, new frame + L2 flush each step')
+    del f5
+    torch.cuda.empty_cache()
+    return out
+
+
+def numpy_baseline_main(args):
+    """--numpy-baseline (a subprocess of the default arm, started before it touches CUDA): the NumPy oracle (SURVEY 8d's CPU
+    baseline) on a bounded sample of the workload - one process on a band of rows, then a multiprocessing pool of all host cores
+    over the row bands of one whole frame.  Prints one JSON object."""
+    import multiprocessing as mp
+    from rdf_b200 import synth
+    from oracle import numpy_oracle as no
+    frames, W, H, T, D, C, kind = WORKLOADS[args.workload]
+    forest = synth.hash_forest(T, D, C, seed=args.seed)
+    depth = synth.depth_frames(kind, 1, H, W, seed=args.seed)
+    cores = host_cores()
+
+    def band(y0, y1):
+        filt = np.zeros((1, H, W), np.uint16)
+        filt[0, y0:y1] = 1
+        lab = np.full((1, H, W), 65535, np.uint16)
+        no.eval_forest(forest, depth, lab, 1, filt, 1)
+        return lab[0, y0:y1]
+    rows1 = max(8, H // 4)
+    t0 = time.perf_counter()
+    band(0, rows1)
+    t1 = time.perf_counter() - t0
+    single = rows1 * W / t1 / 1e6
+    global _NB_BAND
+    _NB_BAND = band
+    bands = [(i * H // cores, (i + 1) * H // cores) for i in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context('fork').Pool(cores) as pool:
+        parts = pool.starmap(_nb_call, bands)
+    t2 = time.perf_counter() - t0
+    print(json.dumps({'unit': 'Mpixels/s', 'single_process': single, 'pool': H * W / t2 / 1e6, 'cores': cores, 'kind': 'port (NumPy oracle)',
+                      'sample': f'single: {rows1} rows of one {W}x{H} frame ({t1:.1f} s); pool: one whole frame in {cores} row bands '
+                                f'({t2:.1f} s); forest and frame of the workload', 'labelled_px_pool': int(sum((p != 65535).sum() for p in parts))}),
+          flush=True)
+
+
+_NB_BAND = None
+
+
+def _nb_call(y0, y1):
+    return _NB_BAND(y0, y1)
+
+
+def numpy_baseline(args):
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), '--numpy-baseline', '--workload', args.workload, '--seed', str(args.seed)],
+                             capture_output=True, text=True, timeout=300, env=dict(os.environ, CUDA_VISIBLE_DEVICES=''))
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:
+        return {'error': repr(e)[:200]}
+
+
+def binding_from_profile(workload):
+    """The physically bounded fraction of the dominant kernel, from the committed ncu capture of this workload's step."""
+    path = os.path.join(ROOT, 'profiles', 'eval_traffic.json')
+    try:
+        tj = json.load(open(path))
+        if tj.get('workload') == workload and 'binding' in tj:
+            return tj['binding'], tj.get('dram_bytes_per_pixel')
+        return None, (tj.get('dram_bytes_per_pixel') if tj.get('workload') == workload else None)
+    except Exception:
+        return None, None
+
+
+def r(x, n=3):
+    return round(float(x), n)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -387,19 +651,30 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg3', choices=sorted(WORKLOADS))
+    ap.add_argument('--forest', default='hash', choices=['hash', 'survey'], help='forest generator of the headline workload')
     ap.add_argument('--frames', type=int, default=0, help='override the number of frames (debug)')
     ap.add_argument('--seed', type=int, default=1234)
     ap.add_argument('--ref-frames', type=int, default=4, help='frames per step of the --impl reference CPU arm')
-    ap.add_argument('--no-extras', action='store_true', help='skip latency / ref_gpu / cpu_baseline / e2e legs')
-    ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--no-extras', action='store_true', help='skip every leg but the headline number')
+    ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--latency-only', action='store_true', help='only the cfg2 frame-latency leg (profiling aid)')
     ap.add_argument('--latency-iters', type=int, default=1000)
+    ap.add_argument('--numpy-baseline', action='store_true', help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.numpy_baseline:
+        numpy_baseline_main(args)
+        return
     if args.impl == 'reference':
         run_reference_arm(args)
         return
+
+    rank_env = int(os.environ.get('RANK', '0'))
+    world_env = int(os.environ.get('WORLD_SIZE', '1'))
+    np_base = None
+    if rank_env == 0 and world_env == 1 and not args.no_extras and not args.latency_only:
+        np_base = numpy_baseline(args)              # before this process initialises CUDA (the pool forks)
 
     import torch
     from rdf_b200 import _capi, dist as rdist
@@ -418,173 +693,178 @@ def main():
         if rank == 0:
             print(json.dumps({'latency': latency_cfg2(iters=args.latency_iters, warm=min(100, args.latency_iters))}), flush=True)
         return
-    lib = _capi.load()
+    _capi.load()
 
     frames, W, H, T, D, C, kind = WORKLOADS[args.workload]
     if args.frames:
         frames = args.frames
     f0, f1 = rdist.shard_range(frames, rank, world)
-    if frames == 1:                                # single-frame workloads do not shard: every rank runs a replica
+    single = frames == 1
+    if single:                                     # single-frame workloads do not shard: every rank runs a replica
         f0, f1 = 0, 1
     my_frames = f1 - f0
 
-    # ---- inputs, generated on the device (bit-exact twins of rdf_b200/synth.py) ----
-    forest = dt.DecisionForest(T, D, C)
-    _capi.check(lib.rdf_synth_forest(_capi.dptr(forest.forest_cu), T, D, C, args.seed, _capi.stream_ptr()))
-    # Single-frame workloads (cfg1, cfg5: replicas only) would re-walk the same tree paths out of L2 every step, so each step
-    # gets its own frame (frame index = step) and L2 is flushed (256 MB written) before it, outside the per-step events.
-    single = frames == 1
-    ring = (args.steps + args.warmup) if single else my_frames
-    depth = dt.cu_array.GPUArray((ring, H, W), dtype=np.uint16)
-    _capi.check(lib.rdf_synth_depth(_capi.dptr(depth), KIND_ID[kind], ring, W, H, args.seed, f0, _capi.stream_ptr()))
-    labels = dt.cu_array.GPUArray((ring, H, W), dtype=np.uint16).fill(65535)
+    # ---- inputs, generated on the device (bit-exact twins of rdf_b200/synth.py); headline: inputs resident ----
+    forest = make_forest(T, D, C, args.seed, args.forest)
     ev = dt.DecisionTreeEvaluator()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda') if single else None
-    torch.cuda.synchronize()
-
-    def step(k=0):
-        if single:
-            ev.get_labels_forest(forest, depth[k:k + 1], labels[k:k + 1])
-        else:
-            ev.get_labels_forest(forest, depth, labels)
-
-    for k in range(args.warmup):
-        step(k)
     torch.cuda.synchronize()
     rdist.barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    if single:
-        elapsed = 0.0
-        for k in range(args.steps):
-            flush.zero_()
-            e0.record()
-            step(args.warmup + k)
-            e1.record()
-            torch.cuda.synchronize()
-            elapsed += e0.elapsed_time(e1)
-    else:
-        e0.record()
-        for _ in range(args.steps):
-            step()
-        e1.record()
-        torch.cuda.synchronize()
-        elapsed = e0.elapsed_time(e1)
+    ms_step, depth, labels = time_eval(forest, kind, my_frames, W, H, args.steps, args.warmup, args.seed, first_frame=f0, single=single)
     rdist.barrier()
-    elapsed_ms = rdist.max_over_ranks(elapsed)
+    ms_step = rdist.max_over_ranks(ms_step)
     clocks = sampler.stop() if rank == 0 else None
     total_px = frames * H * W * (world if single else 1)
-    value = total_px * args.steps / elapsed_ms / 1e3                 # Mpixels/s, whole job
+    value = total_px / ms_step / 1e3                                 # Mpixels/s, whole job
     launches_per_step = (my_frames + 65534) // 65535
 
-    # ---- parity spot check inside the bench: first frame of this rank vs the C oracle (outside the timed region) ----
+    # ---- parity spot check inside the bench: one frame of this rank vs the C oracle (outside the timed region) ----
     parity = None
     if rank == 0:
-        from rdf_b200 import synth
-        from oracle import c_oracle as co
-        canon = forest.forest_cu.get()
-        d0 = synth.depth_frames(kind, 1, H, W, seed=args.seed, first_frame=f0)
-        assert np.array_equal(depth[0:1].get(), d0), 'device frame generator differs from synth.py'
-        exp = np.full((1, H, W), 65535, np.uint16)
-        co.eval_forest(canon, d0, exp)
-        parity = bool(np.array_equal(labels[0:1].get(), exp))
-        assert parity, 'label map of frame 0 differs from the oracle'
+        last = (args.steps + args.warmup - 1) if single else 0
+        if T * (1 << D) * (7 + 2 * C) * 4 <= (2 << 30):
+            parity = parity_vs_c_oracle(forest, kind, W, H, args.seed, f0 + last, labels[last:last + 1])
+        else:                                                        # cfg5: the forest stays on the device
+            parity = parity_vs_reference_kernel(forest, depth[last:last + 1], labels[last:last + 1])
+        assert parity, 'label map differs from the checker'
 
-    # ---- e2e: host buffers through the public host API ----
+    # ---- e2e: host buffers through the public host API, and the same copies with no kernel ----
     e2e = None
     if not args.no_extras:
         depth_host = pinned_like((my_frames, H, W), np.uint16)
         labels_host = pinned_like((my_frames, H, W), np.uint16)
         depth_host.view(torch.int16).copy_(depth.tensor[:my_frames].view(torch.int16))
         hb = HostBatchEvaluator(ev, forest, (H, W), chunk_frames=min(64, my_frames))
-        hb.run(depth_host, labels_host)
-        torch.cuda.synchronize()
-        rdist.barrier()
-        e0.record()
-        for _ in range(args.e2e_steps):
-            hb.run(depth_host, labels_host)
-        e1.record()
-        torch.cuda.synchronize()
-        rdist.barrier()
-        e2e_ms = rdist.max_over_ranks(e0.elapsed_time(e1))
-        if rank == 0:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def timed(n, **kw):
+            hb.run(depth_host, labels_host, **kw)
+            torch.cuda.synchronize()
+            rdist.barrier()
+            e0.record()
+            for _ in range(n):
+                hb.run(depth_host, labels_host, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            rdist.barrier()
+            return rdist.max_over_ranks(e0.elapsed_time(e1)) / n
+        copy_ms = timed(2, copy_only=True)
+        e2e_ms = timed(args.e2e_steps)
+        if rank == 0 and not single:
             got = labels_host[0:1].view(torch.int16).numpy().view(np.uint16)
             assert np.array_equal(got, labels[0:1].get()), 'host-API label map differs from the resident run'
-        e2e = {'value': total_px * args.e2e_steps / e2e_ms / 1e3, 'unit': 'Mpixels/s',
-               'h2d_bytes_per_step': int(rdist.sum_over_ranks(hb.bytes_h2d)), 'd2h_bytes_per_step': int(rdist.sum_over_ranks(hb.bytes_d2h)),
-               'steps': args.e2e_steps, 'api': 'rdf_b200.pipeline.HostBatchEvaluator.run (pinned host frames -> pinned host label maps, 64-frame chunks on 3 streams)'}
+        h2d, d2h = int(rdist.sum_over_ranks(hb.bytes_h2d)), int(rdist.sum_over_ranks(hb.bytes_d2h))
+        e2e = {'value': r(total_px / e2e_ms / 1e3, 1), 'unit': 'Mpixels/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+               'steps': args.e2e_steps, 'ms_per_step': r(e2e_ms),
+               'copy_only_mpix_s': r(total_px / copy_ms / 1e3, 1), 'host_copy_ceiling_gbs': r((h2d + d2h) / copy_ms / 1e6, 1),
+               'achieved_copy_gbs': r((h2d + d2h) / e2e_ms / 1e6, 1),
+               'api': 'rdf_b200.pipeline.HostBatchEvaluator.run (pinned host frames -> pinned host label maps, 64-frame chunks, 3 device '
+                      'buffers on 3 streams); copy_only_* / host_copy_ceiling_gbs = the same chunked H2D + D2H with no kernel'}
         del depth_host, labels_host, hb
 
+    # ---- the reference's own kernel on the same GPU and inputs (sub-batch), with a bit-exact cross-check ----
+    rg = None
+    if rank == 0 and not args.no_extras and not single:
+        sub_frames = min(my_frames, 256)
+        rg = ref_gpu_rate(forest.forest_cu, depth, sub_frames, H, W)
+        if rg is not None:
+            ref_labels = rg.pop('labels')
+            rg['labels_bit_exact_vs_ours'] = bool(torch.equal(ref_labels.view(torch.int16), labels.tensor[:sub_frames].view(torch.int16)))
+            rg['speedup_ours_per_gpu'] = r((value / world) / rg['value'], 2)
+            rg['value'], rg['ms_per_pass'] = r(rg['value'], 1), r(rg['ms_per_pass'])
+            rg.pop('what')
+            del ref_labels
+    del depth, labels, forest
+    torch.cuda.empty_cache()
+
+    # ---- the path's one collective: split search sharded over the ranks (all ranks take part) ----
+    train_mgpu = None
+    if world > 1 and not args.no_extras:
+        try:
+            train_mgpu = train_cfg4_multi_gpu()
+        except Exception as e:                                        # never lose the headline number to an extra
+            train_mgpu = {'error': repr(e)[:300]}
     if rank != 0:
         return
 
     peak, peak_src = measured_peaks()
     b_alg = b_alg_per_pixel(T, D, C)
-    kernel_ms = elapsed_ms / args.steps / max(1, launches_per_step)   # max over ranks; one launch per step and rank
+    kernel_ms = ms_step / max(1, launches_per_step)                  # max over ranks; one launch per step and rank
     px_per_launch = my_frames * H * W / max(1, launches_per_step)
     achieved = b_alg * px_per_launch / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'eval_traffic.json')
-    if os.path.exists(tpath):
-        try:
-            tj = json.load(open(tpath))
-            if tj.get('workload') == args.workload:
-                traffic = tj['dram_bytes_per_pixel'] * px_per_launch
-        except Exception:
-            pass
-    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+    binding, dram_bpp = binding_from_profile(args.workload)
+    roofline = {'bound': 'hbm', 'achieved': r(achieved, 1), 'peak': peak, 'unit': 'GB/s', 'frac': r(achieved / peak, 4),
+                'traffic': (dram_bpp * px_per_launch if dram_bpp else None),
                 'kernel': f'rdf_eval_packed_kernel<{T},*,true,false>', 'algorithmic_bytes_per_pixel': b_alg, 'peak_source': peak_src,
-                'compulsory_hbm_frac': 4.0 * px_per_launch / (kernel_ms * 1e-3) / 1e9 / peak,
-                'node_steps_per_s': T * D * px_per_launch / (kernel_ms * 1e-3),
-                'note': 'logical-traffic roofline (SURVEY 8d): exceeds 1.0 because the forest is cache-resident; the binding '
-                        'resource is the L1 data pipe (93 % of peak under ncu, profiles/r01_ncu_eval_v3.md)'}
+                'compulsory_hbm_frac': r(4.0 * px_per_launch / (kernel_ms * 1e-3) / 1e9 / peak, 5),
+                'node_steps_per_s': T * D * px_per_launch / (kernel_ms * 1e-3), 'binding': binding,
+                'note': 'logical-traffic roofline (SURVEY 8d): exceeds 1.0 because the forest is cache-resident; `binding` is the '
+                        'physically bounded fraction (ncu, profiles/)'}
 
     line = {
-        'metric': 'forest_eval_mpixels_per_s', 'value': value, 'unit': 'Mpixels/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
+        'metric': 'forest_eval_mpixels_per_s', 'value': r(value, 1), 'unit': 'Mpixels/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': r(ms_step), 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_desc(args.workload), 'frames_total': frames, 'frames_per_rank': my_frames,
+    }
+    details = {}
+    if not args.no_extras and world == 1:
+        try:
+            lat = latency_cfg2()
+            details['latency'] = lat
+            line['latency'] = {'p50_us': r(lat['p50_us'], 1), 'p99_us': r(lat['p99_us'], 1), 'device_p50_us': r(lat['device_p50_us'], 1),
+                               'resident_p50_us': r(lat['resident_frame']['p50_us'], 1), 'parity': lat['parity'],
+                               'what': 'cfg2 e2e: host frame -> upload -> 2-layer forest -> mean shift -> centroids in pinned host memory'}
+        except Exception as e:
+            line['latency'] = {'error': repr(e)[:200]}
+        try:
+            line['configs'] = other_configs(args.seed)
+        except Exception as e:
+            line['configs'] = {'error': repr(e)[:300]}
+    line.update({
+        'config': {'workload': workload_desc(args.workload), 'forest': FOREST_DESC[args.forest], 'frames_total': frames,
+                   'frames_per_rank': my_frames,
                    'parallelism': (f'replicas only: the same frame sequence on each of {world} rank(s)' if single else
                                    f'frames sharded over {world} rank(s), no collective'),
                    'l2': ('a different frame every step, L2 flushed (256 MB written) before each step, per-step CUDA events' if single else
                           'inputs larger than L2 (depth + labels = %.1f GB per rank per step)' % (2 * my_frames * H * W * 2 / 1e9))},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': args.steps * launches_per_step, 'roofline': roofline,
-        'host_cpus_bound_per_rank': host_cpus_bound,
-        'parity_checked': parity,
-    }
-
-    if not args.no_extras:
-        # the reference's own kernel on the same GPU and inputs (sub-batch), with a bit-exact cross-check
-        sub_frames = min(my_frames, 256)
-        rg = ref_gpu_rate(forest.forest_cu, depth, sub_frames, H, W)
-        if rg is not None:
-            ref_labels = rg.pop('labels')
-            same = bool(torch.equal(ref_labels.view(torch.int16), labels.tensor[:sub_frames].view(torch.int16)))
-            rg['labels_bit_exact_vs_ours'] = same
-            rg['speedup_ours_per_gpu'] = (value / world) / rg['value']
-            line['ref_gpu'] = rg
-            del ref_labels
-        if world == 1:
-            cb, _ = cpu_oracle_rate(T, D, C, W, H, kind, seed=args.seed)
-            line['cpu_baseline'] = cb
-        del depth, labels
-        torch.cuda.empty_cache()
+        'host_cpus_bound_per_rank': host_cpus_bound, 'parity_checked': parity,
+    })
+    if rg is not None:
+        line['ref_gpu'] = rg
+    if train_mgpu is not None:
+        line['train_cfg4'] = train_mgpu
+    if not args.no_extras and world == 1:
+        cb, _ = cpu_oracle_rate(T, D, C, W, H, kind, seed=args.seed)
+        cb['value'] = r(cb['value'], 3)
+        line['cpu_baseline'] = cb
+        line['cpu_baseline_numpy'] = np_base
         try:
-            line['latency'] = latency_cfg2()
-        except Exception as e:                                        # never lose the headline number to an extra
-            line['latency'] = {'error': repr(e)}
-        try:
-            line['train_cfg4'] = train_cfg4()
+            line['train_cfg4'] = train_cfg4_sweep()
         except Exception as e:
-            line['train_cfg4'] = {'error': repr(e)}
+            line['train_cfg4'] = {'error': repr(e)[:300]}
         try:
-            line['hands_frame'] = hands_frame()
+            hf = hands_frame()
+            details['hands_frame'] = hf
+            line['hands_frame'] = compact_hands(hf)
         except Exception as e:
-            line['hands_frame'] = {'error': repr(e)}
+            line['hands_frame'] = {'error': repr(e)[:200]}
     print(json.dumps(line), flush=True)
+    if details:
+        print('# details: ' + json.dumps(details), file=sys.stderr, flush=True)
+
+
+def compact_hands(hf):
+    """Numbers and parity flags of tools/bench_hands_frame.run's result, without its prose."""
+    def walk(o):
+        if isinstance(o, dict):
+            return {k: walk(v) for k, v in o.items() if not (isinstance(v, str) and len(v) > 60)}
+        if isinstance(o, float):
+            return round(o, 2)
+        return o
+    return walk(hf)
 
 
 if __name__ == '__main__':

@@ -6,6 +6,7 @@
 Time = max over ranks (CUDA events).  Checks that both modes write the same node records."""
 import argparse
 import ctypes
+import hashlib
 import json
 import os
 import sys
@@ -19,19 +20,17 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--frames', type=int, default=42)
-    ap.add_argument('--features', type=int, default=2000)
-    ap.add_argument('--levels', default='0,8,12')
-    ap.add_argument('--iters', type=int, default=3)
-    args = ap.parse_args()
+def run(frames=42, features=2000, levels=(0, 8, 12), iters=3, emit=None):
+    """Needs an initialised process group with world_size > 1 (bench.py's multi-GPU leg and main() below).  Returns one dict per
+    level on every rank (times are max over ranks)."""
+    import types
+    args = types.SimpleNamespace(frames=frames, features=features, iters=iters)
     import torch.distributed as dist
     import torch.distributed._symmetric_memory as symm_mem
     from rdf_b200 import _capi, synth, dist as rdist
-    rank, world, local = rdist.init_from_env()
-    torch.cuda.set_device(local)
+    rank, world, local = rdist.env_rank_world()
     lib = _capi.load()
+    results = []
     H, W, C, F, NT, D = 480, 848, 4, args.features, 64, 16
     n0, n1 = rdist.shard_range(args.frames, rank, world)
     N = n1 - n0
@@ -43,7 +42,7 @@ def main():
     st = _capi.stream_ptr
     E = 7 + 2 * C
     Fo = (F + world - 1) // world
-    for level in [int(x) for x in args.levels.split(',')]:
+    for level in levels:
         S = 1 << level
         nodes_all = synth.random_node_assignment(labels_all, level)
         nodes = torch.from_numpy(np.ascontiguousarray(nodes_all[n0:n1])).cuda()
@@ -120,14 +119,33 @@ def main():
             trees[name] = (t, nx)
         same = bool(torch.equal(trees['allreduce'][0].view(torch.int32), trees['p2p'][0].view(torch.int32)) and
                     torch.equal(trees['allreduce'][1], trees['p2p'][1]))
-        if rank == 0:
-            px = args.frames * H * W
-            print(json.dumps({'cfg4_level': level, 'active_nodes': S, 'n_gpus': world, 'ms_per_level_allreduce': out['allreduce'],
-                              'ms_per_level_p2p': out['p2p'], 'node_records_identical': same, 'hist_GB': S * F * (NT + 1) * C * 4 / 1e9,
-                              'g_feature_evals_per_s_p2p': px * F / out['p2p'] / 1e6}), flush=True)
+        same = bool(rdist.max_over_ranks(0.0 if same else 1.0) == 0.0)          # on every rank
+        digest = hashlib.md5(trees['p2p'][0].cpu().numpy().tobytes() + trees['p2p'][1].cpu().numpy().tobytes()).hexdigest()
+        px = args.frames * H * W
+        rec = {'cfg4_level': level, 'active_nodes': S, 'n_gpus': world, 'ms_per_level_allreduce': out['allreduce'],
+               'ms_per_level_p2p': out['p2p'], 'node_records_identical': same, 'records_md5': digest,
+               'hist_GB': S * F * (NT + 1) * C * 4 / 1e9, 'g_feature_evals_per_s_p2p': px * F / out['p2p'] / 1e6}
+        results.append(rec)
+        if rank == 0 and emit is not None:
+            emit(rec)
         del hist, sym, hdl, ws
         torch.cuda.empty_cache()
     rdist.barrier()
+    return results
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--frames', type=int, default=42)
+    ap.add_argument('--features', type=int, default=2000)
+    ap.add_argument('--levels', default='0,8,12')
+    ap.add_argument('--iters', type=int, default=3)
+    args = ap.parse_args()
+    import torch.distributed as dist
+    from rdf_b200 import dist as rdist
+    rank, world, local = rdist.init_from_env()
+    torch.cuda.set_device(local)
+    run(args.frames, args.features, [int(x) for x in args.levels.split(',')], args.iters, emit=lambda r: print(json.dumps(r), flush=True))
     if world > 1:
         dist.destroy_process_group()
 

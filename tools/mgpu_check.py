@@ -20,11 +20,12 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 
-def main():
+def run():
+    """Needs torch.distributed initialised when WORLD_SIZE > 1 (bench.py's multi-GPU leg, tests/test_gpu_multi.py, main() below).
+    Returns the result dict on every rank (the parity flags are only meaningful on rank 0)."""
     from rdf_b200 import dist as rdist, synth
     from rdf_b200 import decision_tree as dt
-    rank, world, local = rdist.init_from_env()
-    torch.cuda.set_device(local)
+    rank, world, local = rdist.env_rank_world()
     ev = dt.DecisionTreeEvaluator()
 
     # ---- 1. eval ----
@@ -87,13 +88,21 @@ def main():
     if rank == 0:
         single = train(0, Nt, 1)
         train_ok = all(t == single.tobytes() for trees in results.values() for t in trees) and bool((single[:, 5:7] == -1).any())
-        print(json.dumps({'world': world, 'eval_shards_match_single_gpu': eval_ok, 'sharded_training_matches_single_gpu': train_ok,
-                          'exchange_modes_tested': modes, 'frames': N,
-                          'train_images': Nt}), flush=True)
     rdist.barrier()
+    return {'world': world, 'eval_shards_match_single_gpu': eval_ok, 'sharded_training_matches_single_gpu': train_ok,
+            'exchange_modes_tested': modes, 'frames': N, 'train_images': Nt}
+
+
+def main():
+    from rdf_b200 import dist as rdist
+    rank, world, local = rdist.init_from_env()
+    torch.cuda.set_device(local)
+    res = run()
+    if rank == 0:
+        print(json.dumps(res), flush=True)
     if world > 1:
         dist.destroy_process_group()
-    if rank == 0 and not (eval_ok and train_ok):
+    if rank == 0 and not (res['eval_shards_match_single_gpu'] and res['sharded_training_matches_single_gpu']):
         sys.exit(1)
 
 
