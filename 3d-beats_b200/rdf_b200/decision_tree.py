@@ -484,10 +484,17 @@ class DecisionTreeTrainer():
 
     def __init__(self, NUM_IMAGES_PER_IMAGE_BLOCK, NUM_PROPOSALS_PER_PROPOSAL_BLOCK, thresholds_per_feature=1,
                  proposal_fn=None, process_group=None, hist_budget_bytes=8 << 30, exchange=None):
-        """exchange (multi-GPU only): 'p2p' = the reduction is fused into the histogram kernel (every counter is flushed over
-        NVLink into the peer-mapped buffer of the rank owning its feature, then each rank scores its feature slice and the
-        small per-node winners are all-gathered); 'allreduce' = NCCL sum-allreduce of the whole histogram, then every rank
-        scores everything.  Default: 'p2p' when torch symmetric memory can be set up, else 'allreduce' (env RDF_TRAIN_EXCHANGE)."""
+        """exchange (multi-GPU only).  With the images SHARDED over the ranks (every rank passes its own images):
+          'p2p' = the reduction is fused into the histogram kernel (every counter is flushed over NVLink into the peer-mapped
+                  buffer of the rank owning its feature, then each rank scores its feature slice and the small per-node winners
+                  are all-gathered);
+          'allreduce' = NCCL sum-allreduce of the whole histogram, then every rank scores everything.
+        Default: 'p2p' when torch symmetric memory can be set up, else 'allreduce' (env RDF_TRAIN_EXCHANGE).
+        With the dataset REPLICATED (every rank passes ALL images - 180 GB of HBM holds far more than a training set):
+          'features' = every rank buckets all pixels, builds the COMPLETE histograms of its own slice of the proposal block's
+                  features, scores them, and only the per-node winners are all-gathered: no histogram ever crosses NVLink
+                  (4096 nodes: 8.5 GB of counters stay local); node records, next-active lists and nodes_by_pixel are recomputed
+                  identically on every rank."""
         self.exchange = exchange or os.environ.get('RDF_TRAIN_EXCHANGE')
         self._lib = _capi.load()
         self.NUM_IMAGES_PER_IMAGE_BLOCK = NUM_IMAGES_PER_IMAGE_BLOCK
@@ -524,15 +531,30 @@ class DecisionTreeTrainer():
 
         # whole dataset resident: nodes_by_pixel int32[N,H,W] (the reference keeps it nvcomp-compressed per block)
         self.nodes_by_pixel = GPUArray(dataset.images_shape(), dtype=np.int32)
-        per_slot = P * (NT + 1) * C * 4
+        p_hist = P                                                    # features whose histograms this rank holds per slot
+        dist0 = self._dist()
+        if dist0 is not None and self.exchange == 'features':
+            p_hist = (P + dist0.get_world_size(self.process_group) - 1) // dist0.get_world_size(self.process_group)
+        per_slot = p_hist * (NT + 1) * C * 4
         self.MAX_SLOTS_PER_BLOCK = int(max(1, min(self.MAX_LEAF_NODES // 2 or 1, self.hist_budget_bytes // per_slot)))
-        self.hist_cu = GPUArray((self.MAX_SLOTS_PER_BLOCK, P, NT + 1, C), dtype=np.uint32)
+        self.hist_cu = GPUArray((self.MAX_SLOTS_PER_BLOCK, p_hist, NT + 1, C), dtype=np.uint32)
         need = ctypes.c_size_t()
         _capi.check(self._lib.rdf_train_bucket_workspace_bytes(int(np.prod(dataset.images_shape())), self.MAX_SLOTS_PER_BLOCK,
                                                                ctypes.byref(need)))
         self.bucket_ws = GPUArray(((need.value + 3) // 4,), dtype=np.int32)
         self._p2p = None
+        self._feat = None
         dist = self._dist()
+        if dist is not None and self.exchange == 'features':
+            group = self.process_group if self.process_group is not None else dist.group.WORLD
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+            L = self.MAX_LEAF_NODES
+            dev = self.hist_cu.tensor.device
+            self._feat = {'group': group, 'world': world, 'rank': rank, 'Fo': (P + world - 1) // world,
+                          'cand_gain': torch.zeros((L,), dtype=torch.float32, device=dev),
+                          'cand_idx': torch.zeros((L,), dtype=torch.int32, device=dev),
+                          'cand_cnt': torch.zeros((L, 2, C), dtype=torch.int64, device=dev)}
+            return
         ntp = 1
         while ntp < NT:
             ntp *= 2
@@ -637,6 +659,38 @@ class DecisionTreeTrainer():
                                                 _capi.dptr(tree.tree_out_cu), _capi.dptr(self.next_node_counts_cu),
                                                 _capi.dptr(self.best_gain_seen_per_node), st()))
 
+    def _level_block_features(self, lib, st, depth, labels, N, W, H, S, P, NT, C, num_active, level, D, tree):
+        """One (proposal block, node block) with the feature-sharded search over a replicated dataset: complete local histograms
+        of this rank's feature slice, local scoring, all-gather of the per-node winners, identical finalisation everywhere."""
+        import torch.distributed as dist
+        q = self._feat
+        world, rank, Fo = q['world'], q['rank'], q['Fo']
+        f0 = min(P, rank * Fo)
+        nloc = max(0, min(P, (rank + 1) * Fo) - f0)
+        cg, ci, cc = q['cand_gain'][:num_active], q['cand_idx'][:num_active], q['cand_cnt'][:num_active]
+        if nloc > 0:
+            hist = self.hist_cu.tensor.view(-1)[:S * nloc * (NT + 1) * C]
+            hist.view(torch.int32).zero_()
+            _capi.check(lib.rdf_train_hist_bucketed(_capi.dptr(depth), _capi.dptr(labels), N, W, H, _capi.dptr(self.bucket_ws), S,
+                                                    _capi.dptr(self.current_offsets[f0:f0 + nloc]),
+                                                    _capi.dptr(self.current_thresholds[f0:f0 + nloc]), nloc, NT, C, _capi.dptr(hist), st()))
+            _capi.check(lib.rdf_train_pick_candidates(num_active, _capi.dptr(self.active_nodes_cu), _capi.dptr(self.node_slot_cu),
+                                                      _capi.dptr(self.node_counts_cu), _capi.dptr(hist), S, nloc, nloc, f0, NT, C,
+                                                      _capi.dptr(cg), _capi.dptr(ci), _capi.dptr(cc), st()))
+        else:                                                        # more ranks than features: this rank has no candidate
+            cg.fill_(-1.0); ci.fill_(0x7fffffff); cc.zero_()
+        ag = torch.empty((world, num_active), dtype=torch.float32, device=cg.device)
+        ai = torch.empty((world, num_active), dtype=torch.int32, device=cg.device)
+        ac = torch.empty((world, num_active, 2, C), dtype=torch.int64, device=cg.device)
+        dist.all_gather_into_tensor(ag, cg, group=q['group'])
+        dist.all_gather_into_tensor(ai, ci, group=q['group'])
+        dist.all_gather_into_tensor(ac, cc, group=q['group'])
+        _capi.check(lib.rdf_train_pick_finalize(num_active, _capi.dptr(self.active_nodes_cu), _capi.dptr(self.node_slot_cu),
+                                                _capi.dptr(self.node_counts_cu), world, _capi.dptr(ag), _capi.dptr(ai), _capi.dptr(ac),
+                                                _capi.dptr(self.current_offsets), _capi.dptr(self.current_thresholds), NT, C, level, D,
+                                                _capi.dptr(tree.tree_out_cu), _capi.dptr(self.next_node_counts_cu),
+                                                _capi.dptr(self.best_gain_seen_per_node), st()))
+
     def train(self, dataset, tree):
         lib, st = self._lib, _capi.stream_ptr
         C = dataset.num_classes()
@@ -653,7 +707,7 @@ class DecisionTreeTrainer():
         self.node_counts_cu.fill(0)
         _capi.check(lib.rdf_train_init(_capi.dptr(labels), N * H * W, C, _capi.dptr(self.nodes_by_pixel),
                                        _capi.dptr(self.node_counts_cu), st()))
-        if dist is not None:
+        if dist is not None and self._feat is None:                  # sharded images: the root statistics are a sum over the ranks
             root = self.node_counts_cu.tensor[0].view(torch.int64)
             dist.all_reduce(root, group=self.process_group)
         self.active_nodes_cu.fill(np.int32(0))
@@ -683,6 +737,9 @@ class DecisionTreeTrainer():
                         self.node_slot_cu[:num_nodes_level].set(slot_host)
                         _capi.check(lib.rdf_train_bucket(_capi.dptr(self.nodes_by_pixel), N * H * W, _capi.dptr(self.node_slot_cu), S,
                                                          _capi.dptr(self.bucket_ws), self.bucket_ws.nbytes, st()))
+                    if self._feat is not None:
+                        self._level_block_features(lib, st, depth, labels, N, W, H, S, P, NT, C, num_active_nodes, current_level, D, tree)
+                        continue
                     if self._p2p is not None:
                         self._level_block_p2p(lib, st, depth, labels, N, W, H, S, P, NT, C, num_active_nodes, current_level, D, tree)
                         continue

@@ -402,8 +402,10 @@ def train_cfg4_multi_gpu(levels=(0, 8, 12)):
     parity = load('mgpu_check').run()
     out = None
     if rank == 0:
-        out = {'n_gpus': world, 'exchange': 'p2p = reduce-scatter fused into the histogram kernel over NVLink + all-gather of per-node '
-                                            'winners; allreduce = NCCL sum-allreduce of the whole histogram',
+        out = {'n_gpus': world, 'exchange': 'images sharded: p2p = reduce-scatter fused into the histogram kernel over NVLink + all-gather of '
+                                            'per-node winners; allreduce = NCCL sum-allreduce of the whole histogram.  dataset replicated: '
+                                            'features = every rank builds the complete histograms of its own feature slice, only per-node '
+                                            'winners are all-gathered',
                'levels': {}, 'sharded_training_matches_single_gpu': parity['sharded_training_matches_single_gpu'],
                'eval_shards_match_single_gpu': parity['eval_shards_match_single_gpu'],
                'exchange_modes_tested': parity['exchange_modes_tested']}
@@ -412,7 +414,9 @@ def train_cfg4_multi_gpu(levels=(0, 8, 12)):
             t1 = one['ms_per_level']
             out['levels'][str(rec['cfg4_level'])] = {
                 'nodes': rec['active_nodes'], 'ms_per_level_p2p': round(rec['ms_per_level_p2p'], 3),
-                'ms_per_level_allreduce': round(rec['ms_per_level_allreduce'], 3), 'ms_per_level_1gpu': round(t1, 3),
+                'ms_per_level_allreduce': round(rec['ms_per_level_allreduce'], 3),
+                'ms_per_level_features': round(rec['ms_per_level_features'], 3), 'ms_per_level_1gpu': round(t1, 3),
+                'efficiency_features': round(t1 / (world * rec['ms_per_level_features']), 3),
                 'efficiency_p2p': round(t1 / (world * rec['ms_per_level_p2p']), 3),
                 'efficiency_allreduce': round(t1 / (world * rec['ms_per_level_allreduce']), 3),
                 'node_records_identical': bool(rec['node_records_identical'] and rec['records_md5'] == one['records_md5']),

@@ -61,6 +61,8 @@ def run():
     modes = {}
 
     def train(n0, n1, group_world, exchange=None):
+        if exchange == 'features':                           # replicated dataset: every rank trains on ALL images
+            n0, n1 = 0, Nt
         d = synth.depth_frames('dense-smooth', n1 - n0, Ht, Wt, seed=9, first_frame=n0)
         l = synth.train_labels(n1 - n0, Ht, Wt, first_frame=n0)
         ds = dt.DecisionTreeDatasetConfig.from_arrays(d, l, C)
@@ -68,7 +70,9 @@ def run():
                                     process_group=None if group_world > 1 else False, exchange=exchange)
         tr.allocate(ds, F, Dt)
         if group_world > 1:
-            modes[str(exchange)] = 'p2p (reduction fused into the histogram kernel)' if tr._p2p is not None else 'nccl allreduce ' + getattr(tr, '_p2p_error', '')
+            modes[str(exchange)] = ('features (replicated dataset, feature-sharded search, winners all-gathered)' if tr._feat is not None else
+                                    'p2p (reduction fused into the histogram kernel)' if tr._p2p is not None else
+                                    'nccl allreduce ' + getattr(tr, '_p2p_error', ''))
         tree = dt.DecisionTree(Dt, C)
         tr.train(ds, tree)
         torch.cuda.synchronize()
@@ -76,7 +80,7 @@ def run():
 
     i0, i1 = rdist.shard_range(Nt, rank, world)
     results = {}
-    for exchange in ((None, 'allreduce') if world > 1 else (None,)):
+    for exchange in ((None, 'allreduce', 'features') if world > 1 else (None,)):
         sharded = train(i0, i1, world, exchange)
         trees = [None] * world
         if world > 1:
