@@ -241,7 +241,9 @@ static inline bool rdf_scale_fastfloor_ok(float s) {
 static inline cudaStream_t rdf_stream(void* s) { return (cudaStream_t)s; }
 
 // CTAs per SM the register allocation of the per-pixel forest kernels aims for, by number of interleaved trees (see rdf_eval.cu)
+#ifndef RDF_EVAL_MIN_BLOCKS_T
 #define RDF_EVAL_MIN_BLOCKS_T(T) ((T) <= 5 ? 4 : (T) == 6 ? 3 : 2)
+#endif
 
 // Opt-in dynamic shared memory above 48 KB is a PER-DEVICE function attribute: remember what was set on each device so that a
 // process driving several GPUs (or switching devices) gets it on all of them.
