@@ -19,25 +19,36 @@ extern "C" const char* rdf_last_error(void) { return g_err; }
 // canonical node = (ux,uy,vx,vy,thresh,l_next,r_next,l_pdf[C],r_pdf[C]) (src/cuda/tree_eval.cu:47).
 // "child continues" is floor(flag) == -1 exactly as the kernels test it (__float2int_rd, tree_eval.cu:101-102).
 __global__ void rdf_pack_kernel(const float* __restrict__ canon, rdf_node_hdr* __restrict__ hdr, float* __restrict__ pdf,
-                                int64_t total_nodes, int64_t nodes_per_tree, int D, int C, int CP, int* __restrict__ exact_flag) {
+                                int64_t total_nodes, int64_t nodes_per_tree, int64_t rows_per_tree, int layout, int D, int C, int CP,
+                                int* __restrict__ exact_flag) {
     const int E = 7 + 2 * C;
-    const int64_t first_last_level = ((int64_t)1 << (D - 1)) - 1;      // rows >= this are at level D-1: no children
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_nodes; i += (int64_t)gridDim.x * blockDim.x) {
         const float* nd = canon + i * E;
         const int64_t t = i / nodes_per_tree, row = i - t * nodes_per_tree;
+        const int j = 63 - __clzll(row + 1);                             // level of the canonical row
+        const int64_t g = row + 1 - ((int64_t)1 << j);                   // index within the level
+        const bool last = j == D - 1;                                    // level D-1: no children
+        int64_t self, left, right;
+        if (layout == RDF_LAYOUT_BLOCKS) {
+            self = t * rows_per_tree + rdf_blocks_row(j, g, D);
+            left = last ? 0 : t * rows_per_tree + rdf_blocks_row(j + 1, 2 * g, D);
+            right = last ? 0 : t * rows_per_tree + rdf_blocks_row(j + 1, 2 * g + 1, D);
+        } else {
+            self = i;
+            left = t * nodes_per_tree + 2 * row + 1;
+            right = left + 1;
+        }
         rdf_node_hdr h;
         h.a = make_float4(nd[0], nd[1], nd[2], nd[3]);
         h.ithresh = rdf_int_thresh(nd[4]);
-        const bool last = row >= first_last_level;
-        const int child = (int)(t * nodes_per_tree + 2 * row + 1);       // left child; right = child + 1
-        h.left = __float2int_rd(nd[5]) == -1 ? (last ? RDF_NO_LEAF : child) : ~(int)(2 * i);
-        h.right = __float2int_rd(nd[6]) == -1 ? (last ? RDF_NO_LEAF : child + 1) : ~(int)(2 * i + 1);
+        h.left = __float2int_rd(nd[5]) == -1 ? (last ? RDF_NO_LEAF : (int)left) : ~(int)(2 * self);
+        h.right = __float2int_rd(nd[6]) == -1 ? (last ? RDF_NO_LEAF : (int)right) : ~(int)(2 * self + 1);
         // offsets outside the domain of the reciprocal divide + magic-number floor (rdf_common.cuh) -> exact path
         h.flags = (rdf_fastfloor_domain(nd[0]) && rdf_fastfloor_domain(nd[1]) && rdf_fastfloor_domain(nd[2]) &&
                    rdf_fastfloor_domain(nd[3])) ? 0 : RDF_FLAG_EXACT_DIV;
-        hdr[i] = h;
+        hdr[self] = h;
         if (h.flags & RDF_FLAG_EXACT_DIV) *exact_flag = 1;            // benign race: everybody writes 1
-        float* p = pdf + i * 2 * CP;
+        float* p = pdf + self * 2 * CP;
         for (int c = 0; c < CP; c++) {
             p[c] = c < C ? nd[7 + c] : 0.f;
             p[CP + c] = c < C ? nd[7 + C + c] : 0.f;
@@ -50,12 +61,21 @@ static int rdf_pack(rdf_forest* f, const float* canon_dev, cudaStream_t stream) 
     int blocks = (int)((total + 255) / 256);
     if (blocks > rdf_sm_count() * 32) blocks = rdf_sm_count() * 32;
     RDF_CUDA(cudaMemsetAsync(f->exact_flag_dev, 0, sizeof(int), stream));
-    rdf_pack_kernel<<<blocks, 256, 0, stream>>>(canon_dev, f->hdr, f->pdf, total, f->nodes_per_tree, f->D, f->C, f->CP, f->exact_flag_dev);
+    rdf_pack_kernel<<<blocks, 256, 0, stream>>>(canon_dev, f->hdr, f->pdf, total, f->nodes_per_tree, f->rows_per_tree, f->layout, f->D, f->C,
+                                                f->CP, f->exact_flag_dev);
     RDF_LAUNCH_CHECK("rdf_pack_kernel");
     // the flag is needed on the host to choose kernels: packing is handle creation / update, not the per-frame path
     RDF_CUDA(cudaMemcpyAsync(&f->has_exact_nodes, f->exact_flag_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
     RDF_CUDA(cudaStreamSynchronize(stream));
     return RDF_OK;
+}
+
+// RDF_PACK_LAYOUT=heap|blocks chooses the node order of handles created afterwards (read once; default: see rdf_pack_layout)
+static int rdf_pack_layout() {
+    const char* e = RDF_GETENV_ONCE("RDF_PACK_LAYOUT");
+    if (e && !strcmp(e, "blocks")) return RDF_LAYOUT_BLOCKS;
+    if (e && !strcmp(e, "heap")) return RDF_LAYOUT_HEAP;
+    return RDF_LAYOUT_DEFAULT;
 }
 
 extern "C" int rdf_forest_create(const float* canon_dev, int num_trees, int max_depth, int num_classes, void* stream,
@@ -68,17 +88,20 @@ extern "C" int rdf_forest_create(const float* canon_dev, int num_trees, int max_
                 RDF_MAX_DEPTH);
     RDF_REQUIRE(num_classes >= 1 && num_classes <= RDF_MAX_CLASSES, "rdf_forest_create: num_classes=%d outside 1..%d",
                 num_classes, RDF_MAX_CLASSES);
-    RDF_REQUIRE(((int64_t)num_trees << max_depth) < ((int64_t)1 << 30),
-                "rdf_forest_create: %d trees of depth %d exceed the 2^30 nodes a packed forest can index", num_trees, max_depth);
+    RDF_REQUIRE((int64_t)num_trees * rdf_blocks_rows_per_tree(max_depth) < ((int64_t)1 << 30) &&
+                    ((int64_t)num_trees << max_depth) < ((int64_t)1 << 30),
+                "rdf_forest_create: %d trees of depth %d exceed the 2^30 node slots a packed forest can index", num_trees, max_depth);
     rdf_forest* f = new rdf_forest();
     f->T = num_trees;
     f->D = max_depth;
     f->C = num_classes;
     f->CP = (num_classes + 3) & ~3;
     f->nodes_per_tree = ((int64_t)1 << max_depth) - 1;
+    f->layout = rdf_pack_layout();
+    f->rows_per_tree = f->layout == RDF_LAYOUT_BLOCKS ? rdf_blocks_rows_per_tree(max_depth) : f->nodes_per_tree;
     f->hdr = nullptr;
     f->pdf = nullptr;
-    const size_t n = (size_t)f->nodes_per_tree * f->T;
+    const size_t n = (size_t)f->rows_per_tree * f->T;
     const size_t hdr_bytes = n * sizeof(rdf_node_hdr), pdf_bytes = n * 2 * f->CP * sizeof(float);
     f->packed_bytes = hdr_bytes + pdf_bytes;
     cudaError_t e = cudaGetDevice(&f->device);

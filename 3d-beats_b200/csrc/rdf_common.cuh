@@ -61,11 +61,48 @@ struct __align__(32) rdf_node_hdr {
 
 #define RDF_NO_LEAF ((int)0x80000000)
 
+// Node order inside a tree's slice of the packed arrays (free to choose: the headers carry explicit child ids).
+//   RDF_LAYOUT_HEAP    canonical heap order, row = 2^level - 1 + index.
+//   RDF_LAYOUT_BLOCKS  levels 0 .. RDF_PACK_TOP_LEVELS-1 in heap order (the part the kernels stage in shared memory), below that
+//                      the levels are paired and every node of the upper level of a pair sits in ONE 128-byte line with its two
+//                      children (slots 0, 1, 2; slot 3 unused), so the two consecutive levels of a divergent walk touch one line
+//                      instead of two; an unpaired last level is stored densely.  The pdf table uses the same ids.
+#define RDF_LAYOUT_HEAP 0
+#define RDF_LAYOUT_BLOCKS 1
+#define RDF_PACK_TOP_LEVELS 6
+#ifndef RDF_LAYOUT_DEFAULT
+#define RDF_LAYOUT_DEFAULT RDF_LAYOUT_HEAP
+#endif
+
+// first slot of pair p (upper level RDF_PACK_TOP_LEVELS + 2p): 2^K + 4 * 2^K * (4^p - 1) / 3 - the 2^K - 1 heap rows are padded by
+// one slot so that every block starts on a 128-byte line (tree slices are multiples of four slots, the arrays 256-byte aligned)
+__host__ __device__ __forceinline__ int64_t rdf_blocks_pair_offset(int p) {
+    const int64_t top = (int64_t)1 << RDF_PACK_TOP_LEVELS;
+    return top + 4 * top * ((((int64_t)1 << (2 * p)) - 1) / 3);
+}
+__host__ __device__ __forceinline__ int64_t rdf_blocks_rows_per_tree(int D) {
+    if (D <= RDF_PACK_TOP_LEVELS) return ((int64_t)1 << D) - 1;
+    const int pairs = (D - RDF_PACK_TOP_LEVELS) / 2;
+    const int64_t off = rdf_blocks_pair_offset(pairs);
+    return ((D - RDF_PACK_TOP_LEVELS) & 1) ? off + ((int64_t)1 << (D - 1)) : off;
+}
+// slot of node (level j, index g within the level) inside its tree
+__host__ __device__ __forceinline__ int64_t rdf_blocks_row(int j, int64_t g, int D) {
+    if (j < RDF_PACK_TOP_LEVELS) return (((int64_t)1 << j) - 1) + g;
+    const int p = (j - RDF_PACK_TOP_LEVELS) >> 1;
+    const int L = RDF_PACK_TOP_LEVELS + 2 * p;
+    const int64_t off = rdf_blocks_pair_offset(p);
+    if (j == L) return L == D - 1 ? off + g : off + 4 * g;
+    return off + 4 * (g >> 1) + 1 + (g & 1);
+}
+
 struct rdf_forest {
     int T, D, C, CP;
-    int64_t nodes_per_tree;       // 2^D - 1
-    rdf_node_hdr* hdr;            // [T * nodes_per_tree]
-    float* pdf;                   // [T * nodes_per_tree * 2][CP]
+    int64_t nodes_per_tree;       // 2^D - 1 (canonical rows of a tree)
+    int64_t rows_per_tree;        // header slots of a tree in the packed arrays (== nodes_per_tree in heap order, more with blocks)
+    int layout;                   // RDF_LAYOUT_HEAP / RDF_LAYOUT_BLOCKS
+    rdf_node_hdr* hdr;            // [T * rows_per_tree]
+    float* pdf;                   // [T * rows_per_tree * 2][CP]
     size_t packed_bytes;
     int device;
     int has_exact_nodes;          // some node carries RDF_FLAG_EXACT_DIV (set by the last pack; read back at create / update)

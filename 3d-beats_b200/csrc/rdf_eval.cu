@@ -21,6 +21,7 @@ struct rdf_eval_params {
 };
 
 #define RDF_EVAL_SMEM_LEVELS 6
+static_assert(RDF_EVAL_SMEM_LEVELS <= RDF_PACK_TOP_LEVELS, "the staged levels must lie in the heap-ordered top of a packed tree");
 
 // CTAs per SM the register allocation aims for: 4 (<= 64 registers) up to 5 interleaved trees; the state of 6..8 trees does not
 // fit 64 registers (it spilled 64-128 B of stack and cfg5 lost a third of its speed), so those get 3 / 2 CTAs per SM.

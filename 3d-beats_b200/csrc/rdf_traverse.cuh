@@ -24,7 +24,7 @@ static inline rdf_forest_view rdf_view(const rdf_forest* f) {
     rdf_forest_view v;
     v.hdr = f->hdr;
     v.pdf = f->pdf;
-    v.nodes_per_tree = (int)f->nodes_per_tree;
+    v.nodes_per_tree = (int)f->rows_per_tree;      // slots per tree in the packed arrays: roots sit at t * nodes_per_tree
     v.T = f->T;
     v.D = f->D;
     v.C = f->C;

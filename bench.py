@@ -693,6 +693,13 @@ def main():
         host_cpus_bound = rdist.bind_host_to_gpu(local)
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device: the product path has no CPU fallback'
     torch.cuda.set_device(local)
+    if os.environ.get('RDF_L2_FETCH'):               # experiment knob: cudaLimitMaxL2FetchGranularity (32 / 64 / 128 bytes)
+        import ctypes
+        rt = ctypes.CDLL('libcudart.so.12')
+        rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(int(os.environ['RDF_L2_FETCH'])))
+        val = ctypes.c_size_t()
+        rt.cudaDeviceGetLimit(ctypes.byref(val), 5)
+        print(f'# cudaLimitMaxL2FetchGranularity -> rc {rc}, now {val.value}', file=sys.stderr)
     if args.latency_only:
         if rank == 0:
             print(json.dumps({'latency': latency_cfg2(iters=args.latency_iters, warm=min(100, args.latency_iters))}), flush=True)

@@ -321,3 +321,37 @@ def test_texture_probe_variant_matches_oracle(kind, T, D, C, r):
         assert lib.rdf_eval_forest_tex(f.handle(), h, _capi.dptr(d), N, None, -1, _capi.dptr(lab), r, _capi.stream_ptr()) == -3
     finally:
         lib.rdf_depth_tex_destroy(h)
+
+
+_BLOCK_LAYOUT_SCRIPT = r'''
+import sys
+sys.path.insert(0, r"%(root)s"); sys.path.insert(0, r"%(root)s/3d-beats_b200")
+import numpy as np, torch
+from rdf_b200 import synth
+from rdf_b200 import decision_tree as dt
+from oracle import c_oracle as co
+for (T, D, C, ragged, kind, r, scale) in [(3, 9, 4, True, 'dense-noise', 1, 1.0), (4, 12, 5, False, 'dense-smooth', 2, 0.5), (1, 7, 3, True, 'live-mask', 1, 1.0),
+                                          (8, 10, 4, True, 'dense-noise', 1, 1.0), (2, 5, 4, False, 'dense-smooth', 1, 1.0)]:
+    f = synth.random_forest(T, D, C, seed=11 + D, ragged=ragged)
+    d = synth.depth_frames(kind, 2, 96, 160, seed=5)
+    forest = dt.DecisionForest(T, D, C); forest.forest_cu.set(f)
+    out = dt.cu_array.GPUArray((2, 96 // r, 160 // r), dtype=np.uint16).fill(65535)
+    dt.DecisionTreeEvaluator().get_labels_forest(forest, dt.cu_array.to_gpu(d), out, labels_reduce=r, scale_factor=scale)
+    exp = np.full((2, 96 // r, 160 // r), 65535, np.uint16)
+    co.eval_forest(f, d, exp, r, None, None, scale)
+    assert np.array_equal(out.get(), exp), (T, D, C)
+print('ok')
+'''
+
+
+def test_block_layout_is_bit_exact():
+    """RDF_PACK_LAYOUT=blocks (subtree blocks below level 6, csrc/rdf_common.cuh:rdf_blocks_row) gives the same label maps as the
+    heap order: odd and even numbers of paired levels, ragged trees, trees shallower than the heap-ordered top, 8 trees.  The layout
+    is chosen once per process, hence the subprocess.  (Measured slower than heap order: profiles/r02_layout.md.)"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, '-c', _BLOCK_LAYOUT_SCRIPT % {'root': root}], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, RDF_PACK_LAYOUT='blocks'))
+    assert out.returncode == 0 and out.stdout.strip().endswith('ok'), out.stderr[-2000:]
