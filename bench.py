@@ -119,7 +119,7 @@ def host_cores():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_oracle_rate(T, D, C, W, H, kind, budget_s=12.0, max_frames=64, seed=1234):
+def cpu_oracle_rate(T, D, C, W, H, kind, budget_s=12.0, max_frames=512, seed=1234):
     """C oracle (oracle/rdf_oracle.c) on all host threads over a bounded sample of the workload's frames."""
     from rdf_b200 import synth
     from oracle import c_oracle as co
@@ -589,38 +589,39 @@ def numpy_baseline_main(args):
     from oracle import numpy_oracle as no
     frames, W, H, T, D, C, kind = WORKLOADS[args.workload]
     forest = synth.hash_forest(T, D, C, seed=args.seed)
-    depth = synth.depth_frames(kind, 1, H, W, seed=args.seed)
+    NF = 4                                                   # frames of the pooled sample
+    depth = synth.depth_frames(kind, NF, H, W, seed=args.seed)
     cores = host_cores()
 
-    def band(y0, y1):
+    def band(n, y0, y1):
         filt = np.zeros((1, H, W), np.uint16)
         filt[0, y0:y1] = 1
         lab = np.full((1, H, W), 65535, np.uint16)
-        no.eval_forest(forest, depth, lab, 1, filt, 1)
+        no.eval_forest(forest, depth[n:n + 1], lab, 1, filt, 1)
         return lab[0, y0:y1]
-    rows1 = max(8, H // 4)
+    rows1 = H // 2
     t0 = time.perf_counter()
-    band(0, rows1)
+    band(0, 0, rows1)
     t1 = time.perf_counter() - t0
     single = rows1 * W / t1 / 1e6
     global _NB_BAND
     _NB_BAND = band
-    bands = [(i * H // cores, (i + 1) * H // cores) for i in range(cores)]
+    bands = [(n, i * H // cores, (i + 1) * H // cores) for n in range(NF) for i in range(cores)]
     t0 = time.perf_counter()
     with mp.get_context('fork').Pool(cores) as pool:
         parts = pool.starmap(_nb_call, bands)
     t2 = time.perf_counter() - t0
-    print(json.dumps({'unit': 'Mpixels/s', 'single_process': single, 'pool': H * W / t2 / 1e6, 'cores': cores, 'kind': 'port (NumPy oracle)',
-                      'sample': f'single: {rows1} rows of one {W}x{H} frame ({t1:.1f} s); pool: one whole frame in {cores} row bands '
-                                f'({t2:.1f} s); forest and frame of the workload', 'labelled_px_pool': int(sum((p != 65535).sum() for p in parts))}),
+    print(json.dumps({'unit': 'Mpixels/s', 'single_process': single, 'pool': NF * H * W / t2 / 1e6, 'cores': cores, 'kind': 'port (NumPy oracle)',
+                      'sample': f'single: {rows1} rows of one {W}x{H} frame ({t1:.1f} s); pool: {NF} whole frames in {cores} row bands each '
+                                f'({t2:.1f} s); forest and frames of the workload', 'labelled_px_pool': int(sum((p != 65535).sum() for p in parts))}),
           flush=True)
 
 
 _NB_BAND = None
 
 
-def _nb_call(y0, y1):
-    return _NB_BAND(y0, y1)
+def _nb_call(n, y0, y1):
+    return _NB_BAND(n, y0, y1)
 
 
 def numpy_baseline(args):
