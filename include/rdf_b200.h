@@ -310,8 +310,9 @@ RDF_API int rdf_train_hist_bucketed(const uint16_t* depth_dev, const uint16_t* l
                             uint32_t* hist_dev, void* stream);
 /* Multi-GPU split search with the reduction fused into the histogram kernel (the path's only exchange step):
  * the F features of a proposal block are owned in contiguous slices of Fo = ceil(F / world) by the ranks; owner_hist_dev is
- * a DEVICE array of `world` peer-mapped pointers (NVLink), rank r's buffer being uint32[num_slots][Fo][NT+1][C] (zeroed by
- * its owner, all ranks synchronised before and after the launch).  Every rank runs rdf_train_hist_bucketed_p2p on its own
+ * a DEVICE array of `world` peer-mapped pointers (NVLink), rank r's buffer being uint32[num_slots][Fo][NT+1][C], 8-byte aligned
+ * (zeroed by its owner, all ranks synchronised before and after the launch; with an even class count two neighbouring counters
+ * are flushed as one 64-bit reduction).  Every rank runs rdf_train_hist_bucketed_p2p on its own
  * pixels; counters are flushed as system-scope reductions straight into the owner's buffer, so after a barrier rank r holds
  * the FULL histogram of its feature slice - a reduce-scatter without a separate collective.  rdf_train_pick_candidates then
  * scores the local slice (hist_local_dev laid out [num_slots][feature_stride][NT+1][C], the first num_local_features of each
