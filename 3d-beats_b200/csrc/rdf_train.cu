@@ -186,20 +186,20 @@ extern "C" int rdf_train_hist(const uint16_t* depth_dev, const uint16_t* labels_
 // profiles/r01_train_cfg4.md).  Here the active pixels are first grouped by histogram slot (counting sort of pixel indices:
 // rdf_train_bucket, once per level and node block, reused by every proposal block), so a CTA works on pixels of ONE node at
 // a time: its shared-memory histogram is [feature chunk][NT+1][C] whatever the number of nodes, flushed with one global
-// atomic per non-zero counter when the node changes.  Lanes of a warp are consecutive pixels of the same node evaluating the
-// same feature: probes of neighbouring pixels share sectors, thresholds are shared-memory broadcasts, and updates are
-// warp-aggregated (match.all when every lane hits the same counter, else match.any), so no shared-memory atomic ever
-// collides within a warp.
+// reduction per non-zero counter (pair) when the node changes.  Lanes of a warp are consecutive pixels of the same node evaluating
+// the same feature: probes of neighbouring pixels share sectors, thresholds are shared-memory broadcasts, and every lane adds 1
+// to its counter with red.shared - the shared-memory atomic unit resolves collisions faster than a match.any aggregation did.
 // Tunables (overridable with -D for variant builds, tools/build_variant.sh): threads per CTA, CTAs per SM the shared-memory
 // budget is split over, features evaluated together by one thread.
-// Measured on cfg4 (profiles/r02_train_cfg4.md): the kernel is latency-bound (1.65 eligible warps per scheduler of 8 resident), so
-// eight interleaved feature chains per thread and two half-size CTAs per SM (one keeps issuing while the other sits at its
-// per-node flush barrier) beat 1 x 1024 threads x 4 chains by 9-10 %.
+// Measured on cfg4 (profiles/r02_ncu_train.md): the kernel is latency-bound (1.65 eligible warps per scheduler of 8 resident), so
+// eight interleaved feature chains per thread and several small CTAs per SM (the others keep issuing while one sits at its
+// per-node flush barrier) beat 1 x 1024 threads x 4 chains by 9-10 %; 3 x 384 threads (55 registers, 36 warps per SM) is another 3 %
+// ahead of 2 x 512.
 #ifndef TB_THREADS
-#define TB_THREADS 512
+#define TB_THREADS 384
 #endif
 #ifndef TB_CTAS_PER_SM
-#define TB_CTAS_PER_SM 2
+#define TB_CTAS_PER_SM 3
 #endif
 #ifndef TB_U
 #define TB_U 8                  // features evaluated together by one thread (independent load chains)
@@ -346,11 +346,6 @@ __device__ __forceinline__ int tb_int_thresh(float t) {
 __device__ __forceinline__ void tb_red_shared(unsigned smem_addr, unsigned v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_addr), "r"(v) : "memory");
 }
-// if (leader) red.shared.add.u32 [addr], v  as one predicated instruction
-__device__ __forceinline__ void tb_red_shared_if(bool leader, unsigned smem_addr, unsigned v) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" ::"r"(smem_addr), "r"(v), "r"((unsigned)leader)
-                 : "memory");
-}
 // One step of the threshold search on a running shared address: if (*(int*)(addr + OFF) <= f) addr += INC.
 // (Not volatile: the threshold table is read-only after the CTA's first barrier, and the TB_U chains should interleave freely.)
 template <int OFF, int INC>
@@ -392,7 +387,6 @@ __global__ void __launch_bounds__(TB_THREADS, TB_CTAS_PER_SM) rdf_train_hist_buc
     const int tile1 = min(total, tile0 + TB_TILE);
     const int f0 = blockIdx.y * p.FC;
     const int nf = min(p.FC, p.F - f0);
-    const int lane = threadIdx.x & 31;
 
     // the chunk is padded to a multiple of TB_U features (zero offsets, INT_MAX thresholds): padded rows are evaluated and
     // counted into their own (never flushed) histogram rows, which keeps the inner loop free of tail tests
@@ -425,7 +419,6 @@ __global__ void __launch_bounds__(TB_THREADS, TB_CTAS_PER_SM) rdf_train_hist_buc
 
     const int per_img = p.W * p.H;
     const bool any_exact = s_any_exact != 0;                                     // uniform: some feature needs __fdiv_rn
-    const unsigned lanemask_lt = (1u << lane) - 1u;
     const unsigned thr_base = (unsigned)__cvta_generic_to_shared(thr_s);
     const unsigned hist_base = (unsigned)__cvta_generic_to_shared(hist_s);
     const unsigned row_bytes = (unsigned)(p.NB * p.C) * 4u;                      // one feature's histogram
@@ -451,7 +444,6 @@ __global__ void __launch_bounds__(TB_THREADS, TB_CTAS_PER_SM) rdf_train_hist_buc
                 label = __ldg(p.labels + i);
             }
             const bool use = have && label < (unsigned)p.C;                      // labels outside 0..C-1 cannot be counted
-            const unsigned am = __ballot_sync(0xffffffffu, use);
             if (!use) continue;
             const float df = (float)d;
             const float rcp = __frcp_rn(df);
@@ -488,8 +480,11 @@ __global__ void __launch_bounds__(TB_THREADS, TB_CTAS_PER_SM) rdf_train_hist_buc
                     const unsigned dst = hist_base + (unsigned)(j0 + u) * row_bytes + key;
                     // one shared-memory reduction per distinct counter of the warp, issued by the lowest lane of each group as a
                     // PREDICATED instruction (a branch around it cost three more instructions per evaluation)
-                    const unsigned grp = __match_any_sync(am, key);
-                    tb_red_shared_if((grp & lanemask_lt) == 0u, dst, (unsigned)__popc(grp));
+                    // every lane adds 1 and the shared-memory atomic unit resolves the collisions.  Measured against one add per
+                    // distinct counter of the warp (match.any + popc + leader test, 12 instructions and a MATCH latency per
+                    // evaluation): 76-78 ms per cfg4 level instead of 95-99, and still faster (115 vs 124 ms) when every pixel of
+                    // the GPU hits the same counter (all probes outside the image) - profiles/r02_ncu_train.md
+                    tb_red_shared(dst, 1u);
                 }
             }
         }

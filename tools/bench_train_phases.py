@@ -22,6 +22,7 @@ def main():
     ap.add_argument('--frames', type=int, default=42)
     ap.add_argument('--features', type=int, default=2000)
     ap.add_argument('--levels', default='0,8,12')
+    ap.add_argument('--offset-scale', type=float, default=1.0, help='multiply the feature offsets (1e6: every probe leaves the image, every pixel lands in one bin: worst case for colliding shared-memory updates)')
     args = ap.parse_args()
     from rdf_b200 import _capi, synth
     lib = _capi.load()
@@ -30,6 +31,7 @@ def main():
     labels_np = synth.train_labels(N, H, W)
     labels = torch.from_numpy(labels_np.view(np.int16)).cuda()
     off_np, th_np = synth.random_proposals(F, NT)
+    off_np = (off_np * np.float32(args.offset_scale)).astype(np.float32)
     offsets, thresholds = torch.from_numpy(off_np).cuda(), torch.from_numpy(th_np).cuda()
     st = _capi.stream_ptr
     E = 7 + 2 * C

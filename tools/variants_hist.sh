@@ -4,7 +4,7 @@ LEVELS="$1"; shift
 for v in "$@"; do
   if [ "$v" = base ]; then unset RDF_B200_LIB; else export RDF_B200_LIB="$PWD/build/variants/$v/librdf_b200.so"; fi
   echo "== $v"
-  python tools/bench_train_phases.py --levels "$LEVELS" 2>&1 | python -c "
+  python tools/bench_train_phases.py --levels "$LEVELS" $EXTRA 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     try:
