@@ -207,7 +207,10 @@ extern "C" int rdf_train_hist(const uint16_t* depth_dev, const uint16_t* labels_
 static_assert((TB_U & (TB_U - 1)) == 0 && TB_U >= 1, "TB_U must be a power of two: feature chunks are rounded with bit masks");
 #define TB_TILE 8192            // sorted pixels per CTA
 #define TB_MAX_FC 256
-#define TB_SMEM_BUDGET ((size_t)(TB_CTAS_PER_SM == 1 ? 220 : TB_CTAS_PER_SM == 2 ? 110 : 72) * 1024)
+#ifndef TB_SMEM_KB
+#define TB_SMEM_KB (TB_CTAS_PER_SM == 1 ? 220 : TB_CTAS_PER_SM == 2 ? 110 : 60)   /* 3 x 60 KB leave 48 KB of L1 for the probes */
+#endif
+#define TB_SMEM_BUDGET ((size_t)TB_SMEM_KB * 1024)
 
 struct rdf_bucket_ws {           // layout of the caller-provided workspace
     int total;                   // number of bucketed pixels (device-side value, never read by the host)
