@@ -254,6 +254,52 @@ __global__ void __launch_bounds__(256) rdf_train_bucket_kernel(const int32_t* __
     }
 }
 
+// The same two passes with the slot counters privatised per CTA in shared memory (S <= TBK_MAX_SLOTS): at shallow levels every
+// pixel of the GPU lands in a handful of slots, and one global atomic per (warp, slot) on the same few addresses made the level-0
+// bucket 0.74 ms (7 % of an 8-GPU level).  A CTA takes chunks of TBK_CHUNK pixels: count them per slot with shared-memory
+// increments, reserve each slot's range with ONE global atomic, then (MODE 1) hand out positions inside the range with a second
+// round of shared-memory increments.  The order inside a slot's list depends on scheduling; the histograms do not (integer sums).
+#define TBK_THREADS 512
+#define TBK_CHUNK 8192
+#define TBK_MAX_SLOTS 8192
+template <int MODE>
+__global__ void __launch_bounds__(TBK_THREADS) rdf_train_bucket_cta_kernel(const int32_t* __restrict__ nodes, const int32_t* __restrict__ node_slot,
+                                                                           int64_t n, int S, int* __restrict__ counts_or_cursor,
+                                                                           int* __restrict__ list) {
+    extern __shared__ int tbk_s[];                                            // cnt[S], base[S]
+    int* cnt = tbk_s;
+    int* base = tbk_s + S;
+    for (int s = threadIdx.x; s < S; s += TBK_THREADS) cnt[s] = 0;
+    __syncthreads();
+    for (int64_t c0 = (int64_t)blockIdx.x * TBK_CHUNK; c0 < n; c0 += (int64_t)gridDim.x * TBK_CHUNK) {
+        int slot[TBK_CHUNK / TBK_THREADS];
+#pragma unroll
+        for (int k = 0; k < TBK_CHUNK / TBK_THREADS; k++) {
+            const int64_t i = c0 + k * TBK_THREADS + threadIdx.x;
+            slot[k] = i < n ? tb_slot_of(nodes, node_slot, i) : -1;
+            if (slot[k] >= 0) atomicAdd(&cnt[slot[k]], 1);
+        }
+        __syncthreads();
+        for (int s = threadIdx.x; s < S; s += TBK_THREADS) {
+            const int c = cnt[s];
+            if (c) {
+                const int b = atomicAdd(counts_or_cursor + s, c);
+                if (MODE == 1) base[s] = b;
+                cnt[s] = 0;
+            }
+        }
+        __syncthreads();
+        if (MODE == 1) {
+#pragma unroll
+            for (int k = 0; k < TBK_CHUNK / TBK_THREADS; k++)
+                if (slot[k] >= 0) list[base[slot[k]] + atomicAdd(&cnt[slot[k]], 1)] = (int)(c0 + k * TBK_THREADS + threadIdx.x);
+            __syncthreads();
+            for (int s = threadIdx.x; s < S; s += TBK_THREADS) cnt[s] = 0;
+            __syncthreads();
+        }
+    }
+}
+
 // single CTA: exclusive scan of counts[S] (held in starts[]) -> starts[0..S], cursor[s] = starts[s], total
 __global__ void __launch_bounds__(1024) rdf_train_bucket_scan_kernel(int* __restrict__ starts, int* __restrict__ cursor, int S,
                                                                       int* __restrict__ total) {
@@ -313,9 +359,21 @@ extern "C" int rdf_train_bucket(const int32_t* nodes_by_pixel_dev, int64_t num_p
     int blocks = (int)((num_pixels + 255) / 256);
     if (blocks > rdf_sm_count() * 16) blocks = rdf_sm_count() * 16;
     if (blocks < 1) blocks = 1;
-    rdf_train_bucket_kernel<0><<<blocks, 256, 0, st>>>(nodes_by_pixel_dev, node_slot_dev, num_pixels, starts, nullptr);
-    rdf_train_bucket_scan_kernel<<<1, 1024, 0, st>>>(starts, cursor, num_slots, total);
-    rdf_train_bucket_kernel<1><<<blocks, 256, 0, st>>>(nodes_by_pixel_dev, node_slot_dev, num_pixels, cursor, list);
+    if (num_slots <= TBK_MAX_SLOTS) {
+        int cblocks = (int)((num_pixels + TBK_CHUNK - 1) / TBK_CHUNK);
+        if (cblocks > rdf_sm_count() * 4) cblocks = rdf_sm_count() * 4;
+        if (cblocks < 1) cblocks = 1;
+        const size_t smem = sizeof(int) * 2 * (size_t)num_slots;
+        RDF_ENSURE_DYN_SMEM(rdf_train_bucket_cta_kernel<0>, sizeof(int) * 2 * TBK_MAX_SLOTS);
+        RDF_ENSURE_DYN_SMEM(rdf_train_bucket_cta_kernel<1>, sizeof(int) * 2 * TBK_MAX_SLOTS);
+        rdf_train_bucket_cta_kernel<0><<<cblocks, TBK_THREADS, smem, st>>>(nodes_by_pixel_dev, node_slot_dev, num_pixels, num_slots, starts, nullptr);
+        rdf_train_bucket_scan_kernel<<<1, 1024, 0, st>>>(starts, cursor, num_slots, total);
+        rdf_train_bucket_cta_kernel<1><<<cblocks, TBK_THREADS, smem, st>>>(nodes_by_pixel_dev, node_slot_dev, num_pixels, num_slots, cursor, list);
+    } else {
+        rdf_train_bucket_kernel<0><<<blocks, 256, 0, st>>>(nodes_by_pixel_dev, node_slot_dev, num_pixels, starts, nullptr);
+        rdf_train_bucket_scan_kernel<<<1, 1024, 0, st>>>(starts, cursor, num_slots, total);
+        rdf_train_bucket_kernel<1><<<blocks, 256, 0, st>>>(nodes_by_pixel_dev, node_slot_dev, num_pixels, cursor, list);
+    }
     RDF_LAUNCH_CHECK("rdf_train_bucket kernels");
     return RDF_OK;
 }
