@@ -430,6 +430,55 @@ __device__ __forceinline__ int tb_lds(unsigned smem_addr) {
     return v;
 }
 
+// All features of the CTA's chunk at one pixel: probes -> integer feature -> threshold bin -> histogram increment.
+// compute_feature with scale 1 (tree_train.cu:58).  d == 0 -> the feature is 0.f (decision_tree_common.hpp:12): on the reciprocal
+// path that costs nothing per evaluation - with rcp = 0 every quotient is exactly 0, both probes land on the pixel itself and their
+// difference is 0; the exact-divide path (features flagged at staging time) keeps the explicit select.
+template <int LOG2NTP, bool ANY_EXACT>
+__device__ __forceinline__ void tb_pixel_features(const uint16_t* __restrict__ img, int W, int H, int X, int Y, unsigned d,
+                                                  const float4* __restrict__ off_s, const unsigned char* __restrict__ exact_s,
+                                                  unsigned thr_base, unsigned hist_base, unsigned row_bytes, unsigned C, unsigned label4,
+                                                  int nfp) {
+    constexpr int NTP = 1 << LOG2NTP;
+    const float df = (float)d;
+    const float rcp = d != 0u ? __frcp_rn(df) : 0.f;
+    const float xm = (float)X + RDF_MAGIC_F, ym = (float)Y + RDF_MAGIC_F;
+    for (int j0 = 0; j0 < nfp; j0 += TB_U) {
+        int f[TB_U];
+        unsigned tha[TB_U];                                              // shared address of the feature's thresholds
+#pragma unroll
+        for (int u = 0; u < TB_U; u++) {
+            const int j = j0 + u;
+            const float4 o = off_s[j];
+            tha[u] = thr_base + (unsigned)j * (NTP * 4u);
+            if (ANY_EXACT && exact_s[j]) {
+                f[u] = rdf_feature_i<true>(img, W, H, X, Y, df, rcp, xm, ym, o.x, o.y, o.z, o.w);
+                f[u] = d != 0u ? f[u] : 0;
+            } else {
+                f[u] = rdf_feature_i<false>(img, W, H, X, Y, df, rcp, xm, ym, o.x, o.y, o.z, o.w);
+            }
+        }
+        // bin = #{k : t_k <= f}: binary search by halving steps, then one last compare.  The running value is the shared ADDRESS of
+        // thresholds[pos] (one predicated add per step: load, compare, add), not an index that would need a select and a second
+        // add to become an address.
+        unsigned pa[TB_U];
+#pragma unroll
+        for (int u = 0; u < TB_U; u++) pa[u] = tha[u];
+        tb_search_steps<LOG2NTP - 1, TB_U>(pa, f);                               // thresholds[pos + step - 1] <= f ?
+#pragma unroll
+        for (int u = 0; u < TB_U; u++) tb_step<0, 4>(pa[u], f[u]);               // pos <= NTP - 1; then pos = bin in 0..NT
+#pragma unroll
+        for (int u = 0; u < TB_U; u++) {
+            const unsigned key = (pa[u] - tha[u]) * C + label4;                  // byte offset of [bin][label]
+            // every lane adds 1 and the shared-memory atomic unit resolves the collisions (ptxas: ATOMS.POPC.INC).  Measured against
+            // one add per distinct counter of the warp (match.any + popc + leader test, 12 instructions and a MATCH latency per
+            // evaluation): 76-78 ms per cfg4 level instead of 95-99, and still faster (115 vs 124 ms) when every pixel of the GPU
+            // hits the same counter (all probes outside the image) - profiles/r02_ncu_train.md
+            tb_red_shared(hist_base + (unsigned)(j0 + u) * row_bytes + key, 1u);
+        }
+    }
+}
+
 // LOG2NTP: thresholds of a feature are padded in shared memory to NTP = 2^LOG2NTP entries with INT_MAX, so the search is a
 // fixed, fully unrolled sequence of LOG2NTP + 1 loads without bound checks.
 template <int LOG2NTP>
@@ -506,48 +555,13 @@ __global__ void __launch_bounds__(TB_THREADS, TB_CTAS_PER_SM) rdf_train_hist_buc
             }
             const bool use = have && label < (unsigned)p.C;                      // labels outside 0..C-1 cannot be counted
             if (!use) continue;
-            const float df = (float)d;
-            const float rcp = __frcp_rn(df);
-            const float xm = (float)X + RDF_MAGIC_F, ym = (float)Y + RDF_MAGIC_F;
-            const unsigned label4 = label * 4u;
             // TB_U features per trip: their 2 * TB_U probes are issued before any is consumed and the TB_U threshold searches
-            // advance in lock step, so one warp keeps several independent load chains in flight.
-            for (int j0 = 0; j0 < nfp; j0 += TB_U) {
-                int f[TB_U];
-                unsigned tha[TB_U];                                              // shared address of the feature's thresholds
-#pragma unroll
-                for (int u = 0; u < TB_U; u++) {
-                    const int j = j0 + u;
-                    const float4 o = off_s[j];
-                    tha[u] = thr_base + (unsigned)j * (NTP * 4u);
-                    // compute_feature with scale 1 (tree_train.cu:58); d == 0 -> 0.f (decision_tree_common.hpp:12)
-                    if (any_exact && exact_s[j]) f[u] = rdf_feature_i<true>(img, p.W, p.H, X, Y, df, rcp, xm, ym, o.x, o.y, o.z, o.w);
-                    else f[u] = rdf_feature_i<false>(img, p.W, p.H, X, Y, df, rcp, xm, ym, o.x, o.y, o.z, o.w);
-                    f[u] = d != 0u ? f[u] : 0;
-                }
-                // bin = #{k : t_k <= f}: binary search by halving steps, then one last compare.  The running value is the shared
-                // ADDRESS of thresholds[pos] (one predicated add per step: load, compare, add), not an index that would need a
-                // select and a second add to become an address (those were 14 of 79 instructions per evaluation,
-                // profiles/r02_ncu_train_hist.md).
-                unsigned pa[TB_U];
-#pragma unroll
-                for (int u = 0; u < TB_U; u++) pa[u] = tha[u];
-                tb_search_steps<LOG2NTP - 1, TB_U>(pa, f);                               // thresholds[pos + step - 1] <= f ?
-#pragma unroll
-                for (int u = 0; u < TB_U; u++) tb_step<0, 4>(pa[u], f[u]);               // pos <= NTP - 1; then pos = bin in 0..NT
-#pragma unroll
-                for (int u = 0; u < TB_U; u++) {
-                    const unsigned key = (pa[u] - tha[u]) * (unsigned)p.C + label4;     // byte offset of [bin][label]
-                    const unsigned dst = hist_base + (unsigned)(j0 + u) * row_bytes + key;
-                    // one shared-memory reduction per distinct counter of the warp, issued by the lowest lane of each group as a
-                    // PREDICATED instruction (a branch around it cost three more instructions per evaluation)
-                    // every lane adds 1 and the shared-memory atomic unit resolves the collisions.  Measured against one add per
-                    // distinct counter of the warp (match.any + popc + leader test, 12 instructions and a MATCH latency per
-                    // evaluation): 76-78 ms per cfg4 level instead of 95-99, and still faster (115 vs 124 ms) when every pixel of
-                    // the GPU hits the same counter (all probes outside the image) - profiles/r02_ncu_train.md
-                    tb_red_shared(dst, 1u);
-                }
-            }
+            // advance in lock step, so one warp keeps several independent load chains in flight.  Two instances of the loop: the
+            // common one knows that no feature of the chunk needs the exact divide (CTA-uniform) and has no per-evaluation test.
+            if (any_exact)
+                tb_pixel_features<LOG2NTP, true>(img, p.W, p.H, X, Y, d, off_s, exact_s, thr_base, hist_base, row_bytes, (unsigned)p.C, label * 4u, nfp);
+            else
+                tb_pixel_features<LOG2NTP, false>(img, p.W, p.H, X, Y, d, off_s, exact_s, thr_base, hist_base, row_bytes, (unsigned)p.C, label * 4u, nfp);
         }
         __syncthreads();
         // flush this node's counters and clear them for the next node.  With an even class count two neighbouring counters
