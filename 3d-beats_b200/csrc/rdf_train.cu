@@ -191,15 +191,16 @@ extern "C" int rdf_train_hist(const uint16_t* depth_dev, const uint16_t* labels_
 // to its counter with red.shared - the shared-memory atomic unit resolves collisions faster than a match.any aggregation did.
 // Tunables (overridable with -D for variant builds, tools/build_variant.sh): threads per CTA, CTAs per SM the shared-memory
 // budget is split over, features evaluated together by one thread.
-// Measured on cfg4 (profiles/r02_ncu_train.md): the kernel is latency-bound (1.65 eligible warps per scheduler of 8 resident), so
-// eight interleaved feature chains per thread and several small CTAs per SM (the others keep issuing while one sits at its
-// per-node flush barrier) beat 1 x 1024 threads x 4 chains by 9-10 %; 3 x 384 threads (55 registers, 36 warps per SM) is another 3 %
-// ahead of 2 x 512.
+// Measured on cfg4 (profiles/r02_ncu_train.md, gpurun_out/r02_variants*.log).  While the kernel was latency-bound (match.any
+// aggregation, exact-divide test in the loop) several small CTAs per SM won; with the lean loop the per-pixel setup of every
+// feature chunk is what is left to amortise, and ONE 1024-thread CTA per SM with the whole 220 KB of shared memory (160 features
+// per chunk at NT = 64, C = 4) is ahead: 63.8 / 62.9 / 64.2 ms at levels 0 / 8 / 12 against 64.4 / 63.8 / 64.8 (2 x 512 threads,
+// 96 KB) and 65.7 / 65.3 / 66.2 (3 x 384, 60 KB).
 #ifndef TB_THREADS
-#define TB_THREADS 384
+#define TB_THREADS 1024
 #endif
 #ifndef TB_CTAS_PER_SM
-#define TB_CTAS_PER_SM 3
+#define TB_CTAS_PER_SM 1
 #endif
 #ifndef TB_U
 #define TB_U 8                  // features evaluated together by one thread (independent load chains)

@@ -558,7 +558,7 @@ class DecisionTreeTrainer():
         ntp = 1
         while ntp < NT:
             ntp *= 2
-        bucketed_fits = 8 * (16 + 4 * ntp + 4 * (NT + 1) * C + 1) + 64 <= 60 * 1024       # rdf_train_hist_bucketed's shared-memory need (TB_U features, TB_SMEM_KB)
+        bucketed_fits = 8 * (16 + 4 * ntp + 4 * (NT + 1) * C + 1) + 64 <= 220 * 1024      # rdf_train_hist_bucketed's shared-memory need (TB_U features, TB_SMEM_KB)
         if dist is not None and self.exchange != 'allreduce' and bucketed_fits:
             try:
                 self._setup_p2p(dist, P, NT, C)
