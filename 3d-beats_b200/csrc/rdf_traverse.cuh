@@ -51,7 +51,9 @@ __device__ __forceinline__ rdf_hdr_regs rdf_load_hdr(const rdf_node_hdr* __restr
 // Levels [j0, j1) of T interleaved walks.  SMEM = true: headers come from a shared-memory copy of the upper levels (index =
 // t * stride + row, child ids already rewritten to that indexing, see rdf_stage_upper_levels); else from the packed forest.
 // state[t] >= 0: current node; < 0: ended (~leaf_id or RDF_NO_LEAF).
-template <int T, bool SCALE1, bool FORCE_EXACT, bool SMEM>
+// NEVER_EXACT: the forest holds no node flagged RDF_FLAG_EXACT_DIV (known on the host after packing) and the scale is in the fast
+// domain, so the loop carries neither the flag test nor the __fdiv_rn path.
+template <int T, bool SCALE1, bool FORCE_EXACT, bool SMEM, bool NEVER_EXACT = false>
 __device__ __forceinline__ void rdf_walk_levels(const rdf_node_hdr* __restrict__ hdr, int tree_stride, int j0, int j1,
                                                 const uint16_t* __restrict__ img, int W, int H, int X, int Y, float df, float rcp,
                                                 float xm, float ym, float scale, int (&state)[T]) {
@@ -73,7 +75,7 @@ __device__ __forceinline__ void rdf_walk_levels(const rdf_node_hdr* __restrict__
             } else {
                 h[t] = rdf_load_hdr(hdr, node);
             }
-            any_flags |= h[t].b.w;
+            if (!NEVER_EXACT) any_flags |= h[t].b.w;
             if (!SCALE1) {
                 h[t].a.x = __fmul_rn(scale, h[t].a.x);
                 h[t].a.y = __fmul_rn(scale, h[t].a.y);
@@ -82,7 +84,7 @@ __device__ __forceinline__ void rdf_walk_levels(const rdf_node_hdr* __restrict__
             }
         }
         int f[T];
-        if (FORCE_EXACT || (any_flags & RDF_FLAG_EXACT_DIV)) {
+        if (!NEVER_EXACT && (FORCE_EXACT || (any_flags & RDF_FLAG_EXACT_DIV))) {
 #pragma unroll
             for (int t = 0; t < T; t++)
                 f[t] = rdf_feature_i<true>(img, W, H, X, Y, df, rcp, xm, ym, h[t].a.x, h[t].a.y, h[t].a.z, h[t].a.w);
@@ -127,7 +129,7 @@ __device__ __forceinline__ void rdf_stage_upper_levels(const rdf_forest_view& fv
 // SCALE1: scale == 1.0f, so scale*u == u exactly and the multiplies are dropped.  FORCE_EXACT: always use __fdiv_rn
 // (scale outside the fast domain); otherwise nodes flagged RDF_FLAG_EXACT_DIV take the exact path per level.
 // hdr_s / KS: optional shared-memory copy of levels 0 .. KS-1 (rdf_stage_upper_levels); KS = 0: everything from global memory.
-template <int T, bool SCALE1, bool FORCE_EXACT>
+template <int T, bool SCALE1, bool FORCE_EXACT, bool NEVER_EXACT = false>
 __device__ __forceinline__ void rdf_walk(const rdf_forest_view& fv, const uint16_t* __restrict__ img, int W, int H, int X,
                                          int Y, unsigned d, float scale, int (&state)[T], const rdf_node_hdr* hdr_s = nullptr,
                                          int KS = 0) {
@@ -138,12 +140,12 @@ __device__ __forceinline__ void rdf_walk(const rdf_forest_view& fv, const uint16
         const int M = (1 << KS) - 1;
 #pragma unroll
         for (int t = 0; t < T; t++) state[t] = t * M;
-        rdf_walk_levels<T, SCALE1, FORCE_EXACT, true>(hdr_s, M, 0, KS, img, W, H, X, Y, df, rcp, xm, ym, scale, state);
+        rdf_walk_levels<T, SCALE1, FORCE_EXACT, true, NEVER_EXACT>(hdr_s, M, 0, KS, img, W, H, X, Y, df, rcp, xm, ym, scale, state);
     } else {
 #pragma unroll
         for (int t = 0; t < T; t++) state[t] = t * fv.nodes_per_tree;
     }
-    rdf_walk_levels<T, SCALE1, FORCE_EXACT, false>(fv.hdr, fv.nodes_per_tree, KS, fv.D, img, W, H, X, Y, df, rcp, xm, ym, scale, state);
+    rdf_walk_levels<T, SCALE1, FORCE_EXACT, false, NEVER_EXACT>(fv.hdr, fv.nodes_per_tree, KS, fv.D, img, W, H, X, Y, df, rcp, xm, ym, scale, state);
 #pragma unroll
     for (int t = 0; t < T; t++)
         if (state[t] >= 0) state[t] = RDF_NO_LEAF;                   // D levels done and still on a node (cannot happen
