@@ -47,7 +47,10 @@ __global__ void rdf_pack_kernel(const float* __restrict__ canon, rdf_node_hdr* _
         h.flags = (rdf_fastfloor_domain(nd[0]) && rdf_fastfloor_domain(nd[1]) && rdf_fastfloor_domain(nd[2]) &&
                    rdf_fastfloor_domain(nd[3])) ? 0 : RDF_FLAG_EXACT_DIV;
         hdr[self] = h;
-        if (h.flags & RDF_FLAG_EXACT_DIV) *exact_flag = 1;            // benign race: everybody writes 1
+        // forest properties the host dispatches on (bit 0: some node needs the exact divide; bit 1: some walk can end above the
+        // last level, i.e. the forest is not a complete tree of depth D)
+        if (h.flags & RDF_FLAG_EXACT_DIV) atomicOr(exact_flag, 1);
+        if (!last && (h.left < 0 || h.right < 0)) atomicOr(exact_flag, 2);
         float* p = pdf + self * 2 * CP;
         for (int c = 0; c < CP; c++) {
             p[c] = c < C ? nd[7 + c] : 0.f;
@@ -65,8 +68,11 @@ static int rdf_pack(rdf_forest* f, const float* canon_dev, cudaStream_t stream) 
                                                 f->CP, f->exact_flag_dev);
     RDF_LAUNCH_CHECK("rdf_pack_kernel");
     // the flag is needed on the host to choose kernels: packing is handle creation / update, not the per-frame path
-    RDF_CUDA(cudaMemcpyAsync(&f->has_exact_nodes, f->exact_flag_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    int props = 0;
+    RDF_CUDA(cudaMemcpyAsync(&props, f->exact_flag_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
     RDF_CUDA(cudaStreamSynchronize(stream));
+    f->has_exact_nodes = props & 1;
+    f->has_early_leaves = (props >> 1) & 1;
     return RDF_OK;
 }
 
@@ -109,6 +115,7 @@ extern "C" int rdf_forest_create(const float* canon_dev, int num_trees, int max_
     if (e == cudaSuccess) e = cudaMalloc(&f->pdf, pdf_bytes);
     f->exact_flag_dev = nullptr;
     f->has_exact_nodes = 0;
+    f->has_early_leaves = 1;
     if (e == cudaSuccess) e = cudaMalloc(&f->exact_flag_dev, sizeof(int));
     if (e != cudaSuccess) {
         rdf_set_error("rdf_forest_create: allocating %zu packed bytes failed: %s", f->packed_bytes, cudaGetErrorString(e));

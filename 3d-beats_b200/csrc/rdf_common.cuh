@@ -106,6 +106,7 @@ struct rdf_forest {
     size_t packed_bytes;
     int device;
     int has_exact_nodes;          // some node carries RDF_FLAG_EXACT_DIV (set by the last pack; read back at create / update)
+    int has_early_leaves;         // some walk can end above level D-1 (0: every tree is complete, all walks take exactly D steps)
     int* exact_flag_dev;          // device word the pack kernel ORs into
 };
 

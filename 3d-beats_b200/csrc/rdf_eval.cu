@@ -28,10 +28,11 @@ static_assert(RDF_EVAL_SMEM_LEVELS <= RDF_PACK_TOP_LEVELS, "the staged levels mu
 // Measured on cfg3 (T=4): 5 or 6 CTAs per SM with 48 / 40 registers spill and are 18 % / 30 % slower.
 #define RDF_EVAL_MIN_BLOCKS(T) RDF_EVAL_MIN_BLOCKS_T(T)
 // EXACT: 0 = no node of the forest needs the exact divide (the common case: the loop has no flag test and no __fdiv_rn path),
-// 1 = per-node flags, 2 = always exact (scale outside the fast domain)
+// 1 = per-node flags, 2 = always exact (scale outside the fast domain), 3 = as 0 and every tree is complete (no early leaves: no
+// "walk ended" handling in the loop either)
 template <int T, int WARP_W, bool SCALE1, int EXACT>
 __global__ void __launch_bounds__(256, RDF_EVAL_MIN_BLOCKS(T)) rdf_eval_packed_kernel(const rdf_eval_params p) {
-    constexpr bool FORCE_EXACT = EXACT == 2, NEVER_EXACT = EXACT == 0;
+    constexpr bool FORCE_EXACT = EXACT == 2, NEVER_EXACT = EXACT == 0 || EXACT == 3, COMPLETE = EXACT == 3;
     constexpr int WARP_H = 32 / WARP_W;
     constexpr int WARPS_X = 32 / WARP_W;
     // levels 0 .. KS-1 of all T trees in shared memory (2 KB per tree at KS = 6), staged before any thread leaves
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(256, RDF_EVAL_MIN_BLOCKS(T)) rdf_eval_packed_k
     const unsigned d = __ldg(img + (size_t)Y * p.W + X);
     if (d == 0u || d == RDF_NO_PIXEL) return;                                            // tree_eval.cu:88-89
     int state[T];
-    rdf_walk<T, SCALE1, FORCE_EXACT, NEVER_EXACT>(p.fv, img, p.W, p.H, X, Y, d, p.scale, state, hdr_s, KS);
+    rdf_walk<T, SCALE1, FORCE_EXACT, NEVER_EXACT, COMPLETE>(p.fv, img, p.W, p.H, X, Y, d, p.scale, state, hdr_s, KS);
     if (T == 1 && p.tree_mode && state[0] == RDF_NO_LEAF) return;
     const int lab = rdf_vote<T>(p.fv, state, p.probs ? p.probs + li * p.fv.C : nullptr);
     p.labels[li] = (uint16_t)lab;
@@ -151,25 +152,28 @@ static int rdf_warp_w() {
 }
 
 template <int T, int WARP_W>
-static void rdf_launch_packed_tw(const rdf_eval_params& p, bool has_exact_nodes, dim3 grid, cudaStream_t stream) {
+static void rdf_launch_packed_tw(const rdf_eval_params& p, int props, dim3 grid, cudaStream_t stream) {
+    const bool has_exact_nodes = (props & 1) != 0, complete = (props & 2) == 0;
     // fast path (reciprocal divide + magic-number floor): |scale| in [2^-30, 1] and coordinates below 2^16
     if (!rdf_scale_fastfloor_ok(p.scale) || p.W > 65535 || p.H > 65535)
         rdf_eval_packed_kernel<T, WARP_W, false, 2><<<grid, 256, 0, stream>>>(p);
     else if (p.scale == 1.f) {
         if (has_exact_nodes) rdf_eval_packed_kernel<T, WARP_W, true, 1><<<grid, 256, 0, stream>>>(p);
+        else if (complete) rdf_eval_packed_kernel<T, WARP_W, true, 3><<<grid, 256, 0, stream>>>(p);
         else rdf_eval_packed_kernel<T, WARP_W, true, 0><<<grid, 256, 0, stream>>>(p);
     } else {
         if (has_exact_nodes) rdf_eval_packed_kernel<T, WARP_W, false, 1><<<grid, 256, 0, stream>>>(p);
+        else if (complete) rdf_eval_packed_kernel<T, WARP_W, false, 3><<<grid, 256, 0, stream>>>(p);
         else rdf_eval_packed_kernel<T, WARP_W, false, 0><<<grid, 256, 0, stream>>>(p);
     }
 }
 
 template <int T>
-static void rdf_launch_packed_t(const rdf_eval_params& p, bool has_exact_nodes, dim3 grid, cudaStream_t stream) {
+static void rdf_launch_packed_t(const rdf_eval_params& p, int props, dim3 grid, cudaStream_t stream) {
     switch (rdf_warp_w()) {
-        case 32: rdf_launch_packed_tw<T, 32>(p, has_exact_nodes, grid, stream); break;
-        case 16: rdf_launch_packed_tw<T, 16>(p, has_exact_nodes, grid, stream); break;
-        default: rdf_launch_packed_tw<T, 8>(p, has_exact_nodes, grid, stream); break;
+        case 32: rdf_launch_packed_tw<T, 32>(p, props, grid, stream); break;
+        case 16: rdf_launch_packed_tw<T, 16>(p, props, grid, stream); break;
+        default: rdf_launch_packed_tw<T, 8>(p, props, grid, stream); break;
     }
 }
 
@@ -217,14 +221,14 @@ static int rdf_eval_packed(const rdf_forest_t* forest, const uint16_t* depth_dev
         p.image0 = n0;
         dim3 grid((unsigned)(p.tiles_x * tiles_y), (unsigned)nb);
         switch (forest->T) {
-            case 1: rdf_launch_packed_t<1>(p, forest->has_exact_nodes != 0, grid, st); break;
-            case 2: rdf_launch_packed_t<2>(p, forest->has_exact_nodes != 0, grid, st); break;
-            case 3: rdf_launch_packed_t<3>(p, forest->has_exact_nodes != 0, grid, st); break;
-            case 4: rdf_launch_packed_t<4>(p, forest->has_exact_nodes != 0, grid, st); break;
-            case 5: rdf_launch_packed_t<5>(p, forest->has_exact_nodes != 0, grid, st); break;
-            case 6: rdf_launch_packed_t<6>(p, forest->has_exact_nodes != 0, grid, st); break;
-            case 7: rdf_launch_packed_t<7>(p, forest->has_exact_nodes != 0, grid, st); break;
-            default: rdf_launch_packed_t<8>(p, forest->has_exact_nodes != 0, grid, st); break;
+            case 1: rdf_launch_packed_t<1>(p, (forest->has_exact_nodes ? 1 : 0) | (forest->has_early_leaves ? 2 : 0), grid, st); break;
+            case 2: rdf_launch_packed_t<2>(p, (forest->has_exact_nodes ? 1 : 0) | (forest->has_early_leaves ? 2 : 0), grid, st); break;
+            case 3: rdf_launch_packed_t<3>(p, (forest->has_exact_nodes ? 1 : 0) | (forest->has_early_leaves ? 2 : 0), grid, st); break;
+            case 4: rdf_launch_packed_t<4>(p, (forest->has_exact_nodes ? 1 : 0) | (forest->has_early_leaves ? 2 : 0), grid, st); break;
+            case 5: rdf_launch_packed_t<5>(p, (forest->has_exact_nodes ? 1 : 0) | (forest->has_early_leaves ? 2 : 0), grid, st); break;
+            case 6: rdf_launch_packed_t<6>(p, (forest->has_exact_nodes ? 1 : 0) | (forest->has_early_leaves ? 2 : 0), grid, st); break;
+            case 7: rdf_launch_packed_t<7>(p, (forest->has_exact_nodes ? 1 : 0) | (forest->has_early_leaves ? 2 : 0), grid, st); break;
+            default: rdf_launch_packed_t<8>(p, (forest->has_exact_nodes ? 1 : 0) | (forest->has_early_leaves ? 2 : 0), grid, st); break;
         }
         RDF_LAUNCH_CHECK("rdf_eval_packed_kernel");
     }

@@ -53,21 +53,25 @@ __device__ __forceinline__ rdf_hdr_regs rdf_load_hdr(const rdf_node_hdr* __restr
 // state[t] >= 0: current node; < 0: ended (~leaf_id or RDF_NO_LEAF).
 // NEVER_EXACT: the forest holds no node flagged RDF_FLAG_EXACT_DIV (known on the host after packing) and the scale is in the fast
 // domain, so the loop carries neither the flag test nor the __fdiv_rn path.
-template <int T, bool SCALE1, bool FORCE_EXACT, bool SMEM, bool NEVER_EXACT = false>
+// COMPLETE: every tree of the forest is a complete tree (no leaf above level D-1, known on the host after packing): no walk ends
+// early, so the loop needs neither the "all walks ended" exit nor the per-tree "ended" clamp and select.
+template <int T, bool SCALE1, bool FORCE_EXACT, bool SMEM, bool NEVER_EXACT = false, bool COMPLETE = false>
 __device__ __forceinline__ void rdf_walk_levels(const rdf_node_hdr* __restrict__ hdr, int tree_stride, int j0, int j1,
                                                 const uint16_t* __restrict__ img, int W, int H, int X, int Y, float df, float rcp,
                                                 float xm, float ym, float scale, int (&state)[T]) {
     for (int j = j0; j < j1; j++) {
-        int all = state[0];
+        if (!COMPLETE) {
+            int all = state[0];
 #pragma unroll
-        for (int t = 1; t < T; t++) all &= state[t];
-        if (all < 0) break;                                          // every walk of this pixel has ended
+            for (int t = 1; t < T; t++) all &= state[t];
+            if (all < 0) break;                                      // every walk of this pixel has ended
+        }
         rdf_hdr_regs h[T];
         int any_flags = 0;
 #pragma unroll
         for (int t = 0; t < T; t++) {
             // ended walks re-read their tree's root (cached): harmless, keeps the loop branch-free
-            const int node = max(state[t], t * tree_stride);
+            const int node = COMPLETE ? state[t] : max(state[t], t * tree_stride);
             if (SMEM) {
                 const float4* sp = reinterpret_cast<const float4*>(hdr + node);
                 h[t].a = sp[0];
@@ -96,7 +100,7 @@ __device__ __forceinline__ void rdf_walk_levels(const rdf_node_hdr* __restrict__
 #pragma unroll
         for (int t = 0; t < T; t++) {
             const int next = (f[t] < h[t].b.x) ? h[t].b.y : h[t].b.z;   // NaN threshold -> INT_MIN -> right (tree_eval.cu:106)
-            state[t] = state[t] < 0 ? state[t] : next;
+            state[t] = (COMPLETE || state[t] >= 0) ? next : state[t];
         }
     }
 }
@@ -129,7 +133,7 @@ __device__ __forceinline__ void rdf_stage_upper_levels(const rdf_forest_view& fv
 // SCALE1: scale == 1.0f, so scale*u == u exactly and the multiplies are dropped.  FORCE_EXACT: always use __fdiv_rn
 // (scale outside the fast domain); otherwise nodes flagged RDF_FLAG_EXACT_DIV take the exact path per level.
 // hdr_s / KS: optional shared-memory copy of levels 0 .. KS-1 (rdf_stage_upper_levels); KS = 0: everything from global memory.
-template <int T, bool SCALE1, bool FORCE_EXACT, bool NEVER_EXACT = false>
+template <int T, bool SCALE1, bool FORCE_EXACT, bool NEVER_EXACT = false, bool COMPLETE = false>
 __device__ __forceinline__ void rdf_walk(const rdf_forest_view& fv, const uint16_t* __restrict__ img, int W, int H, int X,
                                          int Y, unsigned d, float scale, int (&state)[T], const rdf_node_hdr* hdr_s = nullptr,
                                          int KS = 0) {
@@ -140,12 +144,12 @@ __device__ __forceinline__ void rdf_walk(const rdf_forest_view& fv, const uint16
         const int M = (1 << KS) - 1;
 #pragma unroll
         for (int t = 0; t < T; t++) state[t] = t * M;
-        rdf_walk_levels<T, SCALE1, FORCE_EXACT, true, NEVER_EXACT>(hdr_s, M, 0, KS, img, W, H, X, Y, df, rcp, xm, ym, scale, state);
+        rdf_walk_levels<T, SCALE1, FORCE_EXACT, true, NEVER_EXACT, COMPLETE>(hdr_s, M, 0, KS, img, W, H, X, Y, df, rcp, xm, ym, scale, state);
     } else {
 #pragma unroll
         for (int t = 0; t < T; t++) state[t] = t * fv.nodes_per_tree;
     }
-    rdf_walk_levels<T, SCALE1, FORCE_EXACT, false, NEVER_EXACT>(fv.hdr, fv.nodes_per_tree, KS, fv.D, img, W, H, X, Y, df, rcp, xm, ym, scale, state);
+    rdf_walk_levels<T, SCALE1, FORCE_EXACT, false, NEVER_EXACT, COMPLETE>(fv.hdr, fv.nodes_per_tree, KS, fv.D, img, W, H, X, Y, df, rcp, xm, ym, scale, state);
 #pragma unroll
     for (int t = 0; t < T; t++)
         if (state[t] >= 0) state[t] = RDF_NO_LEAF;                   // D levels done and still on a node (cannot happen
