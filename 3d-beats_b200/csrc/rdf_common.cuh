@@ -69,7 +69,9 @@ struct __align__(32) rdf_node_hdr {
 //                      instead of two; an unpaired last level is stored densely.  The pdf table uses the same ids.
 #define RDF_LAYOUT_HEAP 0
 #define RDF_LAYOUT_BLOCKS 1
+#ifndef RDF_PACK_TOP_LEVELS
 #define RDF_PACK_TOP_LEVELS 6
+#endif
 #ifndef RDF_LAYOUT_DEFAULT
 #define RDF_LAYOUT_DEFAULT RDF_LAYOUT_HEAP
 #endif

@@ -20,7 +20,9 @@ struct rdf_eval_params {
     float scale;
 };
 
+#ifndef RDF_EVAL_SMEM_LEVELS
 #define RDF_EVAL_SMEM_LEVELS 6
+#endif
 static_assert(RDF_EVAL_SMEM_LEVELS <= RDF_PACK_TOP_LEVELS, "the staged levels must lie in the heap-ordered top of a packed tree");
 
 // CTAs per SM the register allocation aims for: 4 (<= 64 registers) up to 5 interleaved trees; the state of 6..8 trees does not
