@@ -20,8 +20,10 @@ struct rdf_eval_params {
     float scale;
 };
 
+// 5 levels (31 headers = 1 KB per tree): with the lean loop instances 5 is ahead of 6 (cfg3 7.60 vs 7.52 Gpx/s, noise 3.10 vs 3.02) - the
+// last staged level costs every 256-pixel CTA twice the staging loads and shared memory that L1 would otherwise have; 7 is 2 % behind 6
 #ifndef RDF_EVAL_SMEM_LEVELS
-#define RDF_EVAL_SMEM_LEVELS 6
+#define RDF_EVAL_SMEM_LEVELS 5
 #endif
 static_assert(RDF_EVAL_SMEM_LEVELS <= RDF_PACK_TOP_LEVELS, "the staged levels must lie in the heap-ordered top of a packed tree");
 
@@ -37,7 +39,7 @@ __global__ void __launch_bounds__(256, RDF_EVAL_MIN_BLOCKS(T)) rdf_eval_packed_k
     constexpr bool FORCE_EXACT = EXACT == 2, NEVER_EXACT = EXACT == 0 || EXACT == 3, COMPLETE = EXACT == 3;
     constexpr int WARP_H = 32 / WARP_W;
     constexpr int WARPS_X = 32 / WARP_W;
-    // levels 0 .. KS-1 of all T trees in shared memory (2 KB per tree at KS = 6), staged before any thread leaves
+    // levels 0 .. KS-1 of all T trees in shared memory (1 KB per tree at KS = 5), staged before any thread leaves
     __shared__ __align__(32) rdf_node_hdr hdr_s[T * ((1 << RDF_EVAL_SMEM_LEVELS) - 1)];
     const int KS = min(p.fv.D, p.smem_levels);
     if (KS > 0) {
