@@ -209,49 +209,44 @@ class LayeredDecisionForest():
     @staticmethod
     def load(config_filename, depth_dims, labels_reduce=1):
         cfg = json.loads(open(config_filename).read())
-        cfg['root'] = os.path.join(*Path(config_filename).parts[0:-1])    # models are relative to the config file
+        cfg['root'] = str(Path(config_filename).parent)                   # model paths are relative to the config file
         return LayeredDecisionForest(cfg, depth_dims, labels_reduce)
 
     def __init__(self, cfg, depth_dims, labels_reduce):
         self.eval = DecisionTreeEvaluator()
-        self.depth_dims = tuple(depth_dims)   # y,x !!
+        self.depth_dims = tuple(depth_dims)                       # (y, x)
         self.labels_reduce = labels_reduce
-        self.labels_dims = (depth_dims[0] // labels_reduce, depth_dims[1] // labels_reduce)
+        self.labels_dims = tuple(d // labels_reduce for d in self.depth_dims[:2])
 
-        self.m = []
-        for l in cfg['layers']:
-            model = l['model']
-            m = model if isinstance(model, DecisionForest) else DecisionForest.load(os.path.join(cfg['root'], model))
-            if 'filter_model' in l:           # the reference's second test is a constant-true string (SURVEY note N2)
-                filter_model = l['filter_model']
-                filter_model_class = l['filter_model_class']
-            else:
-                filter_model = None
-                filter_model_class = None
-            self.m.append((m, filter_model, filter_model_class))
-        self.num_models = len(self.m)
+        # one (forest, filter layer, filter class) triple per layer; a layer without 'filter_model' is ungated.  (The reference's
+        # second membership test is a constant-true string literal, SURVEY note N2, so only 'filter_model' decides.)
+        root = cfg.get('root', '')
+        self.m = [(spec['model'] if isinstance(spec['model'], DecisionForest) else DecisionForest.load(os.path.join(root, spec['model'])),
+                   spec.get('filter_model'), spec['filter_model_class'] if 'filter_model' in spec else None)
+                  for spec in cfg['layers']]
+        self.num_models = L = len(self.m)
 
-        self.label_images = [GpuBuffer(self.labels_dims, dtype=np.uint16) for _ in range(self.num_models)]
-        self.labels_images_ptrs_cu = GpuBuffer((self.num_models,), dtype=np.int64)
-        label_images_ptrs = np.array([i.cu().__cuda_array_interface__['data'][0] for i in self.label_images], dtype=np.int64)
-        self.labels_images_ptrs_cu.cu().set(label_images_ptrs)
+        # per-layer label maps and the device table of their addresses (make_composite_labels_image's first argument)
+        self.label_images = [GpuBuffer(self.labels_dims, dtype=np.uint16) for _ in range(L)]
+        self.labels_images_ptrs_cu = GpuBuffer((L,), dtype=np.int64)
+        self.labels_images_ptrs_cu.cu().set(np.fromiter((b.cu().ptr for b in self.label_images), dtype=np.int64, count=L))
 
-        # conditions: (0, PIXEL_ID) or (1, NEXT_IMG_CONDITION_OFFSET)   (src/decision_tree.py:209-220)
-        labels_conditions = np.array(cfg['conditions'], dtype=np.int32).reshape(-1, 2)
-        self.labels_conditions_cu = GpuBuffer(labels_conditions.shape, dtype=np.int32)
-        self.labels_conditions_cu.cu().set(labels_conditions)
-        self.num_layered_classes = int(max([c[1] for c in filter(lambda c: c[0] == 0, labels_conditions)]))
+        # condition rows are (0, composite id) or (1, row offset of the next layer's block)   (src/decision_tree.py:209-220)
+        conditions = np.asarray(cfg['conditions'], dtype=np.int32).reshape(-1, 2)
+        self.labels_conditions_cu = GpuBuffer(conditions.shape, dtype=np.int32)
+        self.labels_conditions_cu.cu().set(conditions)
+        self.num_layered_classes = int(conditions[conditions[:, 0] == 0, 1].max())
 
-        label_colors = np.array(cfg['label_colors'], dtype=np.uint8)
-        assert label_colors.shape == (self.num_layered_classes, 4)
-        self.label_colors = GpuBuffer(label_colors.shape, dtype=np.uint8)
-        self.label_colors.cu().set(label_colors)
+        colors = np.asarray(cfg['label_colors'], dtype=np.uint8)
+        assert colors.shape == (self.num_layered_classes, 4)
+        self.label_colors = GpuBuffer(colors.shape, dtype=np.uint8)
+        self.label_colors.cu().set(colors)
 
-        L = self.num_models
+        # ctypes views of the same tables for the fused launch
         self._c_filter_model = (ctypes.c_int * L)(*[(-1 if fm is None else int(fm)) for _, fm, _ in self.m])
         self._c_filter_class = (ctypes.c_int * L)(*[(-1 if fc is None else int(fc)) for _, _, fc in self.m])
-        self._c_label_ptrs = (ctypes.c_void_p * L)(*[i.cu().ptr for i in self.label_images])
-        self._n_cond = int(labels_conditions.shape[0])
+        self._c_label_ptrs = (ctypes.c_void_p * L)(*[b.cu().ptr for b in self.label_images])
+        self._n_cond = int(conditions.shape[0])
 
     def run(self, depth_image, labels_image, scale_factor=1., composite_flip_x=None, label_images=None):
         """src/decision_tree.py:233-264 in one launch.  Two keyword extensions for the live product's per-hand loop
@@ -332,56 +327,55 @@ class ResidentBlocks:
         self.block(block_num).set(as_gpuarray(arr_in))
 
 
+def _dataset_config(dataset_dir):
+    """config.json of a dataset directory (`dataset_dir` ends with a separator, as in the reference's call sites)"""
+    with open(dataset_dir + 'config.json') as fh:
+        return json.load(fh)
+
+
 class DecisionTreeDatasetConfig():
+    """src/decision_tree.py:21-122: a directory of `%08d_depth.png` / `%08d_labels.png` pairs described by config.json, served
+    as blocks of `images_per_block` uint16 images that live uncompressed in HBM (ResidentBlocks)."""
 
     @staticmethod
     def multiple(dataset_dir, images):
-        """randomly split up the dataset into chunks of the requested sizes (src/decision_tree.py:24-44)"""
-        total_images = json.loads(open(dataset_dir + 'config.json').read())['num_images']
-        num_images_to_fetch = sum([num_images for num_images, _, _ in images])
-        assert num_images_to_fetch <= total_images
-        # same np.random draw as the reference (src/decision_tree.py:30-31) so that a seeded run consumes the identical random
-        # stream afterwards (per-dataset shuffles, proposals); like the reference, the result is not used: every dataset shuffles
-        # the whole index range itself, so train and test sets are drawn independently and may overlap
-        images_to_fetch = list(range(total_images))
-        np.random.shuffle(images_to_fetch)
-        datasets = []
-        for num_images, images_per_block, imgs_name in images:
-            images_per_block = images_per_block or num_images
-            datasets.append(DecisionTreeDatasetConfig(dataset_dir, num_images=num_images, images_per_block=images_per_block,
-                                                      imgs_name=imgs_name))
-        return tuple(datasets)
+        """One dataset per (num_images, images_per_block, imgs_name) request (src/decision_tree.py:24-44)."""
+        available = _dataset_config(dataset_dir)['num_images']
+        assert sum(req[0] for req in images) <= available
+        # The reference shuffles the whole index range here and then does not use it (src/decision_tree.py:30-31): every dataset
+        # draws its own images below, so train and test sets are independent and may overlap.  The draw is kept so that a
+        # seeded np.random stream reaches the per-dataset shuffles and the proposal generators in the reference's state.
+        np.random.shuffle(list(range(available)))
+        return tuple(DecisionTreeDatasetConfig(dataset_dir, num_images=n, images_per_block=per_block or n, imgs_name=name)
+                     for n, per_block, name in images)
 
     def __init__(self, dataset_dir, num_images=0, images_per_block=0, imgs_name='data0'):
         self.dataset_dir = dataset_dir
-        cfg = json.loads(open(dataset_dir + 'config.json').read())
-        self.cfg = cfg
+        self.cfg = cfg = _dataset_config(dataset_dir)
         self.imgs_name = imgs_name
-        self.img_dims = tuple(cfg['img_dims'])
-        self.id_to_color = {0: np.array([0, 0, 0, 0], dtype=np.uint8)}
-        for i, c in cfg['id_to_color'].items():
-            self.id_to_color[int(i)] = np.array(c, dtype=np.uint8)
+        self.img_dims = tuple(cfg['img_dims'])                                    # (x, y)
+        self.id_to_color = {0: np.zeros(4, dtype=np.uint8)}                       # id 0 = unlabelled, transparent black
+        self.id_to_color.update((int(i), np.array(c, dtype=np.uint8)) for i, c in cfg['id_to_color'].items())
         self.total_available_images = cfg['num_images']
         self.num_images = num_images
-        if self.num_images == 0:
+        if not num_images:                                                        # descriptor only (colours, dims): nothing is loaded
             return
-        self.images_per_block = images_per_block or self.num_images
-        assert self.num_images % self.images_per_block == 0
-        self.num_image_blocks = self.num_images // self.images_per_block
+        self.images_per_block = images_per_block or num_images
+        assert num_images % self.images_per_block == 0
+        self.num_image_blocks = num_images // self.images_per_block
 
-        img_idxes = list(range(cfg['num_images']))
-        np.random.shuffle(img_idxes)
-        img_idxes = img_idxes[0:self.num_images]
+        order = list(range(self.total_available_images))
+        np.random.shuffle(order)                                                  # the reference's draw (a list, not an array)
+        self._image_ids = order[:num_images]
         block_shape = (self.images_per_block, self.img_dims[1], self.img_dims[0])
+        self.depth_blocks = ResidentBlocks(self.num_image_blocks, block_shape, np.uint16, lambda b, out: self._read_block(b, out, 'depth'))
+        self.labels_blocks = ResidentBlocks(self.num_image_blocks, block_shape, np.uint16, lambda b, out: self._read_block(b, out, 'labels'))
 
-        def get_image_block(i, arr_out, name):
-            assert arr_out.shape == block_shape and arr_out.dtype == np.uint16
-            for j in range(self.images_per_block):
-                img_idx = img_idxes[(i * self.images_per_block) + j]
-                arr_out[j] = np.array(Image.open(f'{self.dataset_dir}/{str(img_idx).zfill(8)}_{name}.png')).astype(np.uint16)
-
-        self.depth_blocks = ResidentBlocks(self.num_image_blocks, block_shape, np.uint16, lambda i, a: get_image_block(i, a, 'depth'))
-        self.labels_blocks = ResidentBlocks(self.num_image_blocks, block_shape, np.uint16, lambda i, a: get_image_block(i, a, 'labels'))
+    def _read_block(self, block, out, kind):
+        """decode the PNGs of one block into the host staging array `out` (uint16[images_per_block, H, W])"""
+        first = block * self.images_per_block
+        for j, image_id in enumerate(self._image_ids[first:first + self.images_per_block]):
+            out[j] = np.asarray(Image.open(f'{self.dataset_dir}/{image_id:08d}_{kind}.png')).astype(np.uint16)
 
     @classmethod
     def from_arrays(cls, depth, labels, num_classes, images_per_block=0, imgs_name='mem'):
@@ -412,24 +406,31 @@ class DecisionTreeDatasetConfig():
     def num_classes(self):
         return len(self.id_to_color)
 
+    def _color_table(self):
+        """RGBA colours as one uint32 per class id, in id_to_color order"""
+        ids = np.fromiter(self.id_to_color.keys(), dtype=np.int64)
+        rgba = np.stack([self.id_to_color[int(i)] for i in ids]).astype(np.uint8)
+        return ids, rgba, np.ascontiguousarray(rgba).view(np.uint32).ravel()
+
     def convert_colors_to_ids(self, labels_color):
-        labels_ids = np.zeros((self.img_dims[1], self.img_dims[0]), dtype=np.uint16)
-        labelled_pixels_count = 0
-        for class_id, color in self.id_to_color.items():
-            pixels_of_color = np.all(labels_color == color, axis=2)
-            labels_ids[pixels_of_color] = class_id
-            labelled_pixels_count += np.sum(pixels_of_color)
-        assert (labelled_pixels_count == self.img_dims[0] * self.img_dims[1])   # every pixel was labelled
-        return labels_ids
+        """RGBA label picture uint8[H,W,4] -> class ids uint16[H,W]; every pixel must carry a known colour (src/decision_tree.py:88-99)"""
+        W, H = self.img_dims
+        ids, _, packed = self._color_table()
+        px = np.ascontiguousarray(labels_color, dtype=np.uint8).reshape(H, W, 4).view(np.uint32)[..., 0]
+        hit = px[None] == packed[:, None, None]                                   # [classes, H, W]
+        assert int(hit.sum()) == W * H, 'a pixel carries a colour that is not in id_to_color'
+        out = np.zeros((H, W), dtype=np.uint16)
+        for k, class_id in enumerate(ids):                                        # later ids win, as in the reference's loop
+            out[hit[k]] = class_id
+        return out
 
     def convert_ids_to_colors(self, labels_ids):
-        num_images, y_dim, x_dim = labels_ids.shape
-        assert y_dim == self.img_dims[1]
-        assert x_dim == self.img_dims[0]
-        labels_colors = np.zeros((num_images, y_dim, x_dim, 4), dtype=np.uint8)
-        for class_id, color in self.id_to_color.items():
-            labels_colors[np.where(labels_ids == class_id)] = color
-        return labels_colors
+        """class ids uint16[N,H,W] -> RGBA uint8[N,H,W,4]; ids without a colour stay transparent black (src/decision_tree.py:101-110)"""
+        assert labels_ids.shape[1:] == (self.img_dims[1], self.img_dims[0])
+        ids, rgba, _ = self._color_table()
+        lut = np.zeros((max(int(ids.max()), int(np.max(labels_ids, initial=0))) + 1, 4), dtype=np.uint8)
+        lut[ids] = rgba
+        return lut[labels_ids]
 
     def get_depth_block_cu(self, block_num, arr_out):
         self.depth_blocks.get_block_cu(block_num, arr_out)
