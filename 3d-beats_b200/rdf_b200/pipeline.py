@@ -25,9 +25,14 @@ def pinned_like(shape, np_dtype):
 
 
 class HostBatchEvaluator:
-    def __init__(self, evaluator, forest, frame_shape, chunk_frames=64, labels_reduce=1, scale_factor=1., buffers=3):
+    def __init__(self, evaluator, forest, frame_shape, chunk_frames=128, labels_reduce=1, scale_factor=1., buffers=3, ramp=8):
         """buffers: device chunk buffers in rotation (3: the H2D of chunk i+1, the evaluation of chunk i and the D2H of chunk i-1
-        each own one, so neither copy direction ever waits for the other's buffer)."""
+        each own one, so neither copy direction ever waits for the other's buffer).
+        ramp: frames of the first chunk (0 / False: plain chunks).  The chunks double from there up to chunk_frames and shrink
+        again at the end of the batch, so that the pipeline fills with the upload of `ramp` frames and drains with the download
+        of `ramp` frames whatever the chunk size (the evaluation cannot start before the first upload ends, nor the last
+        download before the last evaluation), while the bulk of the batch runs in large chunks with few stream hand-overs."""
+        self.ramp = int(ramp) if ramp else 0
         self.ev = evaluator
         self.forest = forest
         self.H, self.W = frame_shape
@@ -41,6 +46,24 @@ class HostBatchEvaluator:
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream() for _ in range(3))
         self.bytes_h2d = 0
         self.bytes_d2h = 0
+
+    def chunk_sizes(self, N):
+        """frames per chunk, in order, for a batch of N frames"""
+        def doubling(c):
+            steps, s = [], self.ramp
+            while 0 < s < c:
+                steps.append(s)
+                s *= 2
+            return steps
+        c = self.chunk
+        steps = doubling(c)
+        while steps and 2 * sum(steps) + c > N:                          # a short batch ramps up to a smaller chunk
+            c = max(self.ramp, c // 2)
+            steps = doubling(c)
+        if not steps:
+            return [min(c, N - n0) for n0 in range(0, N, c)]
+        full, rest = divmod(N - 2 * sum(steps), c)
+        return steps + [c] * full + ([rest] if rest else []) + steps[::-1]
 
     def run(self, depth_host, labels_host, prefill=65535, copy_only=False):
         """depth_host: pinned torch uint16[N,H,W]; labels_host: pinned torch uint16[N,h,w] (fully overwritten:
@@ -56,9 +79,10 @@ class HostBatchEvaluator:
         ev_run = [None] * nbuf    # eval on buffer b finished
         ev_out = [None] * nbuf    # D2H of buffer b finished (buffer reusable)
         self.bytes_h2d = self.bytes_d2h = 0
-        for ci, n0 in enumerate(range(0, N, self.chunk)):
+        sizes = self.chunk_sizes(N)
+        starts = np.concatenate(([0], np.cumsum(sizes)[:-1])).tolist() if sizes else []
+        for ci, (n0, nb) in enumerate(zip(starts, sizes)):
             b = ci % nbuf
-            nb = min(self.chunk, N - n0)
             d_dev = self.depth_dev[b][:nb] if nb < self.chunk else self.depth_dev[b]
             l_dev = self.labels_dev[b][:nb] if nb < self.chunk else self.labels_dev[b]
             with torch.cuda.stream(self.s_in):
@@ -69,14 +93,20 @@ class HostBatchEvaluator:
             with torch.cuda.stream(self.s_run):
                 self.s_run.wait_event(ev_in[b])
                 if ev_out[b] is not None:
-                    self.s_run.wait_event(ev_out[b])              # previous D2H of this labels buffer finished
+                    self.s_run.wait_event(ev_out[b])              # previous D2H of this labels buffer (and its re-fill) finished
+                elif not copy_only:
+                    l_dev.fill(prefill)                           # first use of the buffer in this run
                 if not copy_only:
-                    l_dev.fill(prefill)
                     self.ev.get_labels_forest(self.forest, d_dev, l_dev, labels_reduce=self.r, scale_factor=self.scale)
                 ev_run[b] = torch.cuda.Event(); ev_run[b].record(self.s_run)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(ev_run[b])
                 labels_host[n0:n0 + nb].view(torch.int16).copy_(l_dev.tensor.view(torch.int16), non_blocking=True)
+                if not copy_only and ci + nbuf < len(sizes):
+                    # pre-fill for the buffer's next chunk here, behind the download and beside the running evaluation, instead
+                    # of in front of that chunk's evaluation (the kernels never write skipped pixels, tree_eval.cu:81-89)
+                    nxt = sizes[ci + nbuf]
+                    (self.labels_dev[b][:nxt] if nxt < self.chunk else self.labels_dev[b]).fill(prefill)
                 ev_out[b] = torch.cuda.Event(); ev_out[b].record(self.s_out)
             self.bytes_h2d += d_dev.nbytes
             self.bytes_d2h += l_dev.nbytes

@@ -662,6 +662,8 @@ def main():
     ap.add_argument('--ref-frames', type=int, default=4, help='frames per step of the --impl reference CPU arm')
     ap.add_argument('--no-extras', action='store_true', help='skip every leg but the headline number')
     ap.add_argument('--e2e-steps', type=int, default=5)
+    ap.add_argument('--e2e-chunk', type=int, default=128, help='frames per chunk of the host-buffer pipeline')
+    ap.add_argument('--e2e-no-ramp', action='store_true', help='plain chunks (no short first / last chunks): A/B aid')
     ap.add_argument('--latency-only', action='store_true', help='only the cfg2 frame-latency leg (profiling aid)')
     ap.add_argument('--latency-iters', type=int, default=1000)
     ap.add_argument('--numpy-baseline', action='store_true', help=argparse.SUPPRESS)
@@ -748,7 +750,7 @@ def main():
         depth_host = pinned_like((my_frames, H, W), np.uint16)
         labels_host = pinned_like((my_frames, H, W), np.uint16)
         depth_host.view(torch.int16).copy_(depth.tensor[:my_frames].view(torch.int16))
-        hb = HostBatchEvaluator(ev, forest, (H, W), chunk_frames=min(64, my_frames))
+        hb = HostBatchEvaluator(ev, forest, (H, W), chunk_frames=min(args.e2e_chunk, my_frames), ramp=0 if args.e2e_no_ramp else 8)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
         def timed(n, **kw):
@@ -772,8 +774,10 @@ def main():
                'steps': args.e2e_steps, 'ms_per_step': r(e2e_ms),
                'copy_only_mpix_s': r(total_px / copy_ms / 1e3, 1), 'host_copy_ceiling_gbs': r((h2d + d2h) / copy_ms / 1e6, 1),
                'achieved_copy_gbs': r((h2d + d2h) / e2e_ms / 1e6, 1),
-               'api': 'rdf_b200.pipeline.HostBatchEvaluator.run (pinned host frames -> pinned host label maps, 64-frame chunks, 3 device '
-                      'buffers on 3 streams); copy_only_* / host_copy_ceiling_gbs = the same chunked H2D + D2H with no kernel'}
+               'chunks': len(hb.chunk_sizes(my_frames)),
+               'api': 'rdf_b200.pipeline.HostBatchEvaluator.run (pinned host frames -> pinned host label maps, %d-frame chunks%s, 3 device '
+                      'buffers on 3 streams); copy_only_* / host_copy_ceiling_gbs = the same chunked H2D + D2H with no kernel'
+                      % (hb.chunk, ' reached by doubling from %d frames at both ends' % hb.ramp if hb.ramp else '')}
         del depth_host, labels_host, hb
 
     # ---- the reference's own kernel on the same GPU and inputs (sub-batch), with a bit-exact cross-check ----

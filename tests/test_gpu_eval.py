@@ -355,3 +355,32 @@ def test_block_layout_is_bit_exact():
     out = subprocess.run([sys.executable, '-c', _BLOCK_LAYOUT_SCRIPT % {'root': root}], capture_output=True, text=True, timeout=600,
                          env=dict(os.environ, RDF_PACK_LAYOUT='blocks'))
     assert out.returncode == 0 and out.stdout.strip().endswith('ok'), out.stderr[-2000:]
+
+
+@pytest.mark.parametrize('N,chunk,ramp', [(61, 16, 2), (61, 16, 0), (5, 16, 8), (64, 8, 1), (200, 32, 4)])
+def test_host_batch_evaluator_matches_resident_run(N, chunk, ramp):
+    """HostBatchEvaluator (pinned host frames in, pinned host label maps out, ramped chunk schedule on three streams) returns the
+    label maps of one resident get_labels_forest call, skipped pixels holding the pre-fill (test_on_saved_model.py:46-58)."""
+    import torch
+    from rdf_b200 import synth
+    from rdf_b200.pipeline import HostBatchEvaluator, pinned_like
+    dt = _api()
+    H, W = 40, 72
+    depth = synth.depth_frames('live-mask', N, H, W, seed=21)
+    forest_np = synth.random_forest(3, 9, 4, seed=4, ragged=True)
+    want, _ = _run_ours(forest_np, depth, prefill=4321)
+    f = dt.DecisionForest(3, 9, 4)
+    f.forest_cu.set(forest_np)
+    hb = HostBatchEvaluator(dt.DecisionTreeEvaluator(), f, (H, W), chunk_frames=chunk, ramp=ramp)
+    sizes = hb.chunk_sizes(N)
+    assert sum(sizes) == N and max(sizes) <= chunk and min(sizes) >= 1
+    depth_host = pinned_like((N, H, W), np.uint16)
+    labels_host = pinned_like((N, H, W), np.uint16)
+    depth_host.view(torch.int16).copy_(torch.from_numpy(depth.view(np.int16)))
+    for _ in range(2):                                               # the second run reuses buffers the first one left busy
+        labels_host.view(torch.int16).fill_(-1)
+        hb.run(depth_host, labels_host, prefill=4321)
+        torch.cuda.synchronize()
+        got = labels_host.view(torch.int16).numpy().view(np.uint16)
+        assert np.array_equal(got, want)
+    assert hb.bytes_h2d == depth.nbytes and hb.bytes_d2h == want.nbytes
