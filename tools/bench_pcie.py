@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Host <-> device copy ceiling of a box, with NO kernels: every rank moves the e2e leg's traffic (pinned uint16 frames in,
-pinned uint16 label maps out) (a) as the same 64-frame chunks on the same three streams HostBatchEvaluator uses and (b) as one
+pinned uint16 label maps out) (a) as the same chunk schedule on the same three streams HostBatchEvaluator uses and (b) as one
 large H2D and one large D2H issued together.  Run it alone or under torchrun at N = 1, 2, 4, 8:
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 tools/bench_pcie.py
 Prints one JSON line on rank 0: aggregate GB/s (both directions summed over all ranks, max-over-ranks time)."""
@@ -35,7 +35,7 @@ def main():
     n = f1 - f0
     depth_host, labels_host = pinned_like((n, H, W), np.uint16), pinned_like((n, H, W), np.uint16)
     depth_host.view(torch.int16).zero_()
-    hb = HostBatchEvaluator(None, None, (H, W), chunk_frames=min(64, n))
+    hb = HostBatchEvaluator(None, None, (H, W), chunk_frames=min(128, n))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def timed(fn):
