@@ -73,6 +73,24 @@ static int rdf_pack(rdf_forest* f, const float* canon_dev, cudaStream_t stream) 
     RDF_CUDA(cudaStreamSynchronize(stream));
     f->has_exact_nodes = props & 1;
     f->has_early_leaves = (props >> 1) & 1;
+    // host copy of the upper levels for the eval kernel's launch parameters (rdf_eval.cu: rdf_eval_launch)
+    f->top_levels = 0;
+    if (f->T <= 8) {                                                  // RDF_FAST_MAX_TREES: the per-pixel kernels' limit
+        const int KT = rdf_top_levels(f->T);
+        const int KS = f->D < KT ? f->D : KT, M = (1 << KS) - 1, first_last = (1 << (KS - 1)) - 1;
+        delete[] f->top_host;
+        f->top_host = new rdf_node_hdr[(size_t)f->T * M];
+        for (int t = 0; t < f->T; t++) {
+            RDF_CUDA(cudaMemcpy(f->top_host + t * M, f->hdr + (size_t)t * f->rows_per_tree, sizeof(rdf_node_hdr) * M, cudaMemcpyDeviceToHost));
+            const int shift = t * M - (int)(t * f->rows_per_tree);
+            for (int row = 0; row < first_last; row++) {
+                rdf_node_hdr& h = f->top_host[t * M + row];
+                if (h.left >= 0) h.left += shift;
+                if (h.right >= 0) h.right += shift;
+            }
+        }
+        f->top_levels = KS;
+    }
     return RDF_OK;
 }
 
@@ -107,6 +125,8 @@ extern "C" int rdf_forest_create(const float* canon_dev, int num_trees, int max_
     f->rows_per_tree = f->layout == RDF_LAYOUT_BLOCKS ? rdf_blocks_rows_per_tree(max_depth) : f->nodes_per_tree;
     f->hdr = nullptr;
     f->pdf = nullptr;
+    f->top_host = nullptr;
+    f->top_levels = 0;
     const size_t n = (size_t)f->rows_per_tree * f->T;
     const size_t hdr_bytes = n * sizeof(rdf_node_hdr), pdf_bytes = n * 2 * f->CP * sizeof(float);
     f->packed_bytes = hdr_bytes + pdf_bytes;
@@ -143,6 +163,7 @@ extern "C" int rdf_forest_destroy(rdf_forest_t* forest) {
     if (forest->hdr) cudaFree(forest->hdr);
     if (forest->pdf) cudaFree(forest->pdf);
     if (forest->exact_flag_dev) cudaFree(forest->exact_flag_dev);
+    delete[] forest->top_host;
     delete forest;
     return RDF_OK;
 }

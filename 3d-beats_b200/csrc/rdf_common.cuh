@@ -110,7 +110,21 @@ struct rdf_forest {
     int has_exact_nodes;          // some node carries RDF_FLAG_EXACT_DIV (set by the last pack; read back at create / update)
     int has_early_leaves;         // some walk can end above level D-1 (0: every tree is complete, all walks take exactly D steps)
     int* exact_flag_dev;          // device word the pack kernel ORs into
+    rdf_node_hdr* top_host;       // host copy of levels 0 .. top_levels-1 of every tree, [T][2^top_levels - 1], child ids rewritten to
+                                  // this array's indexing (rdf_pack); travels to the eval kernel as a kernel parameter
+    int top_levels;               // min(D, rdf_top_levels(T)); 0: none (more than RDF_FAST_MAX_TREES trees)
 };
+
+// Upper levels that travel as kernel parameters (constant bank): as many as RDF_EVAL_TOP_LEVELS allows and as fit the 32 764-byte
+// parameter space next to the other launch parameters.
+#ifndef RDF_EVAL_TOP_LEVELS
+#define RDF_EVAL_TOP_LEVELS 5
+#endif
+__host__ __device__ constexpr int rdf_top_levels(int T) {
+    int L = RDF_EVAL_TOP_LEVELS;
+    while (L > 0 && (size_t)T * ((1u << L) - 1u) * 32u > 30000u) L--;
+    return L;
+}
 
 // ---- reference arithmetic --------------------------------------------------------------------------------
 // compute_feature (src/cuda/decision_tree_common.hpp:8-28): offsets are floor_rd( (scale*u) / float(d) ) with one fp32

@@ -15,37 +15,45 @@ struct rdf_eval_params {
     int tiles_x;
     int filter_class;
     int image0;
-    int smem_levels;          // upper tree levels staged in shared memory (0 .. RDF_EVAL_SMEM_LEVELS)
+    int top_levels;           // upper tree levels that travel in `top` below (min(D, rdf_top_levels(T)))
     int tree_mode;            // evaluate_image_using_tree semantics: no write when the walk reaches no leaf (tree_eval.cu:174-210)
     float scale;
 };
 
-// 5 levels (31 headers = 1 KB per tree): with the lean loop instances 5 is ahead of 6 (cfg3 7.60 vs 7.52 Gpx/s, noise 3.10 vs 3.02) - the
-// last staged level costs every 256-pixel CTA twice the staging loads and shared memory that L1 would otherwise have; 7 is 2 % behind 6
-#ifndef RDF_EVAL_SMEM_LEVELS
-#define RDF_EVAL_SMEM_LEVELS 5
-#endif
-static_assert(RDF_EVAL_SMEM_LEVELS <= RDF_PACK_TOP_LEVELS, "the staged levels must lie in the heap-ordered top of a packed tree");
+// The upper levels of every tree travel with the launch, as KERNEL PARAMETERS: the headers sit in the constant bank and a walk
+// reads them with register-indexed constant loads (`LDC.64 R, c[0x0][R+imm]`), which do not pass through the L1 data pipe - the
+// unit this kernel saturates (97 % of peak, profiles/r02_ncu_eval.md).  Against the previous form (every 256-pixel CTA staged the
+// same levels into shared memory and read them with broadcast LDS.128 pairs) this removes 9 % of the kernel's L1 wavefronts, the
+// 4 KB of staging loads per CTA, the shared memory and the block barrier: cfg3 7.60 -> 8.22 Gpx/s, cfg3 noise 3.10 -> 3.34, cfg5
+// 2.53 -> 2.63 (profiles/r02_eval_const_top.md).  A constant load serves one address per pass, so lanes on different nodes are
+// serialised: 5 levels (<= 16 nodes per tree on the last one) is where divergent frames stop gaining - with 6 / 7 levels the smooth
+// workload reaches 8.43 / 8.63 Gpx/s but dense-noise frames fall to 2.05 / 0.80, so RDF_EVAL_TOP_LEVELS stays 5.
+// The launch parameters may be as large as 32 764 bytes (CUDA 12.1+, sm_70+); rdf_top_levels(T) keeps T trees below 30 000.
+static_assert(RDF_EVAL_TOP_LEVELS <= RDF_PACK_TOP_LEVELS, "the levels that travel with the launch must lie in the heap-ordered top of a packed tree");
+template <int T>
+struct __align__(32) rdf_eval_launch {
+    rdf_eval_params p;
+    rdf_node_hdr top[T * ((1 << rdf_top_levels(T)) - 1)];     // [t][row], child ids of the levels above the last in this indexing
+};
+template <int T>
+struct rdf_top_ref {                                          // how the walk sees the array: a reference, so loads stay in param space
+    const rdf_node_hdr (&top)[T * ((1 << rdf_top_levels(T)) - 1)];
+};
 
 // CTAs per SM the register allocation aims for: 4 (<= 64 registers) up to 5 interleaved trees; the state of 6..8 trees does not
 // fit 64 registers (it spilled 64-128 B of stack and cfg5 lost a third of its speed), so those get 3 / 2 CTAs per SM.
-// Measured on cfg3 (T=4): 5 or 6 CTAs per SM with 48 / 40 registers spill and are 18 % / 30 % slower.
+// 5 / 6 CTAs per SM (the lean instances need only 38-48 registers) were measured again with the lean loops: no gain.
 #define RDF_EVAL_MIN_BLOCKS(T) RDF_EVAL_MIN_BLOCKS_T(T)
 // EXACT: 0 = no node of the forest needs the exact divide (the common case: the loop has no flag test and no __fdiv_rn path),
 // 1 = per-node flags, 2 = always exact (scale outside the fast domain), 3 = as 0 and every tree is complete (no early leaves: no
 // "walk ended" handling in the loop either)
 template <int T, int WARP_W, bool SCALE1, int EXACT>
-__global__ void __launch_bounds__(256, RDF_EVAL_MIN_BLOCKS(T)) rdf_eval_packed_kernel(const rdf_eval_params p) {
+__global__ void __launch_bounds__(256, RDF_EVAL_MIN_BLOCKS(T)) rdf_eval_packed_kernel(const __grid_constant__ rdf_eval_launch<T> q) {
+    const rdf_eval_params& p = q.p;
     constexpr bool FORCE_EXACT = EXACT == 2, NEVER_EXACT = EXACT == 0 || EXACT == 3, COMPLETE = EXACT == 3;
     constexpr int WARP_H = 32 / WARP_W;
     constexpr int WARPS_X = 32 / WARP_W;
-    // levels 0 .. KS-1 of all T trees in shared memory (1 KB per tree at KS = 5), staged before any thread leaves
-    __shared__ __align__(32) rdf_node_hdr hdr_s[T * ((1 << RDF_EVAL_SMEM_LEVELS) - 1)];
-    const int KS = min(p.fv.D, p.smem_levels);
-    if (KS > 0) {
-        rdf_stage_upper_levels(p.fv, KS, hdr_s);
-        __syncthreads();
-    }
+    const rdf_top_ref<T> top{q.top};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile_y = blockIdx.x / p.tiles_x, tile_x = blockIdx.x - tile_y * p.tiles_x;
     const int x = tile_x * 32 + (warp % WARPS_X) * WARP_W + (lane % WARP_W);
@@ -60,7 +68,7 @@ __global__ void __launch_bounds__(256, RDF_EVAL_MIN_BLOCKS(T)) rdf_eval_packed_k
     const unsigned d = __ldg(img + (size_t)Y * p.W + X);
     if (d == 0u || d == RDF_NO_PIXEL) return;                                            // tree_eval.cu:88-89
     int state[T];
-    rdf_walk<T, SCALE1, FORCE_EXACT, NEVER_EXACT, COMPLETE>(p.fv, img, p.W, p.H, X, Y, d, p.scale, state, hdr_s, KS);
+    rdf_walk<T, SCALE1, FORCE_EXACT, NEVER_EXACT, COMPLETE, rdf_top_ref<T>>(p.fv, img, p.W, p.H, X, Y, d, p.scale, state, top, p.top_levels);
     if (T == 1 && p.tree_mode && state[0] == RDF_NO_LEAF) return;
     const int lab = rdf_vote<T>(p.fv, state, p.probs ? p.probs + li * p.fv.C : nullptr);
     p.labels[li] = (uint16_t)lab;
@@ -156,28 +164,31 @@ static int rdf_warp_w() {
 }
 
 template <int T, int WARP_W>
-static void rdf_launch_packed_tw(const rdf_eval_params& p, int props, dim3 grid, cudaStream_t stream) {
-    const bool has_exact_nodes = (props & 1) != 0, complete = (props & 2) == 0;
+static void rdf_launch_packed_tw(const rdf_eval_params& p, const rdf_forest* forest, dim3 grid, cudaStream_t stream) {
+    const bool has_exact_nodes = forest->has_exact_nodes != 0, complete = forest->has_early_leaves == 0;
+    rdf_eval_launch<T> q;
+    q.p = p;
+    memcpy(q.top, forest->top_host, sizeof(rdf_node_hdr) * T * ((1u << forest->top_levels) - 1u));
     // fast path (reciprocal divide + magic-number floor): |scale| in [2^-30, 1] and coordinates below 2^16
     if (!rdf_scale_fastfloor_ok(p.scale) || p.W > 65535 || p.H > 65535)
-        rdf_eval_packed_kernel<T, WARP_W, false, 2><<<grid, 256, 0, stream>>>(p);
+        rdf_eval_packed_kernel<T, WARP_W, false, 2><<<grid, 256, 0, stream>>>(q);
     else if (p.scale == 1.f) {
-        if (has_exact_nodes) rdf_eval_packed_kernel<T, WARP_W, true, 1><<<grid, 256, 0, stream>>>(p);
-        else if (complete) rdf_eval_packed_kernel<T, WARP_W, true, 3><<<grid, 256, 0, stream>>>(p);
-        else rdf_eval_packed_kernel<T, WARP_W, true, 0><<<grid, 256, 0, stream>>>(p);
+        if (has_exact_nodes) rdf_eval_packed_kernel<T, WARP_W, true, 1><<<grid, 256, 0, stream>>>(q);
+        else if (complete) rdf_eval_packed_kernel<T, WARP_W, true, 3><<<grid, 256, 0, stream>>>(q);
+        else rdf_eval_packed_kernel<T, WARP_W, true, 0><<<grid, 256, 0, stream>>>(q);
     } else {
-        if (has_exact_nodes) rdf_eval_packed_kernel<T, WARP_W, false, 1><<<grid, 256, 0, stream>>>(p);
-        else if (complete) rdf_eval_packed_kernel<T, WARP_W, false, 3><<<grid, 256, 0, stream>>>(p);
-        else rdf_eval_packed_kernel<T, WARP_W, false, 0><<<grid, 256, 0, stream>>>(p);
+        if (has_exact_nodes) rdf_eval_packed_kernel<T, WARP_W, false, 1><<<grid, 256, 0, stream>>>(q);
+        else if (complete) rdf_eval_packed_kernel<T, WARP_W, false, 3><<<grid, 256, 0, stream>>>(q);
+        else rdf_eval_packed_kernel<T, WARP_W, false, 0><<<grid, 256, 0, stream>>>(q);
     }
 }
 
 template <int T>
-static void rdf_launch_packed_t(const rdf_eval_params& p, int props, dim3 grid, cudaStream_t stream) {
+static void rdf_launch_packed_t(const rdf_eval_params& p, const rdf_forest* forest, dim3 grid, cudaStream_t stream) {
     switch (rdf_warp_w()) {
-        case 32: rdf_launch_packed_tw<T, 32>(p, props, grid, stream); break;
-        case 16: rdf_launch_packed_tw<T, 16>(p, props, grid, stream); break;
-        default: rdf_launch_packed_tw<T, 8>(p, props, grid, stream); break;
+        case 32: rdf_launch_packed_tw<T, 32>(p, forest, grid, stream); break;
+        case 16: rdf_launch_packed_tw<T, 16>(p, forest, grid, stream); break;
+        default: rdf_launch_packed_tw<T, 8>(p, forest, grid, stream); break;
     }
 }
 
@@ -211,28 +222,20 @@ static int rdf_eval_packed(const rdf_forest_t* forest, const uint16_t* depth_dev
     p.filter_class = filter_class;
     p.scale = scale;
     p.tree_mode = tree_mode;
-    {
-        static int lv = -1;                                         // RDF_SMEM_LEVELS overrides (experiments)
-        if (lv < 0) {
-            const char* e = RDF_GETENV_ONCE("RDF_SMEM_LEVELS");
-            lv = e ? atoi(e) : RDF_EVAL_SMEM_LEVELS;
-            if (lv < 0 || lv > RDF_EVAL_SMEM_LEVELS) lv = RDF_EVAL_SMEM_LEVELS;
-        }
-        p.smem_levels = lv;
-    }
+    p.top_levels = forest->top_levels;
     for (int n0 = 0; n0 < num_images; n0 += 65535) {
         const int nb = num_images - n0 < 65535 ? num_images - n0 : 65535;
         p.image0 = n0;
         dim3 grid((unsigned)(p.tiles_x * tiles_y), (unsigned)nb);
         switch (forest->T) {
-            case 1: rdf_launch_packed_t<1>(p, (forest->has_exact_nodes ? 1 : 0) | (forest->has_early_leaves ? 2 : 0), grid, st); break;
-            case 2: rdf_launch_packed_t<2>(p, (forest->has_exact_nodes ? 1 : 0) | (forest->has_early_leaves ? 2 : 0), grid, st); break;
-            case 3: rdf_launch_packed_t<3>(p, (forest->has_exact_nodes ? 1 : 0) | (forest->has_early_leaves ? 2 : 0), grid, st); break;
-            case 4: rdf_launch_packed_t<4>(p, (forest->has_exact_nodes ? 1 : 0) | (forest->has_early_leaves ? 2 : 0), grid, st); break;
-            case 5: rdf_launch_packed_t<5>(p, (forest->has_exact_nodes ? 1 : 0) | (forest->has_early_leaves ? 2 : 0), grid, st); break;
-            case 6: rdf_launch_packed_t<6>(p, (forest->has_exact_nodes ? 1 : 0) | (forest->has_early_leaves ? 2 : 0), grid, st); break;
-            case 7: rdf_launch_packed_t<7>(p, (forest->has_exact_nodes ? 1 : 0) | (forest->has_early_leaves ? 2 : 0), grid, st); break;
-            default: rdf_launch_packed_t<8>(p, (forest->has_exact_nodes ? 1 : 0) | (forest->has_early_leaves ? 2 : 0), grid, st); break;
+            case 1: rdf_launch_packed_t<1>(p, forest, grid, st); break;
+            case 2: rdf_launch_packed_t<2>(p, forest, grid, st); break;
+            case 3: rdf_launch_packed_t<3>(p, forest, grid, st); break;
+            case 4: rdf_launch_packed_t<4>(p, forest, grid, st); break;
+            case 5: rdf_launch_packed_t<5>(p, forest, grid, st); break;
+            case 6: rdf_launch_packed_t<6>(p, forest, grid, st); break;
+            case 7: rdf_launch_packed_t<7>(p, forest, grid, st); break;
+            default: rdf_launch_packed_t<8>(p, forest, grid, st); break;
         }
         RDF_LAUNCH_CHECK("rdf_eval_packed_kernel");
     }

@@ -10,6 +10,7 @@
 // 32-bit image indices (no 64-bit address arithmetic per probe).
 #pragma once
 #include "rdf_common.cuh"
+#include <type_traits>
 
 #define RDF_FAST_MAX_TREES 8
 
@@ -55,8 +56,8 @@ __device__ __forceinline__ rdf_hdr_regs rdf_load_hdr(const rdf_node_hdr* __restr
 // domain, so the loop carries neither the flag test nor the __fdiv_rn path.
 // COMPLETE: every tree of the forest is a complete tree (no leaf above level D-1, known on the host after packing): no walk ends
 // early, so the loop needs neither the "all walks ended" exit nor the per-tree "ended" clamp and select.
-template <int T, bool SCALE1, bool FORCE_EXACT, bool SMEM, bool NEVER_EXACT = false, bool COMPLETE = false>
-__device__ __forceinline__ void rdf_walk_levels(const rdf_node_hdr* __restrict__ hdr, int tree_stride, int j0, int j1,
+template <int T, bool SCALE1, bool FORCE_EXACT, bool SMEM, bool NEVER_EXACT = false, bool COMPLETE = false, typename HDR = const rdf_node_hdr*>
+__device__ __forceinline__ void rdf_walk_levels(HDR hdr, int tree_stride, int j0, int j1,
                                                 const uint16_t* __restrict__ img, int W, int H, int X, int Y, float df, float rcp,
                                                 float xm, float ym, float scale, int (&state)[T]) {
     for (int j = j0; j < j1; j++) {
@@ -72,10 +73,15 @@ __device__ __forceinline__ void rdf_walk_levels(const rdf_node_hdr* __restrict__
         for (int t = 0; t < T; t++) {
             // ended walks re-read their tree's root (cached): harmless, keeps the loop branch-free
             const int node = COMPLETE ? state[t] : max(state[t], t * tree_stride);
-            if (SMEM) {
-                const float4* sp = reinterpret_cast<const float4*>(hdr + node);
-                h[t].a = sp[0];
-                h[t].b = *reinterpret_cast<const int4*>(sp + 1);
+            if constexpr (SMEM) {
+                if constexpr (std::is_pointer<HDR>::value) {
+                    const float4* sp = reinterpret_cast<const float4*>(hdr + node);
+                    h[t].a = sp[0];
+                    h[t].b = *reinterpret_cast<const int4*>(sp + 1);
+                } else {                                             // kernel-parameter array: constant-bank loads with a register index
+                    h[t].a = hdr.top[node].a;
+                    h[t].b = make_int4(hdr.top[node].ithresh, hdr.top[node].left, hdr.top[node].right, hdr.top[node].flags);
+                }
             } else {
                 h[t] = rdf_load_hdr(hdr, node);
             }
@@ -133,9 +139,9 @@ __device__ __forceinline__ void rdf_stage_upper_levels(const rdf_forest_view& fv
 // SCALE1: scale == 1.0f, so scale*u == u exactly and the multiplies are dropped.  FORCE_EXACT: always use __fdiv_rn
 // (scale outside the fast domain); otherwise nodes flagged RDF_FLAG_EXACT_DIV take the exact path per level.
 // hdr_s / KS: optional shared-memory copy of levels 0 .. KS-1 (rdf_stage_upper_levels); KS = 0: everything from global memory.
-template <int T, bool SCALE1, bool FORCE_EXACT, bool NEVER_EXACT = false, bool COMPLETE = false>
+template <int T, bool SCALE1, bool FORCE_EXACT, bool NEVER_EXACT = false, bool COMPLETE = false, typename TOP = const rdf_node_hdr*>
 __device__ __forceinline__ void rdf_walk(const rdf_forest_view& fv, const uint16_t* __restrict__ img, int W, int H, int X,
-                                         int Y, unsigned d, float scale, int (&state)[T], const rdf_node_hdr* hdr_s = nullptr,
+                                         int Y, unsigned d, float scale, int (&state)[T], TOP hdr_s = nullptr,
                                          int KS = 0) {
     const float df = (float)d;
     const float rcp = __frcp_rn(df);                                 // RN(1/d), once per pixel
@@ -144,7 +150,7 @@ __device__ __forceinline__ void rdf_walk(const rdf_forest_view& fv, const uint16
         const int M = (1 << KS) - 1;
 #pragma unroll
         for (int t = 0; t < T; t++) state[t] = t * M;
-        rdf_walk_levels<T, SCALE1, FORCE_EXACT, true, NEVER_EXACT, COMPLETE>(hdr_s, M, 0, KS, img, W, H, X, Y, df, rcp, xm, ym, scale, state);
+        rdf_walk_levels<T, SCALE1, FORCE_EXACT, true, NEVER_EXACT, COMPLETE, TOP>(hdr_s, M, 0, KS, img, W, H, X, Y, df, rcp, xm, ym, scale, state);
     } else {
 #pragma unroll
         for (int t = 0; t < T; t++) state[t] = t * fv.nodes_per_tree;
