@@ -59,8 +59,9 @@ RDF_API const char* rdf_last_error(void);
  * src/cuda/tree_eval.cu:47, node addressing src/cuda/cu_utils.hpp:32-39).  The handle owns a packed shadow
  * (32-byte node headers + 16-byte aligned leaf pdf rows); the caller keeps ownership of canon_dev.
  * rdf_forest_update re-packs after the caller mutated canon_dev (e.g. forest_cu.set(...), src/train_model.py:126).
- * Create and update synchronise `stream` once (the pack reports back whether any node needs the exact-divide path); they are
- * set-up calls, not part of the per-frame path. */
+ * Create and update synchronise `stream` once (the pack reports back whether any node needs the exact-divide path, and the handle
+ * keeps a host copy of the upper five levels of every tree, at most 8 KB, which rdf_eval_forest passes to its kernel as launch
+ * parameters); they are set-up calls, not part of the per-frame path. */
 RDF_API int rdf_forest_create(const float* canon_dev, int num_trees, int max_depth, int num_classes, void* stream,
                       rdf_forest_t** out);
 RDF_API int rdf_forest_update(rdf_forest_t* forest, const float* canon_dev, void* stream);
