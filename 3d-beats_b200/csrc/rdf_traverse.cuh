@@ -138,7 +138,7 @@ __device__ __forceinline__ void rdf_stage_upper_levels(const rdf_forest_view& fv
 // off level D-1 with a "continue" flag (adds nothing, src/cuda/tree_eval.cu:95-128).
 // SCALE1: scale == 1.0f, so scale*u == u exactly and the multiplies are dropped.  FORCE_EXACT: always use __fdiv_rn
 // (scale outside the fast domain); otherwise nodes flagged RDF_FLAG_EXACT_DIV take the exact path per level.
-// hdr_s / KS: optional shared-memory copy of levels 0 .. KS-1 (rdf_stage_upper_levels); KS = 0: everything from global memory.
+// hdr_s / KS: optional copy of levels 0 .. KS-1, either a shared-memory pointer (rdf_stage_upper_levels) or a reference wrapper around a kernel-parameter array (rdf_eval.cu: rdf_top_ref, constant-bank loads); KS = 0: everything from global memory.
 template <int T, bool SCALE1, bool FORCE_EXACT, bool NEVER_EXACT = false, bool COMPLETE = false, typename TOP = const rdf_node_hdr*>
 __device__ __forceinline__ void rdf_walk(const rdf_forest_view& fv, const uint16_t* __restrict__ img, int W, int H, int X,
                                          int Y, unsigned d, float scale, int (&state)[T], TOP hdr_s = nullptr,
