@@ -130,3 +130,23 @@ def test_frame_entry_points_validate_arguments_without_gpu():
     assert b'num_fingertips' in lib.rdf_last_error()
     assert lib.rdf_flip_x(p16, 8, 8, p16, None) == -1 and lib.rdf_grow_groups(p16, 8, 8, p16, None) == -1       # aliased
     assert lib.rdf_mean_shift_batch(None, 2, 8, 8, 2, None, 1, None, None, 0, None) == -1
+
+
+def test_eval_kernel_reads_its_upper_levels_from_the_constant_bank():
+    """SASS of the shipped forest-eval instance (T = 4, complete trees, scale 1): the upper levels are register-indexed constant
+    loads from the launch parameters, the levels below are 256-bit global loads, and the kernel neither touches shared memory nor
+    meets at a barrier (csrc/rdf_eval.cu: rdf_eval_launch; profiles/r02_eval_const_top.md)."""
+    import re
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(cuobjdump):
+        pytest.skip('cuobjdump not available')
+    sym = '_Z22rdf_eval_packed_kernelILi4ELi16ELb1ELi3EEv15rdf_eval_launchIXT_EE'
+    from rdf_b200 import _capi
+    out = subprocess.run([cuobjdump, '-sass', '-fun', sym, _capi.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    assert 'sm_100a' in out and 'Function : ' + sym in out, out[:500]
+    assert len(re.findall(r'LDC\.64 R\d+, c\[0x0\]\[R\d+\+', out)) >= 8          # 3 x LDC.64 + 1 x LDC per header, 4 trees
+    assert len(re.findall(r'LDG\.E\.ENL2\.256', out)) >= 4                       # one 256-bit header load per tree below
+    assert 'FFMA2' in out and 'FADD2.RM' in out                                  # packed fp32 divide + magic-number floor
+    assert not re.search(r'\bLDS\b|\bSTS\b|BAR\.SYNC', out)                      # no staging, no barrier
