@@ -813,7 +813,7 @@ def main():
     binding, dram_bpp = binding_from_profile(args.workload)
     roofline = {'bound': 'hbm', 'achieved': r(achieved, 1), 'peak': peak, 'unit': 'GB/s', 'frac': r(achieved / peak, 4),
                 'traffic': (dram_bpp * px_per_launch if dram_bpp else None),
-                'kernel': f'rdf_eval_packed_kernel<{T},*,true,false>', 'algorithmic_bytes_per_pixel': b_alg, 'peak_source': peak_src,
+                'kernel': f'rdf_eval_packed_kernel<{T},16,true,*>(rdf_eval_launch<{T}>)', 'algorithmic_bytes_per_pixel': b_alg, 'peak_source': peak_src,
                 'compulsory_hbm_frac': r(4.0 * px_per_launch / (kernel_ms * 1e-3) / 1e9 / peak, 5),
                 'node_steps_per_s': T * D * px_per_launch / (kernel_ms * 1e-3), 'binding': binding,
                 'note': 'logical-traffic roofline (SURVEY 8d): exceeds 1.0 because the forest is cache-resident; `binding` is the '
